@@ -1,0 +1,189 @@
+/*
+ * mixemt_b200.h -- C-ABI of the B200-native numeric core for svohr/mixemt.
+ *
+ * The reference has no FFI of its own (it is pure Python); the drop-in
+ * boundary is two module attributes:
+ *
+ *   mixemt.preprocess.build_em_matrix(refseq, phylo, reads, haplogroups, args)
+ *       reference: mixemt/preprocess.py:177-198
+ *   mixemt.em.run_em(read_hap_mat, weights, args)
+ *       reference: mixemt/em.py:94-165
+ *   (and, for test parity) mixemt.em.em_step(...)   mixemt/em.py:57-91
+ *
+ * The Python host layer (mixemt_b200/preprocess.py, mixemt_b200/em.py) keeps
+ * those signatures and binds the entry points below with ctypes.  Every entry
+ * point is extern "C", takes plain pointers and sizes, returns an int status
+ * (MXB_OK == 0) and never throws; mxb_last_error() returns the message of the
+ * last failing call on the calling thread.  Host buffers are caller-owned;
+ * opaque handles are library-owned and released by the matching *_destroy.
+ *
+ * There is no CPU fallback: every compute entry point needs a CUDA device and
+ * fails with MXB_ERR_CUDA when there is none.
+ */
+#ifndef MIXEMT_B200_H
+#define MIXEMT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXB_ABI_VERSION 1
+
+enum {
+    MXB_OK = 0,
+    MXB_ERR_CUDA = 1,      /* CUDA runtime / NCCL failure (message has detail)   */
+    MXB_ERR_ARG = 2,       /* bad argument (NULL, negative size, bad handle)     */
+    MXB_ERR_VALUE = 3,     /* malformed signature -> Python ValueError           */
+    MXB_ERR_KEY = 4,       /* unknown variant position -> Python KeyError        */
+    MXB_ERR_NOMEM = 5,     /* host or device allocation failed                   */
+    MXB_ERR_RANGE = 6      /* EM left the representable range (non-finite sums)  */
+};
+
+typedef struct mxb_ctx mxb_ctx;       /* one device + stream + scratch + (optional) NCCL comm */
+typedef struct mxb_phylo mxb_phylo;   /* packed haplotype bitsets + per-position log tables   */
+typedef struct mxb_matrix mxb_matrix; /* device-resident row-major fp64 N x H matrix          */
+typedef struct mxb_em mxb_em;         /* EM session over one matrix (row shard)               */
+
+/* ---- library -------------------------------------------------------------- */
+int mxb_abi_version(void);
+const char *mxb_last_error(void);
+/* Number of visible CUDA devices (0 when there is no GPU / no driver). */
+int mxb_device_count(void);
+
+/* ---- context -------------------------------------------------------------- */
+int mxb_ctx_create(int device, mxb_ctx **out);
+int mxb_ctx_destroy(mxb_ctx *ctx);
+/* Launch on an externally owned cudaStream_t (e.g. torch's current stream). */
+int mxb_ctx_set_stream(mxb_ctx *ctx, void *cuda_stream);
+int mxb_ctx_synchronize(mxb_ctx *ctx);
+/* Kernel launches issued through this context since creation (bench evidence). */
+int64_t mxb_ctx_launch_count(const mxb_ctx *ctx);
+/* Multi-GPU: one process per GPU.  Rank 0 calls mxb_comm_unique_id, the host
+ * layer broadcasts the 128 bytes (torch.distributed), every rank calls
+ * mxb_comm_init.  After that mxb_em_* sessions created with sharded != 0
+ * all-reduce the H column sums once per EM iteration (ncclAllReduce, fp64). */
+int mxb_comm_unique_id(void *id128);
+int mxb_comm_init(mxb_ctx *ctx, const void *id128, int rank, int world);
+int mxb_comm_destroy(mxb_ctx *ctx);
+/* In-place sum / max all-reduce of a host fp64 vector across the comm
+ * (restart fan-out: sum of log-proportions, reference em.py:155). */
+int mxb_comm_allreduce_host(mxb_ctx *ctx, double *buf, int64_t n, int op_is_max);
+
+/* ---- signatures -> CSR (host only; replaces preprocess.pos_obs_from_sig,
+ *      mixemt/preprocess.py:151-160, 26 us/row in Python) -------------------- */
+/* Count observations (comma-separated fields) of every signature.
+ * buf: concatenated UTF-8 signatures; offsets[n_rows+1] delimit them.
+ * row_ptr[n_rows+1] receives the exclusive prefix sum. */
+int mxb_sig_count(const char *buf, const int64_t *offsets, int64_t n_rows,
+                  int64_t *row_ptr);
+/* Parse "pos:base,pos:base,...".  pos2idx[pos] maps a 0-based reference
+ * position to its index in the packed position table (-1: not a variant
+ * position).  sym2code[256] maps a single-byte base to its symbol code
+ * (255: never matches).  On MXB_ERR_VALUE / MXB_ERR_KEY *bad_row is the first
+ * offending row, in the order the reference would have hit it. */
+int mxb_sig_parse(const char *buf, const int64_t *offsets, int64_t n_rows,
+                  const int32_t *pos2idx, int64_t pos2idx_len,
+                  const uint8_t *sym2code, const int64_t *row_ptr,
+                  int32_t *pos_idx, uint8_t *base_code,
+                  int64_t *bad_row, int64_t *bad_pos);
+
+/* ---- haplotype tables (replaces HapVarBaseMatrix, preprocess.py:23-96) ----- */
+/* n_sym symbols (codes 0..n_sym-1).  hit[p] = log(1-mut_prob), miss[p] =
+ * log(mut_prob/3), computed by the host with math.log so they are
+ * bit-identical to the reference's (preprocess.py:75-95).  ref_code[p] is the
+ * code of refseq[pos]; markers are CSR per haplotype column
+ * (marker_ptr[n_hap+1], marker_pos_idx, marker_code). */
+int mxb_phylo_pack(mxb_ctx *ctx, int32_t n_pos, int32_t n_hap, int32_t n_sym,
+                   const double *hit, const double *miss,
+                   const uint8_t *ref_code, const int64_t *marker_ptr,
+                   const int32_t *marker_pos_idx, const uint8_t *marker_code,
+                   mxb_phylo **out);
+int mxb_phylo_destroy(mxb_phylo *phylo);
+
+/* ---- kernel 1: matrix build (replaces build_em_matrix, preprocess.py:177) --- */
+/* CSR rows -> fp64 N x H log-likelihood matrix.  out_host (nullable) receives
+ * the matrix, match_host (nullable) the int32 per-cell match counts
+ * (mismatches = K_i - matches), out_dev (nullable) keeps the matrix resident.
+ * elapsed_ms (nullable) = device time of the build kernel alone. */
+int mxb_build_matrix(mxb_ctx *ctx, const mxb_phylo *phylo, int64_t n_rows,
+                     const int64_t *row_ptr, const int32_t *pos_idx,
+                     const uint8_t *base_code, double *out_host,
+                     int32_t *match_host, mxb_matrix **out_dev,
+                     float *elapsed_ms);
+
+/* ---- device matrices ------------------------------------------------------- */
+int mxb_matrix_alloc(mxb_ctx *ctx, int64_t n_rows, int64_t n_cols, mxb_matrix **out);
+int mxb_matrix_upload(mxb_ctx *ctx, const double *host, int64_t n_rows,
+                      int64_t n_cols, mxb_matrix **out);
+int mxb_matrix_download(mxb_ctx *ctx, const mxb_matrix *m, double *host);
+int mxb_matrix_shape(const mxb_matrix *m, int64_t *n_rows, int64_t *n_cols);
+/* Raw device pointer (for torch interop / tests); row stride == n_cols. */
+void *mxb_matrix_data(const mxb_matrix *m);
+/* Row-wise argmax (first maximum, like numpy.argmax axis=1;
+ * consumers assemble.py:115, stats.py:39). */
+int mxb_matrix_argmax_rows(mxb_ctx *ctx, const mxb_matrix *m, int64_t *out_host);
+int mxb_matrix_destroy(mxb_matrix *m);
+
+/* ---- kernel 2: EM (replaces em_step / run_em, em.py:57-165) ---------------- */
+/* Session over one matrix shard.  weights[n_rows] (fp64).  sharded != 0 and a
+ * comm on ctx: rows are a shard, column sums are all-reduced every iteration. */
+int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
+                  int sharded, mxb_em **out);
+int mxb_em_destroy(mxb_em *em);
+/* Set the current log-proportions (em.py:123-124, host draws the Dirichlet). */
+int mxb_em_set_lnprops(mxb_em *em, const double *lnprops);
+/* Iterate em_step + converged (em.py:126-143) until sum|dprops| < tol or
+ * max_iter.  iters_out = iterations run; converged_out = 1/0. */
+int mxb_em_iterate(mxb_em *em, int64_t max_iter, double tol,
+                   int64_t *iters_out, int32_t *converged_out);
+/* Exactly n_iter iterations without convergence test or host sync (bench);
+ * elapsed_ms (nullable) = device time between first and last launch,
+ * pass_ms (nullable) = summed device time of the fused E/M pass kernel only
+ * (adds an event pair per iteration). */
+int mxb_em_iterate_fixed(mxb_em *em, int64_t n_iter, float *elapsed_ms,
+                         float *pass_ms);
+/* which: 0 = latest log-proportions (new_props), 1 = the ones before them. */
+int mxb_em_get_lnprops(mxb_em *em, int which, double *out);
+/* Read matrix from the *previous* log-proportions (em.py:130 / F5), written or
+ * folded into dst: mode 0 = store, 1 = dst = logaddexp(dst, Z) (em.py:156).
+ * sub_log != 0.0 subtracts it afterwards (em.py:161, log(n_multi)). */
+int mxb_em_read_mix(mxb_em *em, mxb_matrix *dst, int mode, double sub_log);
+
+/* One-call forms with host buffers (what a reference-side FFI would bind). */
+/* em.run_em (em.py:94-165): init_lnprops[n_multi*n_cols] drawn by the host;
+ * props_out[n_cols] linear scale; read_mix_out (nullable) N x H log scale;
+ * iters_out[n_multi], converged_out[n_multi] (nullable). */
+/* flags: MXB_EM_SHARDED = the rows are this rank's shard of a larger matrix
+ * (column sums all-reduced over the ctx comm every iteration);
+ * MXB_EM_RAW = skip the final averaging (em.py:158-163): props_out then holds
+ * the plain sum of the restarts' log-proportions and read_mix the plain
+ * logaddexp fold, for combining restart subsets run on different GPUs. */
+#define MXB_EM_SHARDED 1
+#define MXB_EM_RAW 2
+int mxb_run_em(mxb_ctx *ctx, const double *read_hap_mat, const double *weights,
+               int64_t n_rows, int64_t n_cols, const double *init_lnprops,
+               int32_t n_multi, int64_t max_iter, double tol, int32_t flags,
+               double *props_out, double *read_mix_out,
+               int64_t *iters_out, int32_t *converged_out);
+/* Same, matrix already on the device (kept there by mxb_build_matrix);
+ * read_mix_dev (nullable) keeps the result matrix resident as well. */
+int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
+                   const double *init_lnprops, int32_t n_multi,
+                   int64_t max_iter, double tol, int32_t flags,
+                   double *props_out, double *read_mix_out,
+                   mxb_matrix **read_mix_dev,
+                   int64_t *iters_out, int32_t *converged_out);
+/* Cross-rank fold of per-rank read matrices (restart fan-out):
+ * m = log(sum over ranks of exp(m)) - sub_log, in place, over the ctx comm. */
+int mxb_matrix_fold_ranks(mxb_ctx *ctx, mxb_matrix *m, double sub_log);
+/* em.em_step (em.py:57-91): one E+M step, read_mix_out written in full. */
+int mxb_em_step(mxb_ctx *ctx, const double *read_hap_mat, const double *weights,
+                const double *ln_props, int64_t n_rows, int64_t n_cols,
+                double *read_mix_out, double *new_props_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIXEMT_B200_H */

@@ -1,0 +1,346 @@
+// Context, device matrices, NCCL plumbing and error reporting of libmixemt_b200.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace mxb {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------------------
+// NCCL through dlopen: only the five calls the EM loop needs.
+// ---------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*fn_get_uid)(nccl_uid_t *);
+typedef int (*fn_comm_init_rank)(void **, int, nccl_uid_t, int);
+typedef int (*fn_comm_destroy)(void *);
+typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef const char *(*fn_error_string)(int);
+
+struct NcclApi {
+    void *handle = nullptr;
+    fn_get_uid get_uid = nullptr;
+    fn_comm_init_rank init_rank = nullptr;
+    fn_comm_destroy destroy = nullptr;
+    fn_allreduce allreduce = nullptr;
+    fn_error_string error_string = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.handle) return MXB_OK;
+    const char *names[] = {getenv("MXB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        set_error("cannot dlopen libnccl.so.2 (set MXB_NCCL_LIB): %s", dlerror());
+        return MXB_ERR_CUDA;
+    }
+    g_nccl.get_uid = (fn_get_uid)dlsym(h, "ncclGetUniqueId");
+    g_nccl.init_rank = (fn_comm_init_rank)dlsym(h, "ncclCommInitRank");
+    g_nccl.destroy = (fn_comm_destroy)dlsym(h, "ncclCommDestroy");
+    g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
+    g_nccl.error_string = (fn_error_string)dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.allreduce) {
+        set_error("libnccl is missing a required symbol");
+        dlclose(h);
+        return MXB_ERR_CUDA;
+    }
+    g_nccl.handle = h;
+    return MXB_OK;
+}
+
+#define MXB_NCCL(call)                                                        \
+    do {                                                                      \
+        int r__ = (call);                                                     \
+        if (r__ != 0) {                                                       \
+            set_error("%s:%d: %s -> nccl error %d (%s)", __FILE__, __LINE__,  \
+                      #call, r__,                                             \
+                      g_nccl.error_string ? g_nccl.error_string(r__) : "?");  \
+            return MXB_ERR_CUDA;                                              \
+        }                                                                     \
+    } while (0)
+
+// ncclDouble = 8, ncclSum = 0, ncclMax = 2 (nccl.h, stable since 2.0).
+int nccl_allreduce_f64(mxb_ctx *ctx, double *dev_buf, int64_t n, int op_is_max) {
+    if (!ctx->nccl_comm || ctx->world <= 1) return MXB_OK;
+    MXB_NCCL(g_nccl.allreduce(dev_buf, dev_buf, (size_t)n, 8, op_is_max ? 2 : 0,
+                              ctx->nccl_comm, ctx->stream));
+    return MXB_OK;
+}
+
+int nccl_allreduce_sum_f64(mxb_ctx *ctx, double *dev_buf, int64_t n) {
+    return nccl_allreduce_f64(ctx, dev_buf, n, 0);
+}
+
+// First maximum of every row (numpy.argmax semantics; NaN wins like numpy).
+__global__ void argmax_rows_kernel(const double *__restrict__ m, int64_t n_rows,
+                                   int64_t n_cols, int64_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        const double *row = m + r * n_cols;
+        double best = 0.0;
+        int64_t best_j = INT64_MAX;
+        bool best_nan = false;
+        for (int64_t j = lane; j < n_cols; j += 32) {
+            double v = row[j];
+            bool v_nan = (v != v);
+            if (best_j == INT64_MAX || (!best_nan && (v_nan || v > best))) {
+                best = v; best_j = j; best_nan = v_nan;
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, best, off);
+            long long oj = __shfl_xor_sync(0xffffffffu, (long long)best_j, off);
+            int on = __shfl_xor_sync(0xffffffffu, (int)best_nan, off);
+            if (oj == INT64_MAX) continue;
+            bool take;
+            if (best_j == INT64_MAX) take = true;
+            else if (best_nan || on) take = on && (!best_nan || oj < best_j);
+            else take = (ov > best) || (ov == best && oj < best_j);
+            if (take) { best = ov; best_j = oj; best_nan = on; }
+        }
+        if (lane == 0) out[r] = best_j == INT64_MAX ? 0 : best_j;
+    }
+}
+
+}  // namespace mxb
+
+using namespace mxb;
+
+extern "C" {
+
+int mxb_abi_version(void) { return MXB_ABI_VERSION; }
+
+const char *mxb_last_error(void) { return g_error; }
+
+int mxb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mxb_ctx_create(int device, mxb_ctx **out) {
+    MXB_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    MXB_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        set_error("mxb_ctx_create: device %d out of range (%d visible)", device, n);
+        return MXB_ERR_ARG;
+    }
+    MXB_CUDA(cudaSetDevice(device));
+    mxb_ctx *ctx = new (std::nothrow) mxb_ctx();
+    if (!ctx) { set_error("out of host memory"); return MXB_ERR_NOMEM; }
+    ctx->device = device;
+    cudaDeviceProp prop;
+    MXB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    MXB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    *out = ctx;
+    return MXB_OK;
+}
+
+int mxb_ctx_destroy(mxb_ctx *ctx) {
+    if (!ctx) return MXB_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->nccl_comm) mxb_comm_destroy(ctx);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MXB_OK;
+}
+
+int mxb_ctx_set_stream(mxb_ctx *ctx, void *cuda_stream) {
+    MXB_REQUIRE(ctx != nullptr, "ctx is NULL");
+    if (ctx->own_stream && ctx->stream) {
+        MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+        MXB_CUDA(cudaStreamDestroy(ctx->stream));
+    }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return MXB_OK;
+}
+
+int mxb_ctx_synchronize(mxb_ctx *ctx) {
+    MXB_REQUIRE(ctx != nullptr, "ctx is NULL");
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MXB_OK;
+}
+
+int64_t mxb_ctx_launch_count(const mxb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int mxb_comm_unique_id(void *id128) {
+    MXB_REQUIRE(id128 != nullptr, "id128 is NULL");
+    MXB_TRY(load_nccl());
+    nccl_uid_t uid;
+    MXB_NCCL(g_nccl.get_uid(&uid));
+    memcpy(id128, &uid, sizeof(uid));
+    return MXB_OK;
+}
+
+int mxb_comm_init(mxb_ctx *ctx, const void *id128, int rank, int world) {
+    MXB_REQUIRE(ctx != nullptr && id128 != nullptr, "NULL argument");
+    MXB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+    MXB_REQUIRE(ctx->nccl_comm == nullptr, "comm already initialised");
+    MXB_TRY(load_nccl());
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    nccl_uid_t uid;
+    memcpy(&uid, id128, sizeof(uid));
+    void *comm = nullptr;
+    MXB_NCCL(g_nccl.init_rank(&comm, world, uid, rank));
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    return MXB_OK;
+}
+
+int mxb_comm_destroy(mxb_ctx *ctx) {
+    MXB_REQUIRE(ctx != nullptr, "ctx is NULL");
+    if (ctx->nccl_comm) {
+        cudaStreamSynchronize(ctx->stream);
+        g_nccl.destroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->rank = 0;
+    ctx->world = 1;
+    return MXB_OK;
+}
+
+int mxb_comm_allreduce_host(mxb_ctx *ctx, double *buf, int64_t n, int op_is_max) {
+    MXB_REQUIRE(ctx != nullptr && (buf != nullptr || n == 0) && n >= 0, "bad argument");
+    if (!ctx->nccl_comm || ctx->world <= 1 || n == 0) return MXB_OK;
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    MXB_CUDA(cudaMalloc(&d, n * sizeof(double)));
+    int rc = MXB_OK;
+    if (cudaMemcpyAsync(d, buf, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        rc = MXB_ERR_CUDA;
+    if (rc == MXB_OK) rc = nccl_allreduce_f64(ctx, d, n, op_is_max);
+    if (rc == MXB_OK &&
+        cudaMemcpyAsync(buf, d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        rc = MXB_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == MXB_OK) rc = MXB_ERR_CUDA;
+    cudaFree(d);
+    if (rc == MXB_ERR_CUDA && g_error[0] == 0) set_error("allreduce_host: CUDA failure");
+    return rc;
+}
+
+// ---- matrices ---------------------------------------------------------------
+
+int mxb_matrix_alloc(mxb_ctx *ctx, int64_t n_rows, int64_t n_cols, mxb_matrix **out) {
+    MXB_REQUIRE(ctx != nullptr && out != nullptr, "NULL argument");
+    MXB_REQUIRE(n_rows >= 0 && n_cols >= 0, "negative shape");
+    *out = nullptr;
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    mxb_matrix *m = new (std::nothrow) mxb_matrix();
+    if (!m) { set_error("out of host memory"); return MXB_ERR_NOMEM; }
+    m->ctx = ctx;
+    m->n_rows = n_rows;
+    m->n_cols = n_cols;
+    size_t bytes = (size_t)n_rows * (size_t)n_cols * sizeof(double);
+    if (bytes) {
+        cudaError_t e = cudaMalloc(&m->data, bytes);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) for %lld x %lld matrix: %s", bytes,
+                      (long long)n_rows, (long long)n_cols, cudaGetErrorString(e));
+            delete m;
+            return e == cudaErrorMemoryAllocation ? MXB_ERR_NOMEM : MXB_ERR_CUDA;
+        }
+    }
+    *out = m;
+    return MXB_OK;
+}
+
+int mxb_matrix_upload(mxb_ctx *ctx, const double *host, int64_t n_rows,
+                      int64_t n_cols, mxb_matrix **out) {
+    MXB_REQUIRE(host != nullptr || n_rows * n_cols == 0, "host is NULL");
+    MXB_TRY(mxb_matrix_alloc(ctx, n_rows, n_cols, out));
+    size_t bytes = (size_t)n_rows * (size_t)n_cols * sizeof(double);
+    if (bytes) {
+        cudaError_t e = cudaMemcpyAsync((*out)->data, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            set_error("matrix upload: %s", cudaGetErrorString(e));
+            mxb_matrix_destroy(*out);
+            *out = nullptr;
+            return MXB_ERR_CUDA;
+        }
+    }
+    return MXB_OK;
+}
+
+int mxb_matrix_download(mxb_ctx *ctx, const mxb_matrix *m, double *host) {
+    MXB_REQUIRE(ctx != nullptr && m != nullptr, "NULL argument");
+    size_t bytes = (size_t)m->n_rows * (size_t)m->n_cols * sizeof(double);
+    if (!bytes) return MXB_OK;
+    MXB_REQUIRE(host != nullptr, "host is NULL");
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    MXB_CUDA(cudaMemcpyAsync(host, m->data, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MXB_OK;
+}
+
+int mxb_matrix_shape(const mxb_matrix *m, int64_t *n_rows, int64_t *n_cols) {
+    MXB_REQUIRE(m != nullptr, "matrix is NULL");
+    if (n_rows) *n_rows = m->n_rows;
+    if (n_cols) *n_cols = m->n_cols;
+    return MXB_OK;
+}
+
+void *mxb_matrix_data(const mxb_matrix *m) { return m ? (void *)m->data : nullptr; }
+
+int mxb_matrix_argmax_rows(mxb_ctx *ctx, const mxb_matrix *m, int64_t *out_host) {
+    MXB_REQUIRE(ctx != nullptr && m != nullptr, "NULL argument");
+    if (m->n_rows == 0) return MXB_OK;
+    MXB_REQUIRE(out_host != nullptr, "out_host is NULL");
+    MXB_REQUIRE(m->n_cols > 0, "argmax of empty rows");
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    int64_t *d = nullptr;
+    MXB_CUDA(cudaMalloc(&d, m->n_rows * sizeof(int64_t)));
+    int blocks = (int)std::min<int64_t>(ceil_div(m->n_rows, 8), (int64_t)ctx->num_sms * 8);
+    argmax_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(m->data, m->n_rows, m->n_cols, d);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(out_host, d, m->n_rows * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error("argmax_rows: %s", cudaGetErrorString(e)); return MXB_ERR_CUDA; }
+    return MXB_OK;
+}
+
+int mxb_matrix_destroy(mxb_matrix *m) {
+    if (!m) return MXB_OK;
+    if (m->data) {
+        cudaSetDevice(m->ctx->device);
+        cudaFree(m->data);
+    }
+    delete m;
+    return MXB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Shared internals of libmixemt_b200 (not part of the C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "mixemt_b200.h"
+
+namespace mxb {
+
+void set_error(const char *fmt, ...);
+
+#define MXB_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t err__ = (call);                                           \
+        if (err__ != cudaSuccess) {                                           \
+            mxb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,      \
+                           cudaGetErrorString(err__));                        \
+            return MXB_ERR_CUDA;                                              \
+        }                                                                     \
+    } while (0)
+
+#define MXB_REQUIRE(cond, msg)                                                \
+    do {                                                                      \
+        if (!(cond)) {                                                        \
+            mxb::set_error("%s: %s", __func__, msg);                          \
+            return MXB_ERR_ARG;                                               \
+        }                                                                     \
+    } while (0)
+
+#define MXB_TRY(call)                                                         \
+    do {                                                                      \
+        int rc__ = (call);                                                    \
+        if (rc__ != MXB_OK) return rc__;                                      \
+    } while (0)
+
+// Minimal NCCL surface, resolved with dlopen so that the library loads (and
+// single-GPU runs work) without libnccl on the link line.
+struct NcclApi;
+
+constexpr int kNumSMsFallback = 148;  // B200
+
+}  // namespace mxb
+
+struct mxb_ctx {
+    int device = 0;
+    int num_sms = mxb::kNumSMsFallback;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    // NCCL (optional)
+    void *nccl_comm = nullptr;
+    int rank = 0;
+    int world = 1;
+};
+
+struct mxb_matrix {
+    mxb_ctx *ctx = nullptr;
+    double *data = nullptr;  // row-major, stride n_cols
+    int64_t n_rows = 0;
+    int64_t n_cols = 0;
+};
+
+struct mxb_phylo {
+    mxb_ctx *ctx = nullptr;
+    int32_t n_pos = 0;
+    int32_t n_hap = 0;
+    int32_t n_sym = 0;     // planes 0..n_sym-1, plane n_sym is all-zero ("other")
+    int32_t n_words = 0;   // 32-bit words per plane (padded to a multiple of 4)
+    uint32_t *bits = nullptr;   // [n_pos][n_sym+1][n_words]
+    double2 *hitmiss = nullptr; // [n_pos] (hit, miss)
+};
+
+namespace mxb {
+
+int nccl_allreduce_sum_f64(mxb_ctx *ctx, double *dev_buf, int64_t n);
+int nccl_allreduce_f64(mxb_ctx *ctx, double *dev_buf, int64_t n, int op_is_max);
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+}  // namespace mxb

@@ -1,0 +1,952 @@
+// Kernel 2: the EM mixture-proportion fit.
+//
+// Replaces em_step / converged / run_em (reference mixemt/em.py:39-165) and the
+// scipy.special.logsumexp calls inside them (em.py:82, :87-89).
+//
+// Formulation.  The reference works on Z_ij = M_ij + ln pi_j - lse_i in log
+// space and makes ~30 passes over the N x H matrix per iteration (two
+// max-shifted logsumexp reductions).  With m_i = max_j M_ij and
+// L_ij = exp(M_ij - m_i) (computed once per run_em call, shared by all
+// restarts), one iteration is
+//
+//     s_i   = sum_j L_ij pi_j                      (row dot product)
+//     T_j   = sum_i (w_i / s_i) L_ij               (weighted column sum)
+//     pi'_j = pi_j T_j / sum_k pi_k T_k            (M-step; == em.py:87-89)
+//
+// i.e. exactly two fp64 FMAs per cell and ONE read of L per iteration: the pass
+// is bound by HBM bandwidth (8 B/cell), not by exp throughput.  ln pi is
+// carried in log space next to pi (ln pi'_j = ln pi_j + log(T_j / total) once
+// pi_j leaves the normal range), so dying components keep following the
+// reference's trajectory after exp() underflows.  The read matrix the reference
+// returns (em.py:130-136: responsibilities at the *previous* proportions) is
+// produced in log space straight from M by read_mix_kernel, with scipy's
+// logsumexp formula (log1p(s/m) + log(m) + max).
+//
+// The fused pass (em_pass_fast_kernel) is a persistent kernel, one CTA per SM,
+// that streams its contiguous row range through a shared-memory ring filled by
+// 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier complete_tx).
+// Thread t owns the same 2*NC columns of every row: it reads each staged cell
+// once into registers, contributes to the row's dot product, and after a
+// block-wide reduction adds (w_i/s_i) * L_ij into its private column sums.
+// Per-CTA column sums are written once at the end and reduced in a fixed order
+// (deterministic: no floating-point atomics anywhere).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mxb {
+
+// Device-resident control block: lets every kernel of an iteration early-exit
+// once the run has converged, so iterations can be enqueued ahead of the host.
+struct EmState {
+    int done;            // 0 running, 1 converged, 2 max_iter reached
+    int cur;             // index of the current (input) proportions buffer
+    int bad;             // rows whose mixture likelihood underflowed to 0
+    int pad;
+    long long iters;
+    long long max_iter;
+    double tol;
+    double delta;
+};
+
+constexpr int kPassThreads = 512;
+constexpr int kPassWarps = kPassThreads / 32;
+constexpr int kPassGroup = 2;       // rows reduced together per block barrier
+constexpr int kMaxNC = 8;           // column chunks (double2) per thread
+constexpr int kLdAlign = 16;        // row stride of L in doubles (128 B)
+
+// ---- small PTX helpers ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted on an mbarrier.
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes,
+                                          uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+// Block-wide deterministic reductions (every thread gets the result).
+template <int kThreads>
+__device__ __forceinline__ double block_sum(double v, double *scratch /*[kThreads/32]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // scratch free
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) t += scratch[i];
+    return t;
+}
+template <int kThreads>
+__device__ __forceinline__ double block_max(double v, double *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double t = scratch[0];
+#pragma unroll
+    for (int i = 1; i < kThreads / 32; ++i) t = fmax(t, scratch[i]);
+    return t;
+}
+
+// ---- M -> L ------------------------------------------------------------------
+// L_ij = exp(M_ij - max_j M_ij); padding columns [n_cols, ld) are 0.
+__global__ void __launch_bounds__(256)
+to_linear_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols, int64_t ld,
+                 double *__restrict__ lin) {
+    __shared__ double scratch[8];
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const double *row = m + r * n_cols;
+        double mx = -INFINITY;
+        bool has_nan = false;
+        for (int64_t j = threadIdx.x; j < n_cols; j += 256) {
+            double v = row[j];
+            has_nan |= (v != v);
+            mx = fmax(mx, v);
+        }
+        mx = block_max<256>(mx, scratch);
+        double *dst = lin + r * ld;
+        for (int64_t j = threadIdx.x; j < ld; j += 256)
+            dst[j] = (j < n_cols) ? exp(row[j] - mx) : 0.0;  // row re-read hits L1/L2
+        (void)has_nan;
+    }
+}
+
+// ---- fused E+M pass (fast path) ----------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(kPassThreads, 1)
+em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
+                    const double *__restrict__ weights, const double *__restrict__ pi0,
+                    const double *__restrict__ pi1, EmState *__restrict__ st,
+                    double *__restrict__ partials, int n_stages) {
+    if (st->done) return;
+    const double *__restrict__ pi = st->cur ? pi1 : pi0;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t row_bytes = (uint32_t)(ld * sizeof(double));
+    double *stages = reinterpret_cast<double *>(smem_raw);
+    double *scratch = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * row_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int64_t n_my = r_end - r_begin;
+    const double *my_rows = lin + r_begin * ld;
+
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int64_t q = 0; q < n_my && q < n_stages; ++q) {
+            mbar_expect_tx(&full[q], row_bytes);
+            bulk_load(stages + q * ld, my_rows + q * ld, row_bytes, &full[q]);
+        }
+    }
+
+    // Thread-private column slice: chunk c = tid + k*512 covers doubles 2c, 2c+1.
+    const int64_t n_chunks = ld >> 1;
+    double2 pr[NC], tr[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int64_t c = tid + (int64_t)k * kPassThreads;
+        pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
+        tr[k] = make_double2(0.0, 0.0);
+    }
+
+    int sbuf = 0;
+    int bad = 0;
+    for (int64_t q0 = 0; q0 < n_my; q0 += kPassGroup) {
+        double2 lv[kPassGroup][NC];
+        double dot[kPassGroup], wv[kPassGroup];
+#pragma unroll
+        for (int g = 0; g < kPassGroup; ++g) {
+            const int64_t q = q0 + g;
+            dot[g] = 0.0;
+            wv[g] = 0.0;
+            if (q < n_my) {
+                wv[g] = weights[r_begin + q];
+                const int s = (int)(q % n_stages);
+                mbar_wait(&full[s], (uint32_t)((q / n_stages) & 1));
+                const double2 *srow = reinterpret_cast<const double2 *>(stages + (size_t)s * ld);
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    const int64_t c = tid + (int64_t)k * kPassThreads;
+                    lv[g][k] = (c < n_chunks) ? srow[c] : make_double2(0.0, 0.0);
+                    dot[g] = fma(lv[g][k].x, pr[k].x, dot[g]);
+                    dot[g] = fma(lv[g][k].y, pr[k].y, dot[g]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NC; ++k) lv[g][k] = make_double2(0.0, 0.0);
+            }
+            dot[g] = warp_sum(dot[g]);
+        }
+        double *sc = scratch + sbuf * (kPassWarps * kPassGroup);
+        if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < kPassGroup; ++g) sc[warp * kPassGroup + g] = dot[g];
+        }
+        __syncthreads();  // all reads of this group's stages are done; partial dots visible
+        if (tid == 0) {
+#pragma unroll
+            for (int g = 0; g < kPassGroup; ++g) {
+                const int64_t q = q0 + g + n_stages;
+                if (q0 + g < n_my && q < n_my) {
+                    const int s = (int)(q % n_stages);
+                    mbar_expect_tx(&full[s], row_bytes);
+                    bulk_load(stages + (size_t)s * ld, my_rows + q * ld, row_bytes, &full[s]);
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kPassGroup; ++g) {
+            double s_row = 0.0;
+#pragma unroll
+            for (int wp = 0; wp < kPassWarps; ++wp) s_row += sc[wp * kPassGroup + g];
+            double coef = 0.0;
+            if (wv[g] != 0.0) {
+                coef = wv[g] / s_row;
+                bad |= (s_row == 0.0);
+            }
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                tr[k].x = fma(coef, lv[g][k].x, tr[k].x);
+                tr[k].y = fma(coef, lv[g][k].y, tr[k].y);
+            }
+        }
+        sbuf ^= 1;
+    }
+
+    double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int64_t c = tid + (int64_t)k * kPassThreads;
+        if (c < n_chunks) out[c] = tr[k];
+    }
+    if (bad && tid == 0) atomicAdd(&st->bad, 1);
+}
+
+// ---- general path: any shape, two passes over L -------------------------------
+// coef_i = w_i / sum_j L_ij pi_j, one warp per row.
+__global__ void __launch_bounds__(256)
+em_rowdot_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
+                 const double *__restrict__ weights, const double *__restrict__ pi0,
+                 const double *__restrict__ pi1, EmState *__restrict__ st,
+                 double *__restrict__ coef) {
+    if (st->done) return;
+    const double2 *__restrict__ pi = reinterpret_cast<const double2 *>(st->cur ? pi1 : pi0);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    const int64_t n_chunks = ld >> 1;
+    int bad = 0;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        const double2 *row = reinterpret_cast<const double2 *>(lin + r * ld);
+        double dot = 0.0;
+        for (int64_t c = lane; c < n_chunks; c += 32) {
+            const double2 l = row[c];
+            const double2 p = pi[c];
+            dot = fma(l.x, p.x, dot);
+            dot = fma(l.y, p.y, dot);
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) {
+            const double w = weights[r];
+            double c = 0.0;
+            if (w != 0.0) { c = w / dot; bad |= (dot == 0.0); }
+            coef[r] = c;
+        }
+    }
+    if (bad) atomicAdd(&st->bad, 1);
+}
+
+// partial T_j over a row range; thread owns one double2 column chunk.
+__global__ void __launch_bounds__(256)
+em_colacc_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
+                 const double *__restrict__ coef, const EmState *__restrict__ st,
+                 double *__restrict__ partials) {
+    if (st->done) return;
+    const int64_t c = (int64_t)blockIdx.y * 256 + threadIdx.x;
+    if (c >= (ld >> 1)) return;
+    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    double2 t = make_double2(0.0, 0.0);
+    int64_t r = r_begin;
+    for (; r + 4 <= r_end; r += 4) {
+        double2 l[4];
+        double cf[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            l[u] = reinterpret_cast<const double2 *>(lin + (r + u) * ld)[c];
+            cf[u] = coef[r + u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            t.x = fma(cf[u], l[u].x, t.x);
+            t.y = fma(cf[u], l[u].y, t.y);
+        }
+    }
+    for (; r < r_end; ++r) {
+        const double2 l = reinterpret_cast<const double2 *>(lin + r * ld)[c];
+        const double cf = coef[r];
+        t.x = fma(cf, l.x, t.x);
+        t.y = fma(cf, l.y, t.y);
+    }
+    reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld)[c] = t;
+}
+
+// T_j = sum over CTAs of partials, fixed order.
+__global__ void __launch_bounds__(256)
+em_colreduce_kernel(const double *__restrict__ partials, int n_part, int64_t ld,
+                    const EmState *__restrict__ st, double *__restrict__ tsum) {
+    if (st->done) return;
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= ld) return;
+    double t = 0.0;
+    for (int b = 0; b < n_part; ++b) t += partials[(size_t)b * ld + j];
+    tsum[j] = t;
+}
+
+// M-step normalisation + convergence test (em.py:89 and :39-54), one CTA.
+constexpr int kUpdThreads = 1024;
+__global__ void __launch_bounds__(kUpdThreads)
+em_update_kernel(const double *__restrict__ tsum, int64_t n_cols, int64_t ld,
+                 double *__restrict__ lnp0, double *__restrict__ lnp1,
+                 double *__restrict__ pi0, double *__restrict__ pi1,
+                 EmState *__restrict__ st) {
+    if (st->done) return;
+    __shared__ double scratch[kUpdThreads / 32];
+    const int cur = st->cur;
+    const double *lnp_old = cur ? lnp1 : lnp0;
+    const double *pi_old = cur ? pi1 : pi0;
+    double *lnp_new = cur ? lnp0 : lnp1;
+    double *pi_new = cur ? pi0 : pi1;
+
+    double local = 0.0;
+    for (int64_t j = threadIdx.x; j < n_cols; j += kUpdThreads) local += pi_old[j] * tsum[j];
+    const double total = block_sum<kUpdThreads>(local, scratch);
+
+    double dl = 0.0;
+    for (int64_t j = threadIdx.x; j < n_cols; j += kUpdThreads) {
+        const double p = pi_old[j];
+        const double t = tsum[j];
+        double ln_new;
+        if (p >= 1e-290) ln_new = log(p * t / total);
+        else ln_new = lnp_old[j] + log(t / total);  // pi underflowed: stay in log space
+        const double p_new = exp(ln_new);
+        lnp_new[j] = ln_new;
+        pi_new[j] = p_new;
+        dl += fabs(p_new - p);
+    }
+    const double delta = block_sum<kUpdThreads>(dl, scratch);
+    if (threadIdx.x == 0) {
+        st->delta = delta;
+        const long long it = st->iters + 1;
+        st->iters = it;
+        if (delta < st->tol) st->done = 1;
+        else if (it >= st->max_iter) st->done = 2;
+        else st->cur = 1 - cur;
+    }
+}
+
+// ln pi -> (ln pi, pi) device buffers, padding zeroed.
+__global__ void em_set_props_kernel(const double *__restrict__ src, int64_t n_cols, int64_t ld,
+                                    double *__restrict__ lnp, double *__restrict__ pi,
+                                    double *__restrict__ lnp_other, double *__restrict__ pi_other) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ld) return;
+    const bool in = j < n_cols;
+    const double v = in ? src[j] : -INFINITY;
+    lnp[j] = v;
+    pi[j] = in ? exp(v) : 0.0;
+    lnp_other[j] = -INFINITY;
+    pi_other[j] = 0.0;
+}
+
+// ---- read matrix: Z = (M + ln pi) - logsumexp_row(M + ln pi) -------------------
+// (em.py:80-83).  mode 1 folds into dst with numpy.logaddexp (em.py:156).
+__device__ __forceinline__ double np_logaddexp(double x, double y) {
+    if (x == y) return x + 0.693147180559945309417232121458176568;
+    const double tmp = x - y;
+    if (tmp > 0) return x + log1p(exp(-tmp));
+    if (tmp <= 0) return y + log1p(exp(tmp));
+    return tmp;  // NaN
+}
+
+constexpr int kMixThreads = 256;
+__global__ void __launch_bounds__(kMixThreads)
+read_mix_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols,
+                const double *__restrict__ lnp, double *__restrict__ dst, int mode,
+                double sub_log) {
+    __shared__ double scratch[kMixThreads / 32];
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const double *row = m + r * n_cols;
+        double mx = -INFINITY;
+        double nan_flag = 0.0;  // fmax drops NaN; numpy.max propagates it
+        for (int64_t j = threadIdx.x; j < n_cols; j += kMixThreads) {
+            const double z = row[j] + lnp[j];
+            if (z != z) nan_flag = 1.0;
+            mx = fmax(mx, z);
+        }
+        nan_flag = block_sum<kMixThreads>(nan_flag, scratch);
+        mx = block_max<kMixThreads>(mx, scratch);
+        double lse;
+        if (nan_flag > 0.0) {
+            lse = NAN;
+        } else if (isinf(mx)) {
+            lse = mx;  // all -inf -> log(0); any +inf -> +inf (scipy's out_inf branch)
+        } else {
+            // scipy _logsumexp: s over non-max terms, m = number of max terms
+            double s = 0.0, cnt = 0.0;
+            for (int64_t j = threadIdx.x; j < n_cols; j += kMixThreads) {
+                const double z = row[j] + lnp[j];
+                if (z == mx) cnt += 1.0;
+                else s += exp(z - mx);
+            }
+            s = block_sum<kMixThreads>(s, scratch);
+            cnt = block_sum<kMixThreads>(cnt, scratch);
+            lse = log1p(s / cnt) + log(cnt) + mx;
+        }
+        double *out = dst + r * n_cols;
+        for (int64_t j = threadIdx.x; j < n_cols; j += kMixThreads) {
+            double z = (row[j] + lnp[j]) - lse;
+            if (mode == 1) z = np_logaddexp(out[j], z);
+            if (sub_log != 0.0) z -= sub_log;
+            out[j] = z;
+        }
+    }
+}
+
+// Cross-rank fold helpers: m <- exp(m - mx) ; m <- mx + log(m) - sub_log.
+__global__ void fold_exp_kernel(double *__restrict__ m, const double *__restrict__ mx, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = mx[i];
+        m[i] = isinf(a) ? (a < 0 ? 0.0 : 1.0) : exp(m[i] - a);
+    }
+}
+__global__ void fold_log_kernel(double *__restrict__ m, const double *__restrict__ mx, int64_t n,
+                                double sub_log) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = mx[i];
+        m[i] = (isinf(a) ? a : a + log(m[i])) - sub_log;
+    }
+}
+
+}  // namespace mxb
+
+using namespace mxb;
+
+struct mxb_em {
+    mxb_ctx *ctx = nullptr;
+    const mxb_matrix *mat = nullptr;
+    int64_t n_rows = 0, n_cols = 0, ld = 0;
+    bool sharded = false;
+    double *lin = nullptr;        // [n_rows][ld]
+    double *weights = nullptr;    // [n_rows]
+    double *coef = nullptr;       // [n_rows] (general path)
+    double *lnp[2] = {nullptr, nullptr};
+    double *pi[2] = {nullptr, nullptr};
+    double *partials = nullptr;   // [n_part][ld]
+    double *tsum = nullptr;       // [ld]
+    double *props_in = nullptr;   // [n_cols] staging for set_lnprops
+    EmState *state = nullptr;     // device
+    EmState *host_state = nullptr;  // pinned, 2 slots
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+    int n_part = 0;
+    // fast path
+    bool fast = false;
+    int nc = 0;
+    int n_stages = 0;
+    size_t smem_bytes = 0;
+    int grid_fast = 0;
+    // general path
+    int row_blocks = 0, col_blocks = 0;
+    bool zero_iter = false;  // last iterate() ran no iteration
+};
+
+namespace mxb {
+
+typedef void (*pass_fn)(const double *, int64_t, int64_t, const double *, const double *,
+                        const double *, EmState *, double *, int);
+
+static pass_fn pick_pass(int nc) {
+    switch (nc) {
+        case 1: return em_pass_fast_kernel<1>;
+        case 2: return em_pass_fast_kernel<2>;
+        case 3: return em_pass_fast_kernel<3>;
+        case 4: return em_pass_fast_kernel<4>;
+        case 5: return em_pass_fast_kernel<5>;
+        case 6: return em_pass_fast_kernel<6>;
+        case 7: return em_pass_fast_kernel<7>;
+        case 8: return em_pass_fast_kernel<8>;
+    }
+    return nullptr;
+}
+
+// One EM iteration on em->ctx->stream (no host sync).
+static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
+                             cudaEvent_t pass_end = nullptr) {
+    mxb_ctx *ctx = em->ctx;
+    cudaStream_t s = ctx->stream;
+    if (pass_begin) MXB_CUDA(cudaEventRecord(pass_begin, s));
+    if (em->fast) {
+        pick_pass(em->nc)<<<em->grid_fast, kPassThreads, em->smem_bytes, s>>>(
+            em->lin, em->ld, em->n_rows, em->weights, em->pi[0], em->pi[1], em->state,
+            em->partials, em->n_stages);
+        ctx->launches += 1;
+    } else {
+        const int rd_blocks = (int)std::min<int64_t>(ceil_div(em->n_rows, 8), (int64_t)ctx->num_sms * 8);
+        em_rowdot_kernel<<<rd_blocks, 256, 0, s>>>(em->lin, em->ld, em->n_rows, em->weights,
+                                                   em->pi[0], em->pi[1], em->state, em->coef);
+        dim3 grid(em->row_blocks, em->col_blocks);
+        em_colacc_kernel<<<grid, 256, 0, s>>>(em->lin, em->ld, em->n_rows, em->coef, em->state,
+                                              em->partials);
+        ctx->launches += 2;
+    }
+    if (pass_end) MXB_CUDA(cudaEventRecord(pass_end, s));
+    em_colreduce_kernel<<<(int)ceil_div(em->ld, 256), 256, 0, s>>>(em->partials, em->n_part,
+                                                                  em->ld, em->state, em->tsum);
+    ctx->launches += 1;
+    if (em->sharded && ctx->world > 1) MXB_TRY(nccl_allreduce_sum_f64(ctx, em->tsum, em->ld));
+    em_update_kernel<<<1, kUpdThreads, 0, s>>>(em->tsum, em->n_cols, em->ld, em->lnp[0],
+                                               em->lnp[1], em->pi[0], em->pi[1], em->state);
+    ctx->launches += 1;
+    MXB_CUDA(cudaGetLastError());
+    return MXB_OK;
+}
+
+static int reset_state(mxb_em *em, long long max_iter, double tol) {
+    EmState st;
+    memset(&st, 0, sizeof(st));
+    st.max_iter = max_iter;
+    st.tol = tol;
+    // synchronous w.r.t. the host buffer: pageable copy of a stack struct
+    MXB_CUDA(cudaMemcpyAsync(em->state, &st, sizeof(st), cudaMemcpyHostToDevice, em->ctx->stream));
+    MXB_CUDA(cudaStreamSynchronize(em->ctx->stream));
+    return MXB_OK;
+}
+
+}  // namespace mxb
+
+extern "C" {
+
+int mxb_em_destroy(mxb_em *em) {
+    if (!em) return MXB_OK;
+    cudaSetDevice(em->ctx->device);
+    cudaStreamSynchronize(em->ctx->stream);
+    cudaFree(em->lin);
+    cudaFree(em->weights);
+    cudaFree(em->coef);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(em->lnp[i]);
+        cudaFree(em->pi[i]);
+        if (em->poll_ev[i]) cudaEventDestroy(em->poll_ev[i]);
+    }
+    cudaFree(em->partials);
+    cudaFree(em->tsum);
+    cudaFree(em->props_in);
+    cudaFree(em->state);
+    if (em->host_state) cudaFreeHost(em->host_state);
+    delete em;
+    return MXB_OK;
+}
+
+int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int sharded,
+                  mxb_em **out) {
+    MXB_REQUIRE(ctx != nullptr && m != nullptr && out != nullptr, "NULL argument");
+    MXB_REQUIRE(m->n_rows > 0 && m->n_cols > 0, "EM needs a non-empty matrix");
+    MXB_REQUIRE(weights != nullptr, "weights is NULL");
+    *out = nullptr;
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    mxb_em *em = new (std::nothrow) mxb_em();
+    if (!em) { set_error("out of host memory"); return MXB_ERR_NOMEM; }
+    em->ctx = ctx;
+    em->mat = m;
+    em->n_rows = m->n_rows;
+    em->n_cols = m->n_cols;
+    em->ld = round_up(m->n_cols, kLdAlign);
+    em->sharded = sharded != 0;
+
+    // launch geometry
+    const size_t row_bytes = (size_t)em->ld * sizeof(double);
+    const size_t fixed = 2 * kPassWarps * kPassGroup * sizeof(double) + 8 * sizeof(uint64_t) + 128;
+    const bool force_general = getenv("MXB_EM_FORCE_GENERAL") != nullptr;
+    em->nc = (int)ceil_div(em->ld / 2, kPassThreads);
+    if (!force_general && em->ld >= 1024 && em->nc <= kMaxNC && ctx->smem_optin > fixed) {
+        int stages = (int)std::min<size_t>(8, (ctx->smem_optin - fixed) / row_bytes);
+        if (stages >= kPassGroup + 1) {
+            em->fast = true;
+            em->n_stages = stages;
+            em->smem_bytes = (size_t)stages * row_bytes + fixed;
+            em->grid_fast = (int)std::min<int64_t>(ctx->num_sms, em->n_rows);
+        }
+    }
+    if (em->fast) {
+        em->n_part = em->grid_fast;
+        cudaError_t e = cudaFuncSetAttribute((const void *)pick_pass(em->nc),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)em->smem_bytes);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(smem=%zu): %s", em->smem_bytes, cudaGetErrorString(e));
+            delete em;
+            return MXB_ERR_CUDA;
+        }
+    } else {
+        em->col_blocks = (int)ceil_div(em->ld / 2, 256);
+        int64_t rb = std::max<int64_t>(1, (int64_t)ctx->num_sms * 4 / em->col_blocks);
+        rb = std::min<int64_t>(rb, ceil_div(em->n_rows, 16));
+        em->row_blocks = (int)std::max<int64_t>(1, rb);
+        em->n_part = em->row_blocks;
+    }
+
+    cudaError_t e = cudaSuccess;
+#define STEP(call) do { if (e == cudaSuccess) e = (call); } while (0)
+    STEP(cudaMalloc(&em->lin, (size_t)em->n_rows * row_bytes));
+    STEP(cudaMalloc(&em->weights, em->n_rows * sizeof(double)));
+    if (!em->fast) STEP(cudaMalloc(&em->coef, em->n_rows * sizeof(double)));
+    for (int i = 0; i < 2; ++i) {
+        STEP(cudaMalloc(&em->lnp[i], row_bytes));
+        STEP(cudaMalloc(&em->pi[i], row_bytes));
+        STEP(cudaEventCreateWithFlags(&em->poll_ev[i], cudaEventDisableTiming));
+    }
+    STEP(cudaMalloc(&em->partials, (size_t)em->n_part * row_bytes));
+    STEP(cudaMalloc(&em->tsum, row_bytes));
+    STEP(cudaMalloc(&em->props_in, em->n_cols * sizeof(double)));
+    STEP(cudaMalloc(&em->state, sizeof(EmState)));
+    STEP(cudaMallocHost(&em->host_state, 2 * sizeof(EmState)));
+    STEP(cudaMemcpyAsync(em->weights, weights, em->n_rows * sizeof(double),
+                         cudaMemcpyHostToDevice, ctx->stream));
+    if (e == cudaSuccess) {
+        const int grid = (int)std::min<int64_t>(em->n_rows, (int64_t)ctx->num_sms * 8);
+        to_linear_kernel<<<grid, 256, 0, ctx->stream>>>(m->data, em->n_rows, em->n_cols, em->ld,
+                                                        em->lin);
+        ctx->launches++;
+        STEP(cudaGetLastError());
+    }
+    STEP(cudaStreamSynchronize(ctx->stream));
+#undef STEP
+    if (e != cudaSuccess) {
+        set_error("mxb_em_create (%lld x %lld): %s", (long long)em->n_rows,
+                  (long long)em->n_cols, cudaGetErrorString(e));
+        mxb_em_destroy(em);
+        return e == cudaErrorMemoryAllocation ? MXB_ERR_NOMEM : MXB_ERR_CUDA;
+    }
+    *out = em;
+    return MXB_OK;
+}
+
+int mxb_em_set_lnprops(mxb_em *em, const double *lnprops) {
+    MXB_REQUIRE(em != nullptr && lnprops != nullptr, "NULL argument");
+    mxb_ctx *ctx = em->ctx;
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    MXB_CUDA(cudaMemcpyAsync(em->props_in, lnprops, em->n_cols * sizeof(double),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    em_set_props_kernel<<<(int)ceil_div(em->ld, 256), 256, 0, ctx->stream>>>(
+        em->props_in, em->n_cols, em->ld, em->lnp[0], em->pi[0], em->lnp[1], em->pi[1]);
+    ctx->launches++;
+    MXB_CUDA(cudaGetLastError());
+    MXB_CUDA(cudaStreamSynchronize(ctx->stream));  // lnprops may be a temporary
+    MXB_TRY(reset_state(em, 0, 0.0));
+    em->zero_iter = true;
+    return MXB_OK;
+}
+
+int mxb_em_iterate(mxb_em *em, int64_t max_iter, double tol, int64_t *iters_out,
+                   int32_t *converged_out) {
+    MXB_REQUIRE(em != nullptr, "em is NULL");
+    mxb_ctx *ctx = em->ctx;
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    if (iters_out) *iters_out = 0;
+    if (converged_out) *converged_out = 0;
+    if (max_iter <= 0) {  // em.py:126 loop body never runs; :141-143 hands back the init
+        em->zero_iter = true;
+        return MXB_OK;
+    }
+    em->zero_iter = false;
+    // keep `cur` as set_lnprops left it (0), restart counters
+    MXB_TRY(reset_state(em, max_iter, tol));
+
+    // Chunks of iterations are enqueued ahead of the host; a finished run turns
+    // the remaining launches into early-exit no-ops.  Two chunks in flight.
+    const int64_t kChunk = 16;
+    int64_t enqueued = 0;
+    int slot = 0;
+    bool pending[2] = {false, false};
+    EmState fin;
+    memset(&fin, 0, sizeof(fin));
+    bool finished = false;
+    while (!finished) {
+        if (enqueued < max_iter) {
+            const int64_t n = std::min<int64_t>(kChunk, max_iter - enqueued);
+            for (int64_t i = 0; i < n; ++i) MXB_TRY(enqueue_iteration(em));
+            enqueued += n;
+        }
+        MXB_CUDA(cudaMemcpyAsync(&em->host_state[slot], em->state, sizeof(EmState),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        MXB_CUDA(cudaEventRecord(em->poll_ev[slot], ctx->stream));
+        pending[slot] = true;
+        const int other = slot ^ 1;
+        // wait for the older chunk (or this one when nothing else can be queued)
+        const int wait_slot = pending[other] ? other : slot;
+        const bool must_wait = pending[other] || enqueued >= max_iter;
+        if (must_wait) {
+            MXB_CUDA(cudaEventSynchronize(em->poll_ev[wait_slot]));
+            pending[wait_slot] = false;
+            if (em->host_state[wait_slot].done) {
+                fin = em->host_state[wait_slot];
+                finished = true;
+            } else if (wait_slot == slot && enqueued >= max_iter) {
+                // cannot happen: max_iter iterations always set done
+                set_error("mxb_em_iterate: run did not terminate");
+                return MXB_ERR_CUDA;
+            }
+        }
+        slot = other;
+    }
+    MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (iters_out) *iters_out = fin.iters;
+    if (converged_out) *converged_out = (fin.done == 1);
+    if (fin.bad) {
+        set_error("EM: the mixture likelihood of %d row group(s) underflowed to 0 "
+                  "(proportions left the fp64 range)", fin.bad);
+        return MXB_ERR_RANGE;
+    }
+    return MXB_OK;
+}
+
+int mxb_em_iterate_fixed(mxb_em *em, int64_t n_iter, float *elapsed_ms, float *pass_ms) {
+    MXB_REQUIRE(em != nullptr && n_iter >= 1 && n_iter <= 100000, "bad argument");
+    mxb_ctx *ctx = em->ctx;
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    em->zero_iter = false;
+    MXB_TRY(reset_state(em, (long long)1 << 60, -1.0));
+    std::vector<cudaEvent_t> evs;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    MXB_CUDA(cudaEventCreate(&e0));
+    MXB_CUDA(cudaEventCreate(&e1));
+    if (pass_ms) {
+        evs.resize((size_t)n_iter * 2);
+        for (auto &e : evs) MXB_CUDA(cudaEventCreate(&e));
+    }
+    MXB_CUDA(cudaEventRecord(e0, ctx->stream));
+    for (int64_t i = 0; i < n_iter; ++i) {
+        if (pass_ms) MXB_TRY(enqueue_iteration(em, evs[2 * i], evs[2 * i + 1]));
+        else MXB_TRY(enqueue_iteration(em));
+    }
+    MXB_CUDA(cudaEventRecord(e1, ctx->stream));
+    MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (elapsed_ms) MXB_CUDA(cudaEventElapsedTime(elapsed_ms, e0, e1));
+    if (pass_ms) {
+        double total = 0.0;
+        for (int64_t i = 0; i < n_iter; ++i) {
+            float ms = 0.f;
+            MXB_CUDA(cudaEventElapsedTime(&ms, evs[2 * i], evs[2 * i + 1]));
+            total += ms;
+        }
+        *pass_ms = (float)total;
+        for (auto &e : evs) cudaEventDestroy(e);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return MXB_OK;
+}
+
+int mxb_em_get_lnprops(mxb_em *em, int which, double *out) {
+    MXB_REQUIRE(em != nullptr && out != nullptr && (which == 0 || which == 1), "bad argument");
+    mxb_ctx *ctx = em->ctx;
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    EmState st;
+    MXB_CUDA(cudaMemcpyAsync(&st, em->state, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // after a finished run: lnp[cur] = previous, lnp[1-cur] = latest.
+    int idx = (which == 0) ? 1 - st.cur : st.cur;
+    if (st.done == 0) idx = 1 - idx;  // iterate_fixed: buffers were swapped after the last step
+    if (em->zero_iter) idx = st.cur;  // no iteration ran: only the init exists
+    MXB_CUDA(cudaMemcpyAsync(out, em->lnp[idx], em->n_cols * sizeof(double),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MXB_OK;
+}
+
+int mxb_em_read_mix(mxb_em *em, mxb_matrix *dst, int mode, double sub_log) {
+    MXB_REQUIRE(em != nullptr && dst != nullptr && (mode == 0 || mode == 1), "bad argument");
+    MXB_REQUIRE(dst->n_rows == em->n_rows && dst->n_cols == em->n_cols, "shape mismatch");
+    mxb_ctx *ctx = em->ctx;
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    EmState st;
+    MXB_CUDA(cudaMemcpyAsync(&st, em->state, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int grid = (int)std::min<int64_t>(em->n_rows, (int64_t)ctx->num_sms * 8);
+    read_mix_kernel<<<grid, kMixThreads, 0, ctx->stream>>>(em->mat->data, em->n_rows, em->n_cols,
+                                                           em->lnp[st.cur], dst->data, mode,
+                                                           sub_log);
+    ctx->launches++;
+    MXB_CUDA(cudaGetLastError());
+    return MXB_OK;
+}
+
+int mxb_matrix_fold_ranks(mxb_ctx *ctx, mxb_matrix *m, double sub_log) {
+    MXB_REQUIRE(ctx != nullptr && m != nullptr, "NULL argument");
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = m->n_rows * m->n_cols;
+    if (n == 0) return MXB_OK;
+    const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 16);
+    double *mx = nullptr;
+    MXB_CUDA(cudaMalloc(&mx, n * sizeof(double)));
+    int rc = MXB_OK;
+    cudaError_t e = cudaMemcpyAsync(mx, m->data, n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                    ctx->stream);
+    if (e != cudaSuccess) rc = MXB_ERR_CUDA;
+    if (rc == MXB_OK) rc = nccl_allreduce_f64(ctx, mx, n, 1);
+    if (rc == MXB_OK) {
+        fold_exp_kernel<<<grid, 256, 0, ctx->stream>>>(m->data, mx, n);
+        ctx->launches++;
+        rc = nccl_allreduce_f64(ctx, m->data, n, 0);
+    }
+    if (rc == MXB_OK) {
+        fold_log_kernel<<<grid, 256, 0, ctx->stream>>>(m->data, mx, n, sub_log);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = MXB_ERR_CUDA;
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == MXB_OK) rc = MXB_ERR_CUDA;
+    cudaFree(mx);
+    if (rc == MXB_ERR_CUDA && mxb_last_error()[0] == 0) set_error("mxb_matrix_fold_ranks: CUDA failure");
+    return rc;
+}
+
+int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
+                   const double *init_lnprops, int32_t n_multi, int64_t max_iter, double tol,
+                   int32_t flags, double *props_out, double *read_mix_out,
+                   mxb_matrix **read_mix_dev, int64_t *iters_out, int32_t *converged_out) {
+    MXB_REQUIRE(ctx != nullptr && m != nullptr, "NULL handle");
+    MXB_REQUIRE(init_lnprops != nullptr && props_out != nullptr, "NULL buffer");
+    MXB_REQUIRE(n_multi >= 1, "n_multi must be >= 1");
+    if (read_mix_dev) *read_mix_dev = nullptr;
+    const int64_t h = m->n_cols;
+    const bool raw = (flags & MXB_EM_RAW) != 0;
+    const bool want_mix = read_mix_out != nullptr || read_mix_dev != nullptr;
+
+    mxb_em *em = nullptr;
+    mxb_matrix *mix = nullptr;
+    std::vector<double> acc((size_t)h, 0.0), cur((size_t)h);
+    int rc = mxb_em_create(ctx, m, weights, (flags & MXB_EM_SHARDED) != 0, &em);
+    if (rc == MXB_OK && want_mix) rc = mxb_matrix_alloc(ctx, m->n_rows, h, &mix);
+    for (int32_t i = 0; rc == MXB_OK && i < n_multi; ++i) {
+        int64_t iters = 0;
+        int32_t conv = 0;
+        rc = mxb_em_set_lnprops(em, init_lnprops + (size_t)i * h);
+        if (rc == MXB_OK) rc = mxb_em_iterate(em, max_iter, tol, &iters, &conv);
+        if (iters_out) iters_out[i] = iters;
+        if (converged_out) converged_out[i] = conv;
+        if (rc == MXB_OK) rc = mxb_em_get_lnprops(em, 0, cur.data());
+        if (rc == MXB_OK) {
+            // em.py:145-155: first run stored, later runs added in place
+            if (i == 0) acc = cur;
+            else for (int64_t j = 0; j < h; ++j) acc[j] += cur[j];
+        }
+        if (rc == MXB_OK && want_mix) {
+            const bool last = (i == n_multi - 1);
+            const double sub = (last && n_multi > 1 && !raw) ? log((double)n_multi) : 0.0;
+            rc = mxb_em_read_mix(em, mix, i == 0 ? 0 : 1, sub);
+        }
+    }
+    if (rc == MXB_OK) {
+        for (int64_t j = 0; j < h; ++j) {
+            double v = acc[j];
+            if (!raw) {
+                if (n_multi > 1) v /= (double)n_multi;  // em.py:158-160
+                v = exp(v);                             // em.py:163
+            }
+            props_out[j] = v;
+        }
+        if (read_mix_out) rc = mxb_matrix_download(ctx, mix, read_mix_out);
+        else if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            set_error("mxb_run_em: stream sync failed");
+            rc = MXB_ERR_CUDA;
+        }
+    }
+    mxb_em_destroy(em);
+    if (rc == MXB_OK && read_mix_dev) *read_mix_dev = mix;
+    else mxb_matrix_destroy(mix);
+    return rc;
+}
+
+int mxb_run_em(mxb_ctx *ctx, const double *read_hap_mat, const double *weights, int64_t n_rows,
+               int64_t n_cols, const double *init_lnprops, int32_t n_multi, int64_t max_iter,
+               double tol, int32_t flags, double *props_out, double *read_mix_out,
+               int64_t *iters_out, int32_t *converged_out) {
+    mxb_matrix *m = nullptr;
+    MXB_TRY(mxb_matrix_upload(ctx, read_hap_mat, n_rows, n_cols, &m));
+    int rc = mxb_run_em_dev(ctx, m, weights, init_lnprops, n_multi, max_iter, tol, flags,
+                            props_out, read_mix_out, nullptr, iters_out, converged_out);
+    mxb_matrix_destroy(m);
+    return rc;
+}
+
+int mxb_em_step(mxb_ctx *ctx, const double *read_hap_mat, const double *weights,
+                const double *ln_props, int64_t n_rows, int64_t n_cols, double *read_mix_out,
+                double *new_props_out) {
+    MXB_REQUIRE(read_mix_out != nullptr && new_props_out != nullptr && ln_props != nullptr,
+                "NULL buffer");
+    mxb_matrix *m = nullptr, *mix = nullptr;
+    mxb_em *em = nullptr;
+    MXB_TRY(mxb_matrix_upload(ctx, read_hap_mat, n_rows, n_cols, &m));
+    int rc = mxb_em_create(ctx, m, weights, 0, &em);
+    if (rc == MXB_OK) rc = mxb_matrix_alloc(ctx, n_rows, n_cols, &mix);
+    if (rc == MXB_OK) rc = mxb_em_set_lnprops(em, ln_props);
+    // one iteration, never "converged": afterwards previous = ln_props, latest = new
+    if (rc == MXB_OK) rc = mxb_em_iterate(em, 1, -1.0, nullptr, nullptr);
+    if (rc == MXB_OK) rc = mxb_em_get_lnprops(em, 0, new_props_out);
+    if (rc == MXB_OK) rc = mxb_em_read_mix(em, mix, 0, 0.0);
+    if (rc == MXB_OK) rc = mxb_matrix_download(ctx, mix, read_mix_out);
+    mxb_em_destroy(em);
+    mxb_matrix_destroy(mix);
+    mxb_matrix_destroy(m);
+    return rc;
+}
+
+}  // extern "C"

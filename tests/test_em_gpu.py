@@ -1,0 +1,298 @@
+"""Kernel 2 parity: CUDA em_step / run_em (through the C-ABI) against the
+reference's own unit tests, its golden outputs and the CPU oracle.
+
+Tolerances (north star): proportions within 1e-6 absolute (asserted much
+tighter where the reference result is well conditioned), identical
+read-to-haplotype argmax assignments, log responsibilities within 1e-9
+absolute wherever they are finite."""
+import math
+
+import numpy as np
+import pytest
+
+import mixemt_b200
+from mixemt_b200 import em, synth
+from mixemt_b200.preprocess import HapVarBaseMatrix, build_em_matrix, build_matrix_from_csr
+from mixemt_b200.runtime import DeviceMatrix, get_context
+from oracle import oracle_c, oracle_np
+from conftest import make_args, load_golden
+
+pytestmark = pytest.mark.gpu
+
+PROP_TOL = 1e-6
+
+
+def close_mix(a, b, tol=1e-9):
+    fin = np.isfinite(a) & np.isfinite(b)
+    same_inf = np.array_equal(np.isfinite(a), np.isfinite(b)) and \
+        np.array_equal(a[~fin], b[~fin])
+    return same_inf and (np.abs(a[fin] - b[fin]).max() if fin.any() else 0.0) < tol
+
+
+# ---- the reference's own tests (mixemt/test/em_test.py) ------------------------
+def test_init_props():
+    props = em.init_props(10)
+    assert len(props) == 10 and abs(props.sum() - 1.0) < 1e-9
+    assert np.array_equal(em.init_props(4, float("inf")), np.array([0.25] * 4))
+
+
+def test_converged():
+    prev = np.array([math.log(1.0)] * 10)
+    cur = np.array([math.log(2.0)] * 10)
+    assert em.converged(cur, cur) and em.converged(prev, prev)
+    assert not em.converged(prev, cur) and not em.converged(cur, prev)
+    close = np.array(cur)
+    close[3] = math.log(2.0001)
+    assert em.converged(cur, prev, 20.0)
+    assert not em.converged(cur, close)
+    assert em.converged(cur, close, 0.001)
+
+
+@pytest.mark.parametrize("wts,key", [([1, 1, 1], "step_w111"), ([2, 1, 1], "step_w211")])
+def test_em_step_simple(wts, key, golden_toy):
+    """em_test.py:35-65: identity-like 3 x 3 matrix of 0 / -inf."""
+    inf = float("inf")
+    in_mat = np.array([[0.0, -inf, -inf], [-inf, 0.0, -inf], [-inf, -inf, 0.0]])
+    props = np.log(np.array([0.6, 0.2, 0.2]))
+    mix_mat = np.empty_like(in_mat)
+    res_mat, res_props = em.em_step(in_mat, np.array(wts), props, mix_mat)
+    assert res_mat is mix_mat
+    assert np.all(in_mat == mix_mat)
+    want = np.log(np.array(wts, dtype=float) / sum(wts))
+    # the reference asserts exact equality; device log() is within 1 ulp of libm
+    assert np.abs(res_props - want).max() <= 2.3e-16
+    assert np.abs(res_props - golden_toy[key + "_props"]).max() <= 2.3e-16
+    assert np.array_equal(res_mat, golden_toy[key + "_mix"])
+
+
+def test_em_step_toy_golden(golden_toy):
+    mat = golden_toy["em_mat"]
+    mix = np.empty_like(mat)
+    res_mat, res_props = em.em_step(mat, np.arange(1, 11), golden_toy["step_toy_start"], mix)
+    assert np.abs(res_props - golden_toy["step_toy_props"]).max() < 1e-13
+    assert np.abs(res_mat - golden_toy["step_toy_mix"]).max() < 1e-13
+    # non-contiguous / wrong-dtype destination is still written in place
+    dest = np.zeros((10, 18))[:, ::2]
+    out, _ = em.em_step(mat, np.arange(1, 11), golden_toy["step_toy_start"], dest)
+    assert out is dest and np.array_equal(dest, res_mat)
+
+
+@pytest.mark.parametrize("n_multi", [1, 10])
+def test_em_runs_recover_truth(n_multi, golden_toy):
+    """em_test.py:104-116."""
+    mat = golden_toy["em_mat"]
+    true_props = np.array([0.0, 0.8, 0.0, 0.0, 0.2, 0.0, 0.0, 0.0, 0.0])
+    true_haps = np.full_like(mat, -np.inf)
+    true_haps[0:8, 1] = 0.0
+    true_haps[8:10, 4] = 0.0
+    props, read_mix = em.run_em(mat, np.ones(10), make_args(n_multi=n_multi))
+    assert np.allclose(props, true_props, atol=0.02)
+    assert np.allclose(np.exp(read_mix), np.exp(true_haps), atol=0.05)
+
+
+# ---- golden outputs of the reference -----------------------------------------------
+@pytest.mark.parametrize("n_multi", [1, 4, 10])
+def test_run_em_toy_golden(n_multi, golden_toy):
+    mat = golden_toy["em_mat"].copy()
+    before = mat.copy()
+    np.random.seed(int(golden_toy["run_%d_seed" % n_multi]))
+    props, read_mix = em.run_em(mat, np.ones(10), make_args(n_multi=n_multi))
+    assert np.array_equal(mat, before)                      # inputs untouched
+    assert props.shape == (9,) and read_mix.shape == (10, 9)
+    assert np.abs(props - golden_toy["run_%d_props" % n_multi]).max() < 1e-10
+    assert close_mix(read_mix, golden_toy["run_%d_mix" % n_multi])
+    if n_multi > 1:   # geometric mean of restarts is not renormalised
+        assert abs(props.sum() - golden_toy["run_%d_props" % n_multi].sum()) < 1e-12
+
+
+def test_run_em_iteration_counts(golden_toy, capsys):
+    """'Converged! (n)' lines carry the reference's iteration counts."""
+    import re
+    np.random.seed(int(golden_toy["run_10_seed"]))
+    em.run_em(golden_toy["em_mat"], np.ones(10), make_args(n_multi=10, verbose=True))
+    err = capsys.readouterr().err
+    its = [int(x) for x in re.findall(r"Converged! \((\d+)\)", err)]
+    assert its == golden_toy["run_10_iters"].tolist()
+    assert err.count("Starting EM run") == 10
+
+
+def test_run_em_exhausts_max_iter(golden_toy):
+    """for/else branch em.py:141-143 + uniform start (alpha = inf)."""
+    props, read_mix = em.run_em(golden_toy["em_mat"], np.arange(1, 11),
+                                make_args(init_alpha=float("inf"), max_iter=7))
+    assert np.abs(props - golden_toy["run_exhaust_props"]).max() < 1e-13
+    assert close_mix(read_mix, golden_toy["run_exhaust_mix"], 1e-12)
+
+
+def _em17_inputs(phylo17, gold, tag):
+    haps = sorted(phylo17.hap_var)
+    reads = str(gold[tag + "_reads"]).split("\n")
+    if tag == "b":
+        haps = [haps[j] for j in gold["b_cols"].tolist()]
+    mat = build_em_matrix(phylo17.refseq, phylo17, reads, haps, make_args())
+    return mat, gold[tag + "_weights"]
+
+
+def test_run_em_build17_full_width_trajectory(phylo17):
+    """192 signatures x 5408 haplotypes, 150 iterations from a seeded Dirichlet
+    start, never converging: the whole trajectory must track the reference
+    (fast TMA-ring kernel path, H >= 1024)."""
+    gold = load_golden("golden_em17.npz")
+    mat, wts = _em17_inputs(phylo17, gold, "a")
+    assert abs(mat.sum() - gold["a_mat_checksum"][0]) == 0.0
+    np.random.seed(int(gold["a_seed"]))
+    props, read_mix = em.run_em(mat, wts, make_args(max_iter=int(gold["a_max_iter"]),
+                                                    tolerance=float(gold["a_tol"])))
+    assert np.abs(props - gold["a_props"]).max() < 1e-12
+    assert close_mix(read_mix[:6], gold["a_mix_rows"])
+    assert np.array_equal(np.argmax(read_mix, 1), gold["a_argmax"])
+
+
+@pytest.mark.parametrize("tag,n_multi", [("b1", 1), ("b3", 3)])
+def test_run_em_build17_converged(phylo17, tag, n_multi, capsys):
+    """600 signatures x 512 haplotypes to convergence (general kernel path):
+    same iteration counts, proportions and assignments as the reference."""
+    import re
+    gold = load_golden("golden_em17.npz")
+    mat, wts = _em17_inputs(phylo17, gold, "b")
+    np.random.seed(int(gold[tag + "_seed"]))
+    props, read_mix = em.run_em(mat, wts, make_args(n_multi=n_multi, max_iter=5000, verbose=True))
+    its = [int(x) for x in re.findall(r"Converged! \((\d+)\)", capsys.readouterr().err)]
+    assert its == gold[tag + "_iters"].tolist()
+    assert np.abs(props - gold[tag + "_props"]).max() < 1e-9 < PROP_TOL
+    assert close_mix(read_mix[:6], gold[tag + "_mix_rows"])
+    assert np.array_equal(np.argmax(read_mix, 1), gold[tag + "_argmax"])
+
+
+# ---- against the oracle on seeded inputs ------------------------------------------
+def _random_problem(n, h, seed, spread=30.0):
+    rs = np.random.RandomState(seed)
+    mat = -rs.gamma(2.0, spread / 2.0, size=(n, h))
+    mat[rs.rand(n, h) < 0.3] = mat.max()             # ties at the row maximum
+    wts = rs.randint(1, 50, size=n)
+    inits = np.log(rs.dirichlet([1.0] * h, size=3))
+    return mat, wts, inits
+
+
+@pytest.mark.parametrize("n,h", [(1, 1), (7, 1), (5, 2), (64, 3), (300, 33), (257, 1023),
+                                 (100, 1024), (149, 1040), (500, 2049), (311, 5408),
+                                 (40, 8192), (33, 9000)])
+def test_run_em_vs_oracle_shapes(n, h):
+    """Every kernel path (general, TMA ring with NC = 1..8, wider than the ring)
+    and ragged shapes: H = 1, H not a multiple of the vector width, N smaller
+    than the grid."""
+    mat, wts, inits = _random_problem(n, h, seed=n * 7 + h)
+    ctx = get_context()
+    dev = DeviceMatrix.from_host(ctx, mat)
+    a = make_args(n_multi=3, max_iter=60, tolerance=1e-7)
+    props, read_mix, info, _ = em.run_em_device(dev, wts, a, inits=inits)
+    dev.free()
+    o_props, o_mix, o_iters = oracle_c.run_em(mat, wts, inits, 60, 1e-7)
+    assert info["iterations"] == o_iters
+    assert np.abs(props - o_props).max() < 1e-11
+    assert close_mix(read_mix, o_mix)
+
+
+def test_em_step_vs_numpy_oracle():
+    mat, wts, inits = _random_problem(50, 1500, seed=1)
+    mix = np.empty_like(mat)
+    _, new = em.em_step(mat, wts, inits[0], mix)
+    o_mix, o_new = oracle_np.em_step(mat, wts, inits[0])
+    assert np.abs(new - o_new).max() < 1e-12 and np.abs(mix - o_mix).max() < 1e-11
+
+
+def test_zero_weights_and_dead_columns():
+    """scipy drops zero-weight rows (_logsumexp.py:205-206); an all -inf column
+    gets proportion 0 and -inf log responsibilities."""
+    mat, wts, inits = _random_problem(40, 1200, seed=5)
+    wts = wts.astype(float)
+    wts[::3] = 0.0
+    mat[:, 7] = -np.inf
+    mat[3, :100] = -np.inf
+    o_props, o_mix, o_iters = oracle_c.run_em(mat, wts, inits[:1], 40, 1e-9)
+    ctx = get_context()
+    dev = DeviceMatrix.from_host(ctx, mat)
+    props, read_mix, info, _ = em.run_em_device(dev, wts, make_args(max_iter=40, tolerance=1e-9),
+                                                inits=inits[:1])
+    assert props[7] == 0.0 and np.all(np.isneginf(read_mix[:, 7]))
+    assert np.abs(props - o_props).max() < 1e-12 and close_mix(read_mix, o_mix)
+
+
+def test_dying_components_stay_in_log_space():
+    """A column that is never the best explanation decays geometrically; after
+    thousands of iterations its proportion underflows fp64 but its
+    log-proportion must keep tracking the reference."""
+    rs = np.random.RandomState(3)
+    n, h = 64, 1100
+    mat = np.full((n, h), -40.0)
+    mat[np.arange(n), rs.randint(0, 4, size=n)] = 0.0   # four live columns
+    mat[:, 10] = -3.0                                    # plausible but dominated
+    inits = np.log(np.full((1, h), 1.0 / h))
+    ctx = get_context()
+    dev = DeviceMatrix.from_host(ctx, mat)
+    a = make_args(max_iter=4000, tolerance=0.0)
+    props, read_mix, info, _ = em.run_em_device(dev, np.ones(n), a, inits=inits)
+    o_props, o_mix, _ = oracle_c.run_em(mat, np.ones(n), inits, 4000, 0.0)
+    assert np.abs(props - o_props).max() < 1e-12
+    fin = np.isfinite(o_mix)
+    assert o_mix[fin].min() < -800.0                     # far below exp() underflow
+    assert np.allclose(read_mix[fin], o_mix[fin], rtol=1e-9, atol=1e-9)
+
+
+# ---- size-independent properties at scale ------------------------------------------
+def test_properties_config1_shape(phylo17):
+    """Config-1 shape (10k fragments x 5408): proportions sum to 1, the true
+    contributors dominate, duplicating rows == doubling weights, and a row
+    permutation leaves the proportions unchanged."""
+    haps = sorted(phylo17.hap_var)
+    mix = synth.make_mixture(phylo17, phylo17.refseq, [("H1", 0.7), ("L3e", 0.3)], 10000, seed=1)
+    tables = HapVarBaseMatrix(phylo17.refseq, phylo17, haps).pack()
+    _, _, dmat, _ = build_matrix_from_csr(tables, mix.csr(tables), want_host=False,
+                                          keep_device=True)
+    inits = np.log(np.random.RandomState(0).dirichlet([1.0] * len(haps), size=1))
+    a = make_args(max_iter=300, tolerance=1e-4)
+    props, _, info, mix_dev = em.run_em_device(dmat, mix.weights, a, inits=inits,
+                                               keep_device=True, want_host=False)
+    assert abs(props.sum() - 1.0) < 1e-9
+    votes = np.bincount(mix_dev.argmax_rows(), weights=mix.weights, minlength=len(haps))
+    assert {haps[i].split('/')[0][:2] for i in np.argsort(votes)[::-1][:2]} <= {"H1", "L3", "H", "L"}
+    host = dmat.to_host()
+    perm = np.random.RandomState(1).permutation(host.shape[0])
+    d2 = DeviceMatrix.from_host(dmat.ctx, host[perm])
+    p2, _, _, _ = em.run_em_device(d2, mix.weights[perm], a, inits=inits, want_host=False)
+    assert np.abs(props - p2).max() < 1e-9
+    d3 = DeviceMatrix.from_host(dmat.ctx, np.concatenate([host, host[:1000]]))
+    w3 = np.concatenate([mix.weights, mix.weights[:1000]])
+    w4 = mix.weights.copy()
+    w4[:1000] *= 2
+    p3, _, _, _ = em.run_em_device(d3, w3, a, inits=inits, want_host=False)
+    p4, _, _, _ = em.run_em_device(dmat, w4, a, inits=inits, want_host=False)
+    assert np.abs(p3 - p4).max() < 1e-9
+    for d in (dmat, d2, d3, mix_dev):
+        d.free()
+
+
+def test_resident_matrix_reuse(phylo17):
+    """build_em_matrix(args.b200_resident) hands out a read-only array whose HBM
+    copy run_em reuses; results equal the plain host path."""
+    haps = sorted(phylo17.hap_var)
+    mix = synth.make_mixture(phylo17, phylo17.refseq, [("H1", 0.7), ("L3e", 0.3)], 500, seed=4)
+    a = make_args(max_iter=30, tolerance=1e-9, b200_resident=True)
+    mat = build_em_matrix(phylo17.refseq, phylo17, mix.signatures, haps, a)
+    assert not mat.flags.writeable
+    from mixemt_b200.runtime import lookup_resident
+    assert lookup_resident(mat) is not None
+    np.random.seed(3)
+    p1, m1 = em.run_em(mat, mix.weights, a)
+    np.random.seed(3)
+    p2, m2 = em.run_em(mat.copy(), mix.weights, a)
+    assert np.array_equal(p1, p2) and np.array_equal(m1, m2)
+
+
+def test_install_patches_reference_entry_points():
+    import types
+    fake = types.SimpleNamespace(preprocess=types.SimpleNamespace(build_em_matrix=None),
+                                 em=types.SimpleNamespace(run_em=None, em_step=None))
+    mixemt_b200.install(fake)
+    assert fake.preprocess.build_em_matrix is mixemt_b200.preprocess.build_em_matrix
+    assert fake.em.run_em is mixemt_b200.em.run_em and fake.em.em_step is mixemt_b200.em.em_step
