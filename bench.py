@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Benchmark of the mixemt hot path on B200 (contract: see DESIGN.md, Measurement).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --steps K --warmup W    # CPU reference arm
+
+A *step* is one EM iteration (E-step + M-step + convergence test) over the
+resident read-signature x haplotype matrix of BASELINE.json config 2: a 3-way
+synthetic mixture (H1 50% / L3e 30% / U5a1 20%), 1M fragments of 300 bp reduced
+to unique signatures, against all 5408 Phylotree Build 17 haplotypes.  Under
+torchrun every rank builds its own 1M-fragment shard (weak scaling) and the H
+column sums are all-reduced over NCCL once per iteration.
+
+One JSON line is printed by rank 0:
+  value     matrix cells per second through EM iterations, inputs resident in HBM
+  e2e       same metric through the drop-in call mixemt_b200.run_em(host ndarray,
+            weights, args) run to convergence with the reference's default
+            options: host->device copy of the matrix, all iterations, read-matrix
+            materialisation and the device->host copy of the N x H result inside
+            the timed region
+  roofline  the fused E/M pass kernel against the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle port (C + OpenMP, all host threads) on a row sample
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "em_matrix_cells_per_s"
+UNIT = "cells/s"
+MIXTURE = [("H1", 0.5), ("L3e", 0.3), ("U5a1", 0.2)]
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--fragments", type=int, default=1000000,
+                    help="fragments per GPU (config 2: 1M)")
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="row sample of the CPU legs (0 = auto)")
+    return ap.parse_args()
+
+
+def load_workload(fragments, seed, strings=False):
+    from mixemt_b200.phylo_tables import PhyloTables
+    from mixemt_b200 import synth
+    phylo = PhyloTables.load(os.path.join(GOLDEN, "phylotree17.npz"))
+    haps = sorted(phylo.hap_var)
+    mix = synth.make_mixture(phylo, phylo.refseq, MIXTURE, fragments, seed=seed, strings=strings)
+    return phylo, haps, mix
+
+
+def workload_name(fragments, n_rows, n_hap):
+    return ("config2: 3-way mixture H1/L3e/U5a1 50/30/20, %d fragments x 300bp -> %d unique "
+            "signatures x %d Phylotree-17 haplotypes (fp64 matrix %.2f GB)"
+            % (fragments, n_rows, n_hap, n_rows * n_hap * 8 / 1e9))
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler(object):
+    """Samples SM clock and throttle reasons of one GPU while a region runs."""
+
+    def __init__(self, index, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = [("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"),
+                 ("hw_power_brake", "nvmlClocksThrottleReasonHwPowerBrakeSlowdown")]
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for label, attr in names:
+                    bit = getattr(nv, attr, 0)
+                    if bit and (mask & bit):
+                        self.reasons.add(label)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the pass kernel from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------
+# CPU legs (the only places bench.py may touch oracle/)
+# ---------------------------------------------------------------------------
+def cpu_sample_matrix(rows, seed):
+    """A row sample of the config-2 matrix, built by the CPU oracle itself."""
+    from mixemt_b200.preprocess import HapVarBaseMatrix
+    from oracle import oracle_c
+    phylo, haps, mix = load_workload(max(4000, rows * 8), seed)
+    tables = HapVarBaseMatrix(phylo.refseq, phylo, haps).pack()
+    csr = mix.csr(tables)
+    rows = min(rows, csr.n_rows)
+    from mixemt_b200.preprocess import SignatureCSR
+    sub = SignatureCSR(csr.row_ptr[:rows + 1].copy(), csr.pos_idx[:csr.row_ptr[rows]],
+                       csr.base_code[:csr.row_ptr[rows]])
+    t0 = time.perf_counter()
+    mat, _ = oracle_c.build_matrix(tables, sub, want_counts=False)
+    build_s = time.perf_counter() - t0
+    return mat, mix.weights[:rows].astype(np.float64), len(haps), build_s
+
+
+def cpu_baseline_port(budget_s=15.0):
+    """C/OpenMP oracle em_step on a row sample, all host threads."""
+    from oracle import oracle_c
+    cores = os.cpu_count() or 1
+    rows = 2048
+    mat, wts, h, build_s = cpu_sample_matrix(rows, seed=2)
+    lnp = np.log(np.random.RandomState(0).dirichlet([1.0] * h))
+    oracle_c.em_step(mat, wts, lnp)  # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 20):
+        t0 = time.perf_counter()
+        oracle_c.em_step(mat, wts, lnp)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"value": mat.size / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle.c em_step (OpenMP, %d threads) on %d rows x %d haplotypes of the "
+                      "config-2 matrix, best of %d" % (cores, mat.shape[0], h, len(times)),
+            "build_cells_per_s": mat.size / build_s}
+
+
+def run_reference(opts):
+    """CPU reference arm: the reference is pure Python/numpy/scipy and is not
+    present on the GPU box, so its numpy restatement is timed -- em_step through
+    the same scipy.special.logsumexp call sites (em.py:82, :87-89), one core,
+    like the reference."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import scipy
+    from oracle import oracle_np
+    budget = 100.0
+    rows = opts.cpu_rows or 256
+    mat, wts, h, _ = cpu_sample_matrix(rows, seed=opts.seed)
+    lnp = np.log(np.random.RandomState(0).dirichlet([1.0] * h))
+    if not opts.cpu_rows:
+        t0 = time.perf_counter()
+        oracle_np.em_step_scipy(mat, wts, lnp, np.empty_like(mat))
+        per_row = (time.perf_counter() - t0) / mat.shape[0]
+        rows = int(max(128, min(8192, budget / ((opts.steps + opts.warmup) * per_row))))
+        mat, wts, h, _ = cpu_sample_matrix(rows, seed=opts.seed)
+    mix = np.empty_like(mat)
+    for _ in range(opts.warmup):
+        oracle_np.em_step_scipy(mat, wts, lnp, mix)
+    t0 = time.perf_counter()
+    for _ in range(opts.steps):
+        _, lnp_new = oracle_np.em_step_scipy(mat, wts, lnp, mix)
+    total = time.perf_counter() - t0
+    value = mat.size * opts.steps / total
+    sample = ("numpy/scipy restatement of em.em_step (oracle_np.em_step_scipy) on %d rows x %d "
+              "haplotypes of the config-2 matrix, numpy %s scipy %s, 1 thread"
+              % (mat.shape[0], h, np.__version__, scipy.__version__))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
+            "ms_per_step": 1e3 * total / opts.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config2: 3-way mixture H1/L3e/U5a1 50/30/20, 1M fragments x "
+                       "300bp x %d Phylotree-17 haplotypes [CPU arm: bounded sample of %d "
+                       "signature rows of it per step]" % (h, mat.shape[0])},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------
+def run_b200(opts):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import mixemt_b200
+    from mixemt_b200 import _lib, em as b200_em
+    from mixemt_b200._lib import lib, check, ptr
+    from mixemt_b200.preprocess import HapVarBaseMatrix, build_matrix_from_csr
+    from mixemt_b200.runtime import get_context
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    ctx = get_context()
+    if world > 1:
+        ctx.init_comm_from_torch()
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- workload: every rank its own shard -------------------------------------
+    phylo, haps, mix = load_workload(opts.fragments, opts.seed + rank)
+    tables = HapVarBaseMatrix(phylo.refseq, phylo, haps).pack()
+    csr = mix.csr(tables)
+    n, h = csr.n_rows, len(haps)
+    weights = mix.weights.astype(np.float64)
+    launches0 = ctx.launch_count
+
+    # ---- kernel 1: build (device resident) --------------------------------------
+    build_ms = []
+    dmat = None
+    for _ in range(3):
+        if dmat is not None:
+            dmat.free()
+        _, _, dmat, ms = build_matrix_from_csr(tables, csr, ctx=ctx, want_host=False,
+                                               keep_device=True)
+        build_ms.append(ms)
+    build_best = min(build_ms)
+
+    # ---- kernel 2: EM iterations, inputs resident -------------------------------
+    sess = ctypes.c_void_p()
+    check(lib.mxb_em_create(ctx.handle, dmat.handle, ptr(weights), 1 if world > 1 else 0,
+                            ctypes.byref(sess)))
+    lnp0 = np.log(np.random.RandomState(1).dirichlet([1.0] * h))
+    check(lib.mxb_em_set_lnprops(sess, ptr(lnp0)))
+    el, ps = ctypes.c_float(), ctypes.c_float()
+    if opts.warmup > 0:
+        check(lib.mxb_em_iterate_fixed(sess, opts.warmup, ctypes.byref(el), None))
+    peak, peak_src = measured_peak()
+    with ClockSampler(local) as clocks:
+        barrier()
+        l0 = ctx.launch_count
+        t0 = time.perf_counter()
+        check(lib.mxb_em_iterate_fixed(sess, opts.steps, ctypes.byref(el), None))
+        barrier()
+        wall = time.perf_counter() - t0
+        launches = ctx.launch_count - l0
+        dev_s = max_over_ranks(el.value / 1e3)
+        # the dominant kernel alone (event pair around every launch), rank-local
+        check(lib.mxb_em_iterate_fixed(sess, min(opts.steps, 100), ctypes.byref(el),
+                                       ctypes.byref(ps)))
+        pass_s = ps.value / 1e3 / min(opts.steps, 100)
+    cells_total = sum_over_ranks(float(n) * h)
+    value = cells_total * opts.steps / dev_s
+    lib.mxb_em_destroy(sess)
+
+    ld = ((h + 15) // 16) * 16
+    pass_bytes = float(n) * ld * 8
+    achieved = pass_bytes / pass_s / 1e9
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "em_pass_fast_kernel", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": pass_bytes,
+                "ms_per_launch": pass_s * 1e3,
+                "traffic": (traffic or {}).get("em_pass_fast_kernel_bytes_per_launch")}
+
+    # ---- e2e: the drop-in call with host buffers ---------------------------------
+    e2e = None
+    if not opts.no_e2e:
+        host = torch.empty((n, h), dtype=torch.float64, pin_memory=True).numpy()
+        dmat.to_host(out=host)
+        args = argparse.Namespace(verbose=False, init_alpha=1.0, tolerance=1e-4, max_iter=10000,
+                                  n_multi=1, b200_shard="rows" if world > 1 else None)
+        import io
+        import re
+        import contextlib
+        np.random.seed(opts.seed)
+        args.verbose = True
+        buf = io.StringIO()
+        with ClockSampler(local) as clocks_e2e:
+            barrier()
+            t0 = time.perf_counter()
+            with contextlib.redirect_stderr(buf):
+                props, read_mix = mixemt_b200.run_em(host, weights, args)
+            barrier()
+            e2e_s = max_over_ranks(time.perf_counter() - t0)
+        found = re.findall(r"Converged! \((\d+)\)", buf.getvalue())
+        iters = int(found[0]) if found else args.max_iter
+        top = np.argsort(props)[::-1][:3]
+        e2e = {"value": cells_total * iters / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": (host.nbytes + weights.nbytes + 8 * h) / iters,
+               "d2h_bytes_per_step": (read_mix.nbytes + 8 * h) / iters,
+               "call": "mixemt_b200.run_em(host ndarray, weights, args) to convergence "
+                       "(tolerance 1e-4, Dirichlet(1) start, seed %d)" % opts.seed,
+               "iterations": iters, "seconds": e2e_s,
+               "h2d_bytes": host.nbytes + weights.nbytes, "d2h_bytes": read_mix.nbytes,
+               "em_iters_per_s": iters / e2e_s,
+               "top_haplogroups": [[haps[i], float(props[i])] for i in top],
+               "clocks": clocks_e2e.summary()}
+        del host, read_mix
+    dmat.free()
+
+    cpu = None
+    if rank == 0 and world == 1 and not opts.no_cpu:
+        try:
+            cpu = cpu_baseline_port()
+        except Exception as exc:  # the baseline must not take the bench down
+            cpu = {"error": repr(exc)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": opts.steps, "warmup": opts.warmup,
+                "ms_per_step": 1e3 * dev_s / opts.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(opts.fragments, n, h),
+                           "rows_per_gpu": n, "haplotypes": h, "parallelism":
+                           "rows sharded x%d, ncclAllReduce(H fp64) per iteration" % world
+                           if world > 1 else "single GPU",
+                           "l2_policy": "input (%.2f GB) larger than L2, no flush needed"
+                           % (pass_bytes / 1e9)},
+                "em_iters_per_s": opts.steps / dev_s,
+                "wall_ms_per_step": 1e3 * wall / opts.steps,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks.summary(),
+                "build": {"ms": build_best, "cells_per_s": float(n) * h / (build_best / 1e3),
+                          "write_GBs": float(n) * h * 8 / (build_best / 1e3) / 1e9,
+                          "frac_of_hbm_peak": float(n) * h * 8 / (build_best / 1e3) / 1e9 / peak},
+                "versions": {"numpy": np.__version__, "torch": torch.__version__}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    opts = parse_args()
+    if opts.impl == "reference":
+        run_reference(opts)
+    else:
+        run_b200(opts)
+
+
+if __name__ == "__main__":
+    main()
