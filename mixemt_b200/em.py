@@ -13,6 +13,7 @@ import numpy
 
 from . import _lib
 from ._lib import lib, check, ptr
+from . import sharding
 from .runtime import DeviceMatrix, get_context, lookup_resident
 
 
@@ -99,7 +100,7 @@ def run_em_device(dev_mat, weights, args, keep_device=False, want_host=True, ini
         ctx.init_comm_from_torch()
         if ctx.world > 1:
             flags |= _lib.MXB_EM_RAW
-            mine = list(range(ctx.rank, n_multi, ctx.world))
+            mine = sharding.restart_shard(n_multi, ctx.rank, ctx.world)
 
     props = numpy.zeros(h)
     iters = numpy.zeros(max(1, len(mine)), dtype=numpy.int64)
@@ -121,8 +122,7 @@ def run_em_device(dev_mat, weights, args, keep_device=False, want_host=True, ini
         if mix_dev is None:
             # no restart landed on this rank: neutral element of logaddexp
             mix_dev = DeviceMatrix.from_host(ctx, numpy.full((n, h), -numpy.inf))
-        ctx.allreduce_host(props, "sum")
-        props = numpy.exp(props / n_multi if n_multi > 1 else props)
+        props = sharding.combine_restart_props(props, n_multi, ctx.allreduce_host)
         mix_dev.fold_ranks(numpy.log(n_multi) if n_multi > 1 else 0.0)
         if want_host:
             read_mix = mix_dev.to_host()

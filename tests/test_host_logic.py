@@ -1,0 +1,141 @@
+"""Host-side logic that needs no GPU: signature parsing (C), table packing,
+the synthetic generator, and the Build-17 fixture."""
+import collections
+
+import numpy as np
+import pytest
+
+from mixemt_b200 import synth
+from mixemt_b200.preprocess import (HapVarBaseMatrix, parse_signatures, pos_from_var, der_allele)
+from oracle import oracle_np
+
+
+def py_pos_obs(sig):
+    """What preprocess.pos_obs_from_sig (reference :151-160) returns."""
+    out = []
+    for var in sig.split(','):
+        pos, obs = var.split(':')
+        out.append((int(pos), obs))
+    return out
+
+
+def test_variant_string_helpers():
+    for var, pos, der in [("A73G", 72, "G"), ("(C16519T)", 16518, "T"), ("T152C!", 151, "C"),
+                          ("(T195C!)", 194, "C"), ("G1438a", 1437, "A"), ("C150T!!", 149, "T")]:
+        assert pos_from_var(var) == pos and der_allele(var) == der
+        assert oracle_np.variant_pos(var) == pos and oracle_np.variant_der(var) == der
+
+
+def test_markers_match_reference_unit_test(toy_phylo):
+    """reference preprocess_test.py:34-53."""
+    hvb = HapVarBaseMatrix("AAAAAAAAA", toy_phylo, mut_wt=0.02, mut_max=0.6)
+    markers = {'A': {1: 'T', 3: 'T', 0: 'G'},
+               'B': {0: 'G', 2: 'T', 4: 'T', 5: 'T', 7: 'T'},
+               'C': {0: 'G', 2: 'T', 5: 'T'},
+               'D': {0: 'G', 2: 'T', 4: 'T', 6: 'T', 8: 'T'},
+               'E': {0: 'G', 2: 'T', 3: 'T', 4: 'T', 6: 'T'},
+               'F': {0: 'G', 2: 'T', 4: 'T', 5: 'T'},
+               'G': {0: 'G', 2: 'T', 4: 'T', 6: 'T'},
+               'H': {0: 'G', 2: 'T', 4: 'T'},
+               'I': {0: 'G'}}
+    assert hvb.markers == markers
+    assert hvb.markers == oracle_np.marker_table(toy_phylo, "AAAAAAAAA")
+
+
+def test_probs_match_reference_unit_tests(toy_phylo):
+    """reference preprocess_test.py:55-79."""
+    hvb = HapVarBaseMatrix("AAAAAAAAA", toy_phylo, mut_wt=0.10, mut_max=0.50)
+    assert hvb._prob(hvb.markers['I'], 0, 'G') == 1.0 - 0.1
+    assert hvb._prob(hvb.markers['I'], 4, 'A') == 1.0 - 0.2
+    assert hvb._prob(hvb.markers['I'], 0, 'A') == 0.1 / 3.0
+    assert hvb._prob(hvb.markers['I'], 4, 'T') == 0.2 / 3.0
+
+
+def test_pack_tables(toy_phylo):
+    t = HapVarBaseMatrix("AAAAAAAAA", toy_phylo, list("ABCDEFGHI")).pack()
+    assert t.positions.tolist() == list(range(9)) and t.n_hap == 9 and t.n_pos == 9
+    assert t.symbols == ['A', 'G', 'T']
+    assert t.sym2code[ord('A')] == 0 and t.sym2code[ord('T')] == 2 and t.sym2code[ord('C')] == 255
+    assert np.array_equal(t.hit[:2], np.log([0.99, 0.99]))      # one mutation each
+    assert t.miss[3] == np.log(0.02 / 3.0)                      # A4T occurs twice
+    assert int(t.marker_ptr[-1]) == sum(len(m) for m in t.markers.values())
+
+
+def test_pack_keeps_phylo_counts_as_is(toy_phylo):
+    """ignore_sites doubles the counts; the tables must follow
+    phylo.variants, never recount from the tree."""
+    doubled = type(toy_phylo)({p: collections.Counter({b: 2 * c for b, c in cnt.items()})
+                               for p, cnt in toy_phylo.variants.items()},
+                              toy_phylo.hap_var, toy_phylo.refseq)
+    a = HapVarBaseMatrix("AAAAAAAAA", toy_phylo, list("ABC")).pack()
+    b = HapVarBaseMatrix("AAAAAAAAA", doubled, list("ABC")).pack()
+    assert np.allclose(np.exp(b.miss) * 3, 2 * np.exp(a.miss) * 3)
+
+
+def test_unknown_haplogroup_is_a_keyerror(toy_phylo):
+    with pytest.raises(KeyError):
+        HapVarBaseMatrix("AAAAAAAAA", toy_phylo, ["A", "nope"]).pack()
+
+
+@pytest.mark.parametrize("sig", ["1:A,2:T,3:A", "9:G", " 4 :T,5:AC,6:", "+7:a,1_0:T"])
+def test_parse_matches_python(toy_phylo, sig):
+    variants = dict(toy_phylo.variants)
+    variants[9] = collections.Counter("A")
+    variants[10] = collections.Counter("C")
+    phylo = type(toy_phylo)(variants, toy_phylo.hap_var, "AAAAAAAAAAAA")
+    t = HapVarBaseMatrix("AAAAAAAAAAAA", phylo, list("ABCDEFGHI")).pack()
+    csr, err = parse_signatures([sig], t)
+    assert err is None
+    want = py_pos_obs(sig)
+    assert csr.row_ptr.tolist() == [0, len(want)]
+    assert [int(t.positions[i]) for i in csr.pos_idx] == [p for p, _ in want]
+    for code, (_, obs) in zip(csr.base_code.tolist(), want):
+        assert (t.symbols[code] if code != 255 else None) == (obs if obs in t.symbols else None)
+
+
+@pytest.mark.parametrize("sig", ["", "1A", "1:A:C", "1:A,,2:T", "x:A", "1 2:A", "1:A,", "1__0:A",
+                                 "_1:A", "1_:A"])
+def test_parse_malformed_is_valueerror_like_python(toy_phylo, sig):
+    t = HapVarBaseMatrix("AAAAAAAAA", toy_phylo, list("ABC")).pack()
+    with pytest.raises(ValueError):
+        py_pos_obs(sig)
+    _, err = parse_signatures(["1:A", sig, "77:A"], t)
+    assert err == (1, "value", None)
+
+
+def test_parse_error_order(toy_phylo):
+    t = HapVarBaseMatrix("AAAAAAAAA", toy_phylo, list("ABC")).pack()
+    assert parse_signatures(["1:A", "77:A", "bad"], t)[1] == (1, "key", 77)
+    assert parse_signatures(["1:A", "2:T,-3:A"], t)[1] == (1, "key", -3)
+    assert parse_signatures(["1:A", "99999999999:T"], t)[1][:2] == (1, "key")
+    # a malformed field later in the same row still wins (whole row is parsed first)
+    assert parse_signatures(["77:A,oops"], t)[1] == (0, "value", None)
+    many = ["1:A"] * 5000 + ["5:T,66:A"] + ["1:A"] * 5000 + ["zzz"]
+    assert parse_signatures(many, t)[1] == (5000, "key", 66)
+
+
+def test_fixture_has_build17_shape(phylo17, phylo17_cfg5):
+    assert len(phylo17.hap_var) == 5408 and len(phylo17.variants) == 4070
+    assert len(phylo17.refseq) == 16569
+    for hap in ("H1", "L3e", "U5a1", "M7", "D4a"):
+        assert hap in phylo17.hap_var
+    t = HapVarBaseMatrix(phylo17.refseq, phylo17, sorted(phylo17.hap_var)).pack()
+    assert t.symbols == ['A', 'C', 'G', 'T'] and int(t.marker_ptr[-1]) == 263826
+    assert len(set(np.round(np.exp(t.miss) * 3, 12))) == 44        # 44 distinct mut_prob
+    assert len(phylo17_cfg5.variants) < 4070 and "custom_hap1" in phylo17_cfg5.hap_var
+
+
+def test_synth_is_deterministic_and_well_formed(phylo17):
+    a = synth.make_mixture(phylo17, phylo17.refseq, [("H1", 0.7), ("L3e", 0.3)], 3000, seed=1)
+    b = synth.make_mixture(phylo17, phylo17.refseq, [("H1", 0.7), ("L3e", 0.3)], 3000, seed=1)
+    assert a.signatures == b.signatures and np.array_equal(a.weights, b.weights)
+    assert a.signatures == sorted(a.signatures) and len(set(a.signatures)) == a.n_rows
+    assert a.weights.sum() <= 3000 and a.weights.min() >= 1
+    t = HapVarBaseMatrix(phylo17.refseq, phylo17, ["H1", "L3e"]).pack()
+    csr, err = parse_signatures(a.signatures, t)
+    direct = a.csr(t)
+    assert err is None and np.array_equal(csr.row_ptr, direct.row_ptr)
+    assert np.array_equal(csr.pos_idx, direct.pos_idx)
+    assert np.array_equal(csr.base_code, direct.base_code)
+    k = np.diff(csr.row_ptr)
+    assert 10 <= k.min() and k.max() <= 200 and 60 < k.mean() < 100
