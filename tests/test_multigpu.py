@@ -1,0 +1,20 @@
+"""Runs tests/multigpu_check.py under torchrun on 2 GPUs when the box has them."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_two_gpu_rows_and_restarts():
+    from mixemt_b200 import _lib
+    if _lib.lib.mxb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29517",
+           os.path.join(ROOT, "tests", "multigpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and "MULTIGPU_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
