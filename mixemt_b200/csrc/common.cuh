@@ -72,6 +72,11 @@ struct mxb_phylo {
     int32_t n_words = 0;   // 32-bit words per plane (padded to a multiple of 4)
     uint32_t *bits = nullptr;   // [n_pos][n_sym+1][n_words]
     double2 *hitmiss = nullptr; // [n_pos] (hit, miss)
+    // sparse deviation form of `bits` (see build.cu)
+    uint8_t *ref_code = nullptr;  // [n_pos]
+    int32_t *dev_ptr = nullptr;   // [n_pos * (n_sym+1) + 1]
+    uint2 *dev_ent = nullptr;     // {word index, D}
+    int64_t n_dev = 0;
 };
 
 namespace mxb {

@@ -34,6 +34,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <vector>
 
@@ -559,6 +560,24 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
     return MXB_OK;
 }
 
+// MXB_TIMING=1: wall-clock stage times of the one-call entry points on stderr.
+struct StageTimer {
+    bool on;
+    cudaStream_t stream;
+    std::chrono::steady_clock::time_point t;
+    explicit StageTimer(cudaStream_t s) : on(getenv("MXB_TIMING") != nullptr), stream(s) {
+        if (on) t = std::chrono::steady_clock::now();
+    }
+    void mark(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(stream);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mxb timing] %-28s %9.3f ms\n", what,
+                std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 static int reset_state(mxb_em *em, long long max_iter, double tol) {
     EmState st;
     memset(&st, 0, sizeof(st));
@@ -873,13 +892,17 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
     mxb_em *em = nullptr;
     mxb_matrix *mix = nullptr;
     std::vector<double> acc((size_t)h, 0.0), cur((size_t)h);
+    StageTimer tm(ctx->stream);
     int rc = mxb_em_create(ctx, m, weights, (flags & MXB_EM_SHARDED) != 0, &em);
+    tm.mark("em_create (alloc+to_linear)");
     if (rc == MXB_OK && want_mix) rc = mxb_matrix_alloc(ctx, m->n_rows, h, &mix);
+    tm.mark("alloc read_mix");
     for (int32_t i = 0; rc == MXB_OK && i < n_multi; ++i) {
         int64_t iters = 0;
         int32_t conv = 0;
         rc = mxb_em_set_lnprops(em, init_lnprops + (size_t)i * h);
         if (rc == MXB_OK) rc = mxb_em_iterate(em, max_iter, tol, &iters, &conv);
+        tm.mark("iterate");
         if (iters_out) iters_out[i] = iters;
         if (converged_out) converged_out[i] = conv;
         if (rc == MXB_OK) rc = mxb_em_get_lnprops(em, 0, cur.data());
@@ -892,6 +915,7 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
             const bool last = (i == n_multi - 1);
             const double sub = (last && n_multi > 1 && !raw) ? log((double)n_multi) : 0.0;
             rc = mxb_em_read_mix(em, mix, i == 0 ? 0 : 1, sub);
+            tm.mark("read_mix kernel");
         }
     }
     if (rc == MXB_OK) {
@@ -903,7 +927,7 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
             }
             props_out[j] = v;
         }
-        if (read_mix_out) rc = mxb_matrix_download(ctx, mix, read_mix_out);
+        if (read_mix_out) { rc = mxb_matrix_download(ctx, mix, read_mix_out); tm.mark("download read_mix"); }
         else if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
             set_error("mxb_run_em: stream sync failed");
             rc = MXB_ERR_CUDA;
@@ -912,6 +936,7 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
     mxb_em_destroy(em);
     if (rc == MXB_OK && read_mix_dev) *read_mix_dev = mix;
     else mxb_matrix_destroy(mix);
+    tm.mark("free");
     return rc;
 }
 

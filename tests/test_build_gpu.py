@@ -150,3 +150,46 @@ def test_verbose_messages(toy_phylo, capsys):
     build_em_matrix("AAAAAAAAA", toy_phylo, reads, list("ABCDEFGHI"), make_args(verbose=True))
     err = capsys.readouterr().err
     assert err.startswith("Building EM input matrix...\n") and err.endswith("Done.\n\n")
+
+
+def test_build_class_kernel_equals_dense_kernel(phylo17, monkeypatch):
+    """The class kernel (shared chains, sparse deviation lists) and the plain
+    dense kernel (MXB_BUILD_DENSE=1) produce the same bits; noisy reads with
+    unknown bases exercise non-reference observations."""
+    haps = sorted(phylo17.hap_var)
+    mix = synth.make_mixture(phylo17, phylo17.refseq,
+                             [("H1", 0.4), ("L3e", 0.3), ("U5a1", 0.2), ("M7", 0.1)], 1500,
+                             err=0.04, seed=21)
+    tables = HapVarBaseMatrix(phylo17.refseq, phylo17, haps).pack()
+    csr = mix.csr(tables)
+    csr.base_code = csr.base_code.copy()
+    csr.base_code[::37] = 255          # bases outside the alphabet never match
+    mat, cnt, _, _ = build_matrix_from_csr(tables, csr, want_counts=True)
+    mat_nc, _, _, _ = build_matrix_from_csr(tables, csr, want_counts=False)
+    monkeypatch.setenv("MXB_BUILD_DENSE", "1")
+    d_mat, d_cnt, _, _ = build_matrix_from_csr(tables, csr, want_counts=True)
+    monkeypatch.delenv("MXB_BUILD_DENSE")
+    o_mat, o_cnt = oracle_c.build_matrix(tables, csr)
+    assert np.array_equal(mat, o_mat) and np.array_equal(cnt, o_cnt)
+    assert np.array_equal(mat_nc, o_mat)
+    assert np.array_equal(d_mat, o_mat) and np.array_equal(d_cnt, o_cnt)
+
+
+def test_build_unsorted_and_repeated_positions(phylo17):
+    """Signature order is the summation order (preprocess.py:92-95): shuffled
+    and repeated positions must give the reference's sums, not a sorted sum."""
+    haps = sorted(phylo17.hap_var)
+    positions = sorted(phylo17.variants)
+    rs = np.random.RandomState(5)
+    reads = []
+    for _ in range(64):
+        start = rs.randint(0, len(positions) - 120)
+        pick = rs.permutation(np.arange(start, start + 120))[:rs.randint(1, 100)]
+        pick = np.concatenate([pick, pick[:rs.randint(0, 4)]])     # repeats
+        reads.append(",".join("%d:%s" % (positions[i], "ACGT"[rs.randint(4)]) for i in pick))
+    mat = build_em_matrix(phylo17.refseq, phylo17, reads, haps, make_args())
+    tables = HapVarBaseMatrix(phylo17.refseq, phylo17, haps).pack()
+    csr, err = parse_signatures(reads, tables)
+    assert err is None
+    o_mat, _ = oracle_c.build_matrix(tables, csr)
+    assert np.array_equal(mat, o_mat)
