@@ -29,25 +29,33 @@
 // classes, so the class kernel evaluates ~12x fewer dependent-add chains than
 // cells, each about half as long.
 //
-// build_matrix_kernel (class kernel), one CTA (512 threads) per row at a time:
-//   0. stage the row: per observation (base term, deviating term), the range
-//      of its sparse deviation list, whether the marker-free outcome is a match;
-//   1. one thread forms the marker-free prefix sums P[0..K] (and match counts)
-//      while the other warps scatter the row's deviation entries into
-//      per-group lists in shared memory (shared-memory atomics);
-//   2. one warp per 32-column group: sort the group's (k, D) entries by k, give
-//      every lane its pattern over them, find the distinct patterns with
-//      match.any and allocate one chain item per distinct non-empty pattern;
-//   3. one thread per chain item: start at P[k0], add the remaining terms in
-//      order, taking the deviating term where the pattern says so;
+// build_matrix_kernel (class kernel), one CTA per row at a time:
+//   0. stage the row: per observation k the (marker-free, deviating) term pair,
+//      its (position, symbol) plane and whether the marker-free outcome matches;
+//   1. the last warp forms the marker-free prefix sums P[0..K] (one dependent
+//      chain) while the other warps collect the row's deviation entries per
+//      32-column group: a first walk over the sparse lists sets bit k in the
+//      group's observation bitmap (shared-memory atomicOr), a scan of the
+//      popcounts sizes the groups, and a second walk drops every (k, D) at
+//      offset[group] + rank of k in the bitmap -- sorted by k without a sort;
+//   2. one warp per group: every lane reads its pattern over the group's
+//      entries (bit e = "deviates at the e-th deviating observation"),
+//      match.any finds the distinct patterns and one chain item is allocated
+//      per distinct non-empty pattern; a cell remembers its class within the group;
+//   3. one thread per chain item: start at P[k0] of the first deviation, add the
+//      remaining terms in order, taking the deviating term where the pattern
+//      says so (next set bit = next deviating observation);
 //   4. every cell looks up the value of its class and the row is written with
 //      coalesced 16-byte stores.
-// Rows or groups that exceed the shared-memory budgets (K > 512 observations,
-// more than 16 deviating positions in a group, more than 2048 chains in a row)
-// take the dense path: build_dense_row / the per-group dense loop walk the
-// dense bitset table cell by cell, exactly like build_matrix_dense_kernel, the
-// plain kernel that is also used when H is too large for the class kernel's
-// shared-memory layout (or MXB_BUILD_DENSE=1 is set).
+// Two launches share the code: tier 1 (256 threads, 38 KB of shared memory, 5
+// CTAs per SM) takes rows with <= 256 observations, <= 1536 deviation entries
+// and <= 1024 chains (94 % of the config-2 rows); rows beyond that are queued
+// on the device and re-run by tier 2 (512 threads, 8192 entries, 4096 chains).
+// What exceeds tier 2 as well (K > 512, or a group with more than 32 deviating
+// observations) walks the dense bitset table cell by cell: build_dense_row /
+// the per-group dense loop, the same arithmetic as build_matrix_dense_kernel,
+// the plain kernel that is also used when H is too large for the class
+// kernel's shared-memory layout (or MXB_BUILD_DENSE=1 is set).
 #include <new>
 #include <vector>
 
@@ -55,19 +63,16 @@
 
 namespace mxb {
 
-constexpr int kBuildThreads = 512;
-constexpr int kBuildWarps = kBuildThreads / 32;
+constexpr int kBuildThreads = 512;   // dense kernel
 constexpr int kBuildCols = 4;        // dense path: haplotype columns per thread and group
-constexpr int kBuildObsChunk = 512;  // observations staged per pass (dense path), KMAX (class path)
-constexpr int kGroupCap = 16;        // deviating observations kept per 32-column group
-constexpr int kMaxItems = 2048;      // chain items per row
-constexpr unsigned kNoItem = 0xFFFFu;
+constexpr int kBuildObsChunk = 512;  // observations staged per pass (dense path)
 
 // ---- dense path ---------------------------------------------------------------
 // One CTA walks one row; a thread owns 4 haplotype columns per 2048-column
 // group (same bit lane, 4 different words), so every bitset load is
 // warp-uniform and the four accumulation chains are independent.
-__device__ __forceinline__ void build_dense_row(
+template <int kThreads>
+__device__ __noinline__ void build_dense_row(
         const uint32_t *__restrict__ bits, const double2 *__restrict__ hitmiss, int n_planes,
         int n_words, int n_hap, int64_t k0, int64_t k1, const int32_t *__restrict__ pos_idx,
         const uint8_t *__restrict__ base_code, double *__restrict__ out_row,
@@ -75,13 +80,13 @@ __device__ __forceinline__ void build_dense_row(
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    constexpr int kGroup = kBuildThreads * kBuildCols;
-    constexpr int kWordsPerSlot = kBuildThreads / 32;
+    constexpr int kGroup = kThreads * kBuildCols;
+    constexpr int kWordsPerSlot = kThreads / 32;
 
     for (int64_t kc = k0; kc < k1 || kc == k0; kc += kBuildObsChunk) {
         const int n_obs = (int)min((int64_t)kBuildObsChunk, k1 - kc);
         __syncthreads();  // previous users of s_hm / s_off are done
-        for (int k = tid; k < n_obs; k += kBuildThreads) {
+        for (int k = tid; k < n_obs; k += kThreads) {
             const int p = pos_idx[kc + k];
             int c = base_code[kc + k];
             if (c >= n_planes - 1) c = n_planes - 1;  // "other": all-zero plane
@@ -97,7 +102,7 @@ __device__ __forceinline__ void build_dense_row(
             const int word0 = (g0 >> 5) + warp;
 #pragma unroll
             for (int u = 0; u < kBuildCols; ++u) {
-                const int j = g0 + u * kBuildThreads + tid;
+                const int j = g0 + u * kThreads + tid;
                 acc[u] = 0.0;
                 cnt[u] = 0;
                 if (!first && j < n_hap) {
@@ -124,7 +129,7 @@ __device__ __forceinline__ void build_dense_row(
             }
 #pragma unroll
             for (int u = 0; u < kBuildCols; ++u) {
-                const int j = g0 + u * kBuildThreads + tid;
+                const int j = g0 + u * kThreads + tid;
                 if (j < n_hap) {
                     out_row[j] = acc[u];
                     if (match_row) match_row[j] = cnt[u];
@@ -145,7 +150,7 @@ build_matrix_dense_kernel(const uint32_t *__restrict__ bits, const double2 *__re
     __shared__ double2 s_hm[kBuildObsChunk];
     __shared__ uint32_t s_off[kBuildObsChunk];
     for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
-        build_dense_row(bits, hitmiss, n_planes, n_words, n_hap, row_ptr[row], row_ptr[row + 1],
+        build_dense_row<kBuildThreads>(bits, hitmiss, n_planes, n_words, n_hap, row_ptr[row], row_ptr[row + 1],
                         pos_idx, base_code, out + row * (int64_t)n_hap,
                         match_out ? match_out + row * (int64_t)n_hap : nullptr, s_hm, s_off);
     }
@@ -161,90 +166,144 @@ struct BuildTables {
     int n_planes, n_words, n_hap, n_groups;
 };
 
+constexpr int kMaxObs = 512;         // observations per row (longer rows: dense path)
+constexpr unsigned kDenseGroup = 0xFFFFu;
+static_assert(kMaxObs == kBuildObsChunk, "the dense row path reuses the class kernel's staging area");
+
+// Pool sizes of the two launches: tier 1 serves the common rows at 5 CTAs/SM,
+// tier 2 re-runs the few rows that overflowed tier 1's pools with larger ones.
+// kObsWords * 32 = observations per row the tier accepts.
+struct Tier1 {
+    static constexpr int kThreads = 256, kEntries = 1536, kItems = 1024, kObsWords = 8, kMinBlocks = 5;
+};
+struct Tier2 {
+    static constexpr int kThreads = 512, kEntries = 8192, kItems = 4096, kObsWords = 16, kMinBlocks = 2;
+};
+static_assert(Tier2::kObsWords * 32 == kMaxObs, "tier 2 takes every row the staging area holds");
+
 // Shared-memory layout of the class kernel (bytes), shared by host and device.
 struct BuildSmem {
-    size_t term, prefix, range, off, pcnt, gcnt, glist, cell, item, icnt, total;
-    __host__ __device__ BuildSmem(int n_groups, bool counts) {
+    size_t term, prefix, item, ew, plane, gmap, gcnt, goff, icnt, ek, pcnt, gbase, cell, total;
+    __host__ __device__ BuildSmem(int n_groups, bool counts, int n_entries, int n_items,
+                                  int obs_words) {
+        const int n_obs = obs_words * 32;
         size_t o = 0;
-        term = o;   o += sizeof(double2) * kBuildObsChunk;          // (base, deviating) terms
-        prefix = o; o += sizeof(double) * (kBuildObsChunk + 1);     // marker-free prefix sums
-        glist = o;  o += sizeof(uint2) * (size_t)kGroupCap * n_groups;  // per-group (k, D)
-        item = o;   o += sizeof(uint2) * kMaxItems;                 // (pattern, group) -> value
-        range = o;  o += sizeof(int2) * kBuildObsChunk;             // sparse list range per k
-        off = o;    o += sizeof(uint32_t) * kBuildObsChunk;         // dense plane offset per k
-        gcnt = o;   o += sizeof(int) * (size_t)n_groups;            // entries per group
-        icnt = o;   o += counts ? sizeof(int) * kMaxItems : 0;      // match count per item
-        pcnt = o;   o += sizeof(uint16_t) * (kBuildObsChunk + 2);   // marker-free match prefix
-        cell = o;   o += sizeof(uint16_t) * (size_t)n_groups * 32;  // item of every cell
+        term = o;   o += sizeof(double2) * n_obs;                // (marker-free, deviating) terms
+        prefix = o; o += sizeof(double) * (n_obs + 1);           // marker-free prefix sums
+        item = o;   o += sizeof(uint2) * n_items;                // (pattern, group) -> value
+        ew = o;     o += sizeof(uint32_t) * (n_entries > n_obs ? n_entries : n_obs);  // entry pool: D words
+        plane = o;  o += sizeof(int) * n_obs;                    // (position, symbol) plane per k
+        gmap = o;   o += sizeof(uint32_t) * (size_t)n_groups * obs_words;  // deviating k per group
+        gcnt = o;   o += sizeof(int) * (size_t)n_groups;         // entries per group
+        goff = o;   o += sizeof(int) * (size_t)n_groups;         // pool offset of the group
+        icnt = o;   o += counts ? sizeof(int) * n_items : 0;     // match count per item
+        ek = o;     o += sizeof(uint16_t) * n_entries;           // entry pool: observation index
+        pcnt = o;   o += sizeof(uint16_t) * (n_obs + 2);         // marker-free match prefix
+        gbase = o;  o += sizeof(uint16_t) * (size_t)n_groups;    // first item of the group
+        cell = o;   o += (size_t)n_groups * 32;                  // class of the cell in its group
         total = (o + 15) & ~(size_t)15;
     }
 };
 
-template <bool kCounts>
-__global__ void __launch_bounds__(kBuildThreads)
-build_matrix_kernel(BuildTables tb, int64_t n_rows, const int64_t *__restrict__ row_ptr,
+// Barrier among the scatter/classify warps only (all but the last warp, which
+// runs the prefix chain meanwhile).
+template <int kWorkThreads>
+__device__ __forceinline__ void work_warps_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");
+}
+
+
+// Rows come from row_list[0 .. *n_list) when row_list != NULL, else 0 .. n_rows.
+// Rows that do not fit the pools are appended to overflow_list when there is
+// one (tier 1), else they take the dense path (tier 2).
+template <bool kCounts, class Tier>
+__global__ void __launch_bounds__(Tier::kThreads, kCounts ? 1 : Tier::kMinBlocks)
+build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ row_list,
+                    const int *__restrict__ n_list, int32_t *__restrict__ overflow_list,
+                    int *__restrict__ overflow_count, const int64_t *__restrict__ row_ptr,
                     const int32_t *__restrict__ pos_idx, const uint8_t *__restrict__ base_code,
                     double *__restrict__ out, int32_t *__restrict__ match_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_nitems;
     __shared__ int s_overflow;
-    const BuildSmem L(tb.n_groups, kCounts);
+    constexpr int W = Tier::kObsWords;
+    constexpr int kClassThreads = Tier::kThreads;
+    constexpr int kClassWarps = kClassThreads / 32;
+    constexpr int kWorkWarps = kClassWarps - 1;  // the last warp runs the prefix chain
+    __shared__ int s_ndense;
+    const BuildSmem L(tb.n_groups, kCounts, Tier::kEntries, Tier::kItems, W);
     double2 *s_term = reinterpret_cast<double2 *>(smem + L.term);
     double *s_prefix = reinterpret_cast<double *>(smem + L.prefix);
-    uint2 *s_glist = reinterpret_cast<uint2 *>(smem + L.glist);
     uint2 *s_item = reinterpret_cast<uint2 *>(smem + L.item);
     double *s_val = reinterpret_cast<double *>(smem + L.item);  // overwrites the item
-    int2 *s_range = reinterpret_cast<int2 *>(smem + L.range);
-    uint32_t *s_off = reinterpret_cast<uint32_t *>(smem + L.off);
+    uint32_t *s_ew = reinterpret_cast<uint32_t *>(smem + L.ew);
+    int *s_plane = reinterpret_cast<int *>(smem + L.plane);
+    uint32_t *s_gmap = reinterpret_cast<uint32_t *>(smem + L.gmap);
     int *s_gcnt = reinterpret_cast<int *>(smem + L.gcnt);
+    int *s_goff = reinterpret_cast<int *>(smem + L.goff);
     int *s_icnt = reinterpret_cast<int *>(smem + L.icnt);
+    uint16_t *s_ek = reinterpret_cast<uint16_t *>(smem + L.ek);
     uint16_t *s_pcnt = reinterpret_cast<uint16_t *>(smem + L.pcnt);
-    uint16_t *s_cell = reinterpret_cast<uint16_t *>(smem + L.cell);
+    uint16_t *s_gbase = reinterpret_cast<uint16_t *>(smem + L.gbase);
+    uint8_t *s_cell = reinterpret_cast<uint8_t *>(smem + L.cell);
+    // the dense row path reuses the staging areas: (hit, miss) and plane offsets
+    uint32_t *s_off = reinterpret_cast<uint32_t *>(smem + L.ew);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int n_hap = tb.n_hap;
     const int n_groups = tb.n_groups;
+    const int64_t n_work = row_list ? (int64_t)*n_list : n_rows;
 
-    for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    for (int64_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int64_t row = row_list ? (int64_t)row_list[wi] : wi;
         const int64_t k0 = row_ptr[row];
         const int64_t k1 = row_ptr[row + 1];
         double *out_row = out + row * (int64_t)n_hap;
         int32_t *match_row = kCounts ? match_out + row * (int64_t)n_hap : nullptr;
-        if (k1 - k0 > kBuildObsChunk) {  // block-uniform: long rows go dense
-            build_dense_row(tb.bits, tb.hitmiss, tb.n_planes, tb.n_words, n_hap, k0, k1, pos_idx,
-                            base_code, out_row, match_row, s_term, s_off);
-            continue;
-        }
-        const int n_obs = (int)(k1 - k0);
+        const bool too_long = k1 - k0 > W * 32;  // block-uniform
+        const int n_obs = too_long ? 0 : (int)(k1 - k0);
 
+        if (!too_long) {
         // ---- 0. stage the row -------------------------------------------------------
-        for (int k = tid; k < n_obs; k += kBuildThreads) {
+        for (int k = tid; k < n_obs; k += kClassThreads) {
             const int p = pos_idx[k0 + k];
             int c = base_code[k0 + k];
             if (c >= tb.n_planes - 1) c = tb.n_planes - 1;
-            const int plane = p * tb.n_planes + c;
             const double2 hm = tb.hitmiss[p];
             const bool base_match = (c == (int)tb.ref_code[p]);
             s_term[k] = base_match ? hm : make_double2(hm.y, hm.x);
-            s_range[k] = make_int2(tb.dev_ptr[plane], tb.dev_ptr[plane + 1]);
-            s_off[k] = (uint32_t)(plane * tb.n_words);
+            s_plane[k] = p * tb.n_planes + c;
             // the match flag rides in s_pcnt[k + 1] until the prefix pass
             s_pcnt[k + 1] = base_match ? 1 : 0;
         }
-        for (int g = tid; g < n_groups; g += kBuildThreads) s_gcnt[g] = 0;
-        if (tid == 0) { s_nitems = 1; s_overflow = 0; }
+        for (int i = tid; i < n_groups * W; i += kClassThreads) s_gmap[i] = 0u;
+        if (tid == 0) { s_nitems = 1; s_overflow = 0; s_ndense = 0; }
         __syncthreads();
 
-        // ---- 1. marker-free prefix sums | scatter deviations into group lists ----------
-        if (warp == kBuildWarps - 1) {
+        if (warp == kWorkWarps) {
+            // ---- 1'. marker-free prefix sums (one dependent-add chain), off the others' path
             if (lane == 0) {
                 double acc = 0.0;
                 int cnt = 0;
                 s_prefix[0] = acc;
                 s_pcnt[0] = 0;
-                for (int k = 0; k < n_obs; ++k) {
+                int k = 0;
+                for (; k + 8 <= n_obs; k += 8) {
+                    double t[8];
+                    int f[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { t[u] = s_term[k + u].x; f[u] = s_pcnt[k + u + 1]; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        acc += t[u];
+                        cnt += f[u];
+                        s_prefix[k + u + 1] = acc;
+                        s_pcnt[k + u + 1] = (uint16_t)cnt;
+                    }
+                }
+                for (; k < n_obs; ++k) {
                     acc += s_term[k].x;
                     cnt += s_pcnt[k + 1];
                     s_prefix[k + 1] = acc;
@@ -252,81 +311,126 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int64_t *__restrict__ 
                 }
             }
         } else {
-            for (int k = warp; k < n_obs; k += kBuildWarps - 1) {
-                const int2 r = s_range[k];
-                for (int e = r.x + lane; e < r.y; e += 32) {
-                    const uint2 ent = tb.dev_ent[e];
-                    const int slot = atomicAdd(&s_gcnt[ent.x], 1);
-                    if (slot < kGroupCap) s_glist[ent.x * kGroupCap + slot] = make_uint2(k, ent.y);
+            // ---- 1. deviation entries of the row, grouped by 32-column group ------------------
+            // 8 lanes walk the sparse list of one observation (5.7 entries on average)
+            // (the loops are kept warp-uniform: the four lists advance together)
+            const int sub = lane >> 3, sl = lane & 7;
+#pragma unroll 1
+            for (int kb = warp * 4; kb < n_obs; kb += kWorkWarps * 4) {
+                const int k = kb + sub;
+                int e = 0, e1 = 0;
+                if (k < n_obs) {
+                    const int plane = s_plane[k];
+                    e = tb.dev_ptr[plane] + sl;
+                    e1 = tb.dev_ptr[plane + 1];
+                }
+#pragma unroll 1
+                while (__any_sync(0xffffffffu, e < e1)) {
+                    if (e < e1) atomicOr(&s_gmap[tb.dev_ent[e].x * W + (k >> 5)], 1u << (k & 31));
+                    e += 8;
                 }
             }
-        }
-        __syncthreads();
+            work_warps_sync<kWorkWarps * 32>();
+            if (warp == 0) {  // entries per group and their exclusive scan
+                int carry = 0;
+                for (int g0 = 0; g0 < n_groups; g0 += 32) {
+                    const int g = g0 + lane;
+                    int c = 0;
+                    if (g < n_groups) {
+#pragma unroll
+                        for (int w = 0; w < W; ++w) c += __popc(s_gmap[g * W + w]);
+                        s_gcnt[g] = c;
+                    }
+                    int incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (g < n_groups) s_goff[g] = carry + incl - c;
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0 && carry > Tier::kEntries) s_overflow = 1;
+            }
+            work_warps_sync<kWorkWarps * 32>();
+            // read once, before any warp can raise the flag again: the branch and the
+            // loops below hold warp-synchronous intrinsics and must stay warp-uniform
+            const bool too_many_entries = s_overflow != 0;
+            if (!too_many_entries) {
+#pragma unroll 1
+                for (int kb = warp * 4; kb < n_obs; kb += kWorkWarps * 4) {
+                    const int k = kb + sub;
+                    int e = 0, e1 = 0;
+                    if (k < n_obs) {
+                        const int plane = s_plane[k];
+                        e = tb.dev_ptr[plane] + sl;
+                        e1 = tb.dev_ptr[plane + 1];
+                    }
+#pragma unroll 1
+                    while (__any_sync(0xffffffffu, e < e1)) {
+                        if (e < e1) {
+                            // slot = rank of k among the group's deviating observations:
+                            // the group's entries end up sorted by k without a sort
+                            const uint2 ent = tb.dev_ent[e];
+                            const uint32_t *map = s_gmap + ent.x * W;
+                            int slot = s_goff[ent.x] + __popc(map[k >> 5] & ((1u << (k & 31)) - 1u));
+                            for (int w = 0; w < (k >> 5); ++w) slot += __popc(map[w]);
+                            s_ek[slot] = (uint16_t)k;
+                            s_ew[slot] = ent.y;
+                        }
+                        e += 8;
+                    }
+                }
+            }
+            work_warps_sync<kWorkWarps * 32>();
 
-        // ---- 2. classes of every 32-column group ------------------------------------------
-        for (int g = warp; g < n_groups; g += kBuildWarps) {
-            const int a = s_gcnt[g];
-            if (a == 0) {
-                s_cell[g * 32 + lane] = 0;
-                continue;
-            }
-            if (a > kGroupCap) {
-                // too many deviating positions: this warp walks the dense table
-                const int j = g * 32 + lane;
-                double acc = 0.0;
-                int cnt = 0;
-                for (int k = 0; k < n_obs; ++k) {
-                    const uint32_t w = __ldg(tb.bits + s_off[k] + g);
-                    const uint32_t d = ((w >> lane) & 1u);   // 1 = match
-                    const double2 t = s_term[k];
-                    const bool bm = s_pcnt[k + 1] != s_pcnt[k];
-                    acc += (d != 0) == bm ? t.x : t.y;
-                    cnt += d;
+            // ---- 2. classes of every 32-column group ------------------------------------------
+#pragma unroll 1
+            for (int g = warp; g < n_groups && !too_many_entries; g += kWorkWarps) {
+                const int a = s_gcnt[g];
+                if (a == 0) {
+                    s_cell[g * 32 + lane] = 0;
+                    if (lane == 0) s_gbase[g] = 0;
+                    continue;
                 }
-                if (j < n_hap) {
-                    out_row[j] = acc;
-                    if (kCounts) match_row[j] = cnt;
+                if (a > 32) {  // handled after the prefix pass
+                    if (lane == 0) { s_gbase[g] = (uint16_t)kDenseGroup; atomicAdd(&s_ndense, 1); }
+                    continue;
                 }
-                s_cell[g * 32 + lane] = (uint16_t)kNoItem;
-                continue;
+                const uint32_t *w = s_ew + s_goff[g];
+                uint32_t pattern = 0;
+#pragma unroll 4
+                for (int e = a - 1; e >= 0; --e) pattern = (pattern << 1) | ((w[e] >> lane) & 1u);
+                const uint32_t peers = __match_any_sync(0xffffffffu, pattern);
+                const int leader_lane = __ffs(peers) - 1;
+                const bool leader = (lane == leader_lane) && pattern != 0u;
+                const uint32_t lead_mask = __ballot_sync(0xffffffffu, leader);
+                const int n_lead = __popc(lead_mask);
+                int base_idx = 0;
+                if (lane == 0 && n_lead) base_idx = atomicAdd(&s_nitems, n_lead);
+                base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
+                int local = 1 + __popc(lead_mask & ((1u << lane) - 1u));  // 1-based within the group
+                if (base_idx + n_lead > Tier::kItems) {
+                    if (lane == 0) s_overflow = 1;
+                } else if (leader) {
+                    s_item[base_idx + local - 1] = make_uint2(pattern, (uint32_t)g);
+                }
+                local = __shfl_sync(0xffffffffu, local, leader_lane);
+                s_cell[g * 32 + lane] = (uint8_t)(pattern ? local : 0);
+                if (lane == 0) s_gbase[g] = (uint16_t)base_idx;
             }
-            // lane e < a holds entry e; rank it by k (k is unique within a group)
-            uint2 ent = make_uint2(0xFFFFFFFFu, 0u);
-            if (lane < a) ent = s_glist[g * kGroupCap + lane];
-            int rank = 0;
-            uint32_t pattern = 0;
-            for (int e = 0; e < a; ++e) {
-                const uint32_t ke = __shfl_sync(0xffffffffu, ent.x, e);
-                rank += (ke < ent.x) ? 1 : 0;
-            }
-            for (int e = 0; e < a; ++e) {
-                const uint32_t we = __shfl_sync(0xffffffffu, ent.y, e);
-                const int re = __shfl_sync(0xffffffffu, rank, e);
-                pattern |= ((we >> lane) & 1u) << re;
-            }
-            __syncwarp();
-            if (lane < a) s_glist[g * kGroupCap + rank] = ent;  // sorted by k
-            const uint32_t peers = __match_any_sync(0xffffffffu, pattern);
-            const int leader_lane = __ffs(peers) - 1;
-            const bool leader = (lane == leader_lane) && pattern != 0u;
-            const uint32_t lead_mask = __ballot_sync(0xffffffffu, leader);
-            int base_idx = 0;
-            if (lane == 0 && lead_mask) base_idx = atomicAdd(&s_nitems, __popc(lead_mask));
-            base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
-            int idx = base_idx + __popc(lead_mask & ((1u << lane) - 1u));
-            if (leader && idx < kMaxItems) s_item[idx] = make_uint2(pattern, (uint32_t)g);
-            idx = __shfl_sync(0xffffffffu, idx, leader_lane);
-            if (pattern == 0u) idx = 0;
-            if (base_idx + __popc(lead_mask) > kMaxItems) {
-                if (lane == 0) s_overflow = 1;
-                idx = 0;
-            }
-            s_cell[g * 32 + lane] = (uint16_t)idx;
         }
         __syncthreads();
-        if (s_overflow) {  // block-uniform: more classes than chain items
-            build_dense_row(tb.bits, tb.hitmiss, tb.n_planes, tb.n_words, n_hap, k0, k1, pos_idx,
-                            base_code, out_row, match_row, s_term, s_off);
+        }  // !too_long
+        if (too_long || s_overflow) {  // block-uniform: the row does not fit this tier's pools
+            if (overflow_list) {
+                if (tid == 0) overflow_list[atomicAdd(overflow_count, 1)] = (int32_t)row;
+            } else if constexpr (W * 32 == kMaxObs) {  // only the last tier has the staging room
+                build_dense_row<kClassThreads>(tb.bits, tb.hitmiss, tb.n_planes, tb.n_words, n_hap,
+                                               k0, k1, pos_idx, base_code, out_row, match_row,
+                                               s_term, s_off);
+            }
+            __syncthreads();
             continue;
         }
 
@@ -336,15 +440,15 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int64_t *__restrict__ 
             s_val[0] = s_prefix[n_obs];
             if (kCounts) s_icnt[0] = s_pcnt[n_obs];
         }
-        for (int it = 1 + tid; it < n_items; it += kBuildThreads) {
+#pragma unroll 1
+        for (int it = 1 + tid; it < n_items; it += kClassThreads) {
             const uint2 item = s_item[it];
-            const uint2 *list = s_glist + item.y * kGroupCap;
-            uint32_t rem = item.x;
-            int e = __ffs(rem) - 1;
-            rem >>= e;
-            int nk = (int)list[e].x;
+            uint32_t rem = item.x;   // bit e: deviates at the group's e-th deviating observation
+            const uint16_t *ek = s_ek + s_goff[item.y];
+            int nk = ek[__ffs(rem) - 1];
             double acc = s_prefix[nk];
             int cnt = kCounts ? (int)s_pcnt[nk] : 0;
+#pragma unroll 2
             for (int k = nk; k < n_obs; ++k) {
                 const double2 t = s_term[k];
                 const bool dev = (k == nk);
@@ -354,34 +458,52 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int64_t *__restrict__ 
                     cnt += dev ? 1 - bm : bm;
                 }
                 if (dev) {
-                    rem >>= 1;
-                    if (rem) {
-                        const int s = __ffs(rem) - 1;
-                        rem >>= s;
-                        e += s + 1;
-                        nk = (int)list[e].x;
-                    } else {
-                        nk = -1;
-                    }
+                    rem &= rem - 1;
+                    nk = rem ? (int)ek[__ffs(rem) - 1] : 0x7FFFFFFF;
                 }
             }
             s_val[it] = acc;
             if (kCounts) s_icnt[it] = cnt;
         }
+        // groups with more than 32 deviating positions: walk the dense table, one warp each
+#pragma unroll 1
+        for (int g = warp; g < n_groups && s_ndense > 0; g += kClassWarps) {
+            if (s_gbase[g] != kDenseGroup) continue;
+            const int j = g * 32 + lane;
+            double acc = 0.0;
+            int cnt = 0;
+            for (int k = 0; k < n_obs; ++k) {
+                const uint32_t w = __ldg(tb.bits + (size_t)s_plane[k] * tb.n_words + g);
+                const uint32_t d = (w >> lane) & 1u;   // 1 = match
+                const double2 t = s_term[k];
+                const bool bm = s_pcnt[k + 1] != s_pcnt[k];
+                acc += (d != 0) == bm ? t.x : t.y;
+                cnt += d;
+            }
+            if (j < n_hap) {
+                out_row[j] = acc;
+                if (kCounts) match_row[j] = cnt;
+            }
+        }
         __syncthreads();
 
         // ---- 4. write the row -----------------------------------------------------------------
-        if (((n_hap & 1) == 0)) {
-            for (int j = tid * 2; j < n_hap; j += kBuildThreads * 2) {
-                const unsigned i0 = s_cell[j], i1 = s_cell[j + 1];
-                if (i0 == kNoItem) continue;  // dense group (both cells are in it)
+        if ((n_hap & 1) == 0) {
+            for (int j = tid * 2; j < n_hap; j += kClassThreads * 2) {
+                const unsigned gb = s_gbase[j >> 5];
+                if (gb == kDenseGroup) continue;
+                const unsigned c0 = s_cell[j], c1 = s_cell[j + 1];
+                const unsigned i0 = c0 ? gb + c0 - 1 : 0, i1 = c1 ? gb + c1 - 1 : 0;
                 *reinterpret_cast<double2 *>(out_row + j) = make_double2(s_val[i0], s_val[i1]);
-                if (kCounts) *reinterpret_cast<int2 *>(match_row + j) = make_int2(s_icnt[i0], s_icnt[i1]);
+                if (kCounts)
+                    *reinterpret_cast<int2 *>(match_row + j) = make_int2(s_icnt[i0], s_icnt[i1]);
             }
         } else {
-            for (int j = tid; j < n_hap; j += kBuildThreads) {
-                const unsigned i0 = s_cell[j];
-                if (i0 == kNoItem) continue;
+            for (int j = tid; j < n_hap; j += kClassThreads) {
+                const unsigned gb = s_gbase[j >> 5];
+                if (gb == kDenseGroup) continue;
+                const unsigned c0 = s_cell[j];
+                const unsigned i0 = c0 ? gb + c0 - 1 : 0;
                 out_row[j] = s_val[i0];
                 if (kCounts) match_row[j] = s_icnt[i0];
             }
@@ -541,7 +663,7 @@ int mxb_build_matrix(mxb_ctx *ctx, const mxb_phylo *ph, int64_t n_rows,
     MXB_TRY(mxb_matrix_alloc(ctx, n_rows, ph->n_hap, &m));
     const size_t cells = (size_t)n_rows * (size_t)ph->n_hap;
     int64_t *d_row_ptr = nullptr;
-    int32_t *d_pos = nullptr, *d_match = nullptr;
+    int32_t *d_pos = nullptr, *d_match = nullptr, *d_overflow = nullptr;
     uint8_t *d_code = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaError_t e = cudaSuccess;
@@ -565,21 +687,32 @@ int mxb_build_matrix(mxb_ctx *ctx, const mxb_phylo *ph, int64_t n_rows,
         STEP(cudaEventCreate(&ev0));
         STEP(cudaEventCreate(&ev1));
         if (e == cudaSuccess) {
-            // class kernel when its shared-memory layout fits, else the dense kernel
+            // class kernel (two tiers) when its shared-memory layouts fit, else the dense kernel
             const bool counts = d_match != nullptr;
             const int n_groups = (int)ceil_div(ph->n_hap, 32);
-            const BuildSmem lay(n_groups, counts);
-            const void *fn = counts ? (const void *)build_matrix_kernel<true>
-                                    : (const void *)build_matrix_kernel<false>;
-            bool use_class = getenv("MXB_BUILD_DENSE") == nullptr && n_groups < (int)kNoItem / 32 &&
-                             lay.total + 1024 <= ctx->smem_optin;
-            int per_sm = 0;
+            const BuildSmem lay1(n_groups, counts, Tier1::kEntries, Tier1::kItems, Tier1::kObsWords);
+            const BuildSmem lay2(n_groups, counts, Tier2::kEntries, Tier2::kItems, Tier2::kObsWords);
+            const void *fn1 = counts ? (const void *)build_matrix_kernel<true, Tier1>
+                                     : (const void *)build_matrix_kernel<false, Tier1>;
+            const void *fn2 = counts ? (const void *)build_matrix_kernel<true, Tier2>
+                                     : (const void *)build_matrix_kernel<false, Tier2>;
+            bool use_class = getenv("MXB_BUILD_DENSE") == nullptr &&
+                             lay2.total + 1024 <= ctx->smem_optin && n_rows < ((int64_t)1 << 31);
+            int per_sm1 = 0, per_sm2 = 0;
             if (use_class) {
-                STEP(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)lay.total));
-                STEP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBuildThreads,
-                                                                   lay.total));
-                if (e == cudaSuccess && per_sm < 1) use_class = false;
+                STEP(cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)lay1.total));
+                STEP(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)lay2.total));
+                STEP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fn1, Tier1::kThreads,
+                                                                   lay1.total));
+                STEP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, fn2, Tier2::kThreads,
+                                                                   lay2.total));
+                if (e == cudaSuccess && (per_sm1 < 1 || per_sm2 < 1)) use_class = false;
+            }
+            if (use_class) {
+                STEP(cudaMalloc(&d_overflow, (n_rows + 1) * sizeof(int32_t)));
+                STEP(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), ctx->stream));
             }
             STEP(cudaEventRecord(ev0, ctx->stream));
             if (e == cudaSuccess && use_class) {
@@ -593,13 +726,27 @@ int mxb_build_matrix(mxb_ctx *ctx, const mxb_phylo *ph, int64_t n_rows,
                 tb.n_words = ph->n_words;
                 tb.n_hap = ph->n_hap;
                 tb.n_groups = n_groups;
-                const int grid = (int)std::min<int64_t>(n_rows, (int64_t)ctx->num_sms * per_sm);
-                if (counts)
-                    build_matrix_kernel<true><<<grid, kBuildThreads, lay.total, ctx->stream>>>(
-                        tb, n_rows, d_row_ptr, d_pos, d_code, m->data, d_match);
-                else
-                    build_matrix_kernel<false><<<grid, kBuildThreads, lay.total, ctx->stream>>>(
-                        tb, n_rows, d_row_ptr, d_pos, d_code, m->data, d_match);
+                // d_overflow[0] = number of rows deferred to tier 2, d_overflow[1..] = the rows
+                int *ov_count = reinterpret_cast<int *>(d_overflow);
+                int32_t *ov_list = d_overflow + 1;
+                const int grid1 = (int)std::min<int64_t>(n_rows, (int64_t)ctx->num_sms * per_sm1);
+                const int grid2 = (int)std::min<int64_t>(n_rows, (int64_t)ctx->num_sms * per_sm2);
+                if (counts) {
+                    build_matrix_kernel<true, Tier1><<<grid1, Tier1::kThreads, lay1.total, ctx->stream>>>(
+                        tb, n_rows, nullptr, nullptr, ov_list, ov_count, d_row_ptr, d_pos, d_code,
+                        m->data, d_match);
+                    build_matrix_kernel<true, Tier2><<<grid2, Tier2::kThreads, lay2.total, ctx->stream>>>(
+                        tb, n_rows, ov_list, ov_count, nullptr, nullptr, d_row_ptr, d_pos, d_code,
+                        m->data, d_match);
+                } else {
+                    build_matrix_kernel<false, Tier1><<<grid1, Tier1::kThreads, lay1.total, ctx->stream>>>(
+                        tb, n_rows, nullptr, nullptr, ov_list, ov_count, d_row_ptr, d_pos, d_code,
+                        m->data, d_match);
+                    build_matrix_kernel<false, Tier2><<<grid2, Tier2::kThreads, lay2.total, ctx->stream>>>(
+                        tb, n_rows, ov_list, ov_count, nullptr, nullptr, d_row_ptr, d_pos, d_code,
+                        m->data, d_match);
+                }
+                ctx->launches++;
             } else if (e == cudaSuccess) {
                 const int grid = (int)std::min<int64_t>(n_rows, (int64_t)ctx->num_sms * 4);
                 build_matrix_dense_kernel<<<grid, kBuildThreads, 0, ctx->stream>>>(
@@ -630,6 +777,7 @@ int mxb_build_matrix(mxb_ctx *ctx, const mxb_phylo *ph, int64_t n_rows,
     cudaFree(d_pos);
     cudaFree(d_code);
     cudaFree(d_match);
+    cudaFree(d_overflow);
     if (rc != MXB_OK || !out_dev) mxb_matrix_destroy(m);
     else *out_dev = m;
     return rc;
