@@ -668,8 +668,11 @@ int mxb_build_matrix(mxb_ctx *ctx, const mxb_phylo *ph, int64_t n_rows,
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaError_t e = cudaSuccess;
     int rc = MXB_OK;
+    Prefault fault_out, fault_match;  // first-touch the result pages while the GPU works
 #define STEP(call) do { if (e == cudaSuccess) e = (call); } while (0)
     if (cells) {
+        if (out_host) fault_out.start(out_host, cells * sizeof(double));
+        if (match_host) fault_match.start(match_host, cells * sizeof(int32_t));
         STEP(cudaMalloc(&d_row_ptr, (n_rows + 1) * sizeof(int64_t)));
         if (n_obs) {
             STEP(cudaMalloc(&d_pos, n_obs * sizeof(int32_t)));
@@ -757,16 +760,21 @@ int mxb_build_matrix(mxb_ctx *ctx, const mxb_phylo *ph, int64_t n_rows,
             STEP(cudaGetLastError());
             STEP(cudaEventRecord(ev1, ctx->stream));
         }
-        if (out_host)
-            STEP(cudaMemcpyAsync(out_host, m->data, cells * sizeof(double),
-                                 cudaMemcpyDeviceToHost, ctx->stream));
-        if (match_host)
-            STEP(cudaMemcpyAsync(match_host, d_match, cells * sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, ctx->stream));
+        // pageable results leave through the staged copy engine (api.cu)
+        if (e == cudaSuccess && out_host) {
+            fault_out.join();
+            rc = copy_d2h(ctx, out_host, m->data, cells * sizeof(double));
+        }
+        if (e == cudaSuccess && rc == MXB_OK && match_host) {
+            fault_match.join();
+            rc = copy_d2h(ctx, match_host, d_match, cells * sizeof(int32_t));
+        }
         STEP(cudaStreamSynchronize(ctx->stream));
         if (e == cudaSuccess && elapsed_ms) STEP(cudaEventElapsedTime(elapsed_ms, ev0, ev1));
     }
 #undef STEP
+    fault_out.join();
+    fault_match.join();
     if (e != cudaSuccess) {
         set_error("mxb_build_matrix: %s", cudaGetErrorString(e));
         rc = (e == cudaErrorMemoryAllocation) ? MXB_ERR_NOMEM : MXB_ERR_CUDA;

@@ -51,6 +51,10 @@ struct mxb_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t launches = 0;
+    // pinned staging ring of the host<->device copy engine (api.cu), lazily allocated
+    void *stage_buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t stage_chunk = 0;
     // NCCL (optional)
     void *nccl_comm = nullptr;
     int rank = 0;
@@ -83,6 +87,21 @@ namespace mxb {
 
 int nccl_allreduce_sum_f64(mxb_ctx *ctx, double *dev_buf, int64_t n);
 int nccl_allreduce_f64(mxb_ctx *ctx, double *dev_buf, int64_t n, int op_is_max);
+
+// Host <-> device copies of matrix-sized buffers (api.cu).  Pageable host memory
+// goes through a pinned staging ring filled/drained by several host threads
+// (~43 GB/s instead of 11-19 GB/s for a plain pageable cudaMemcpy); pinned or
+// registered host memory is copied directly.  Both return after completion.
+int copy_h2d(mxb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int copy_d2h(mxb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+// Touch every page of a caller-owned *output* buffer from background threads
+// while the GPU works, so that the final copy does not pay first-touch faults.
+struct Prefault {
+    void *impl = nullptr;
+    void start(void *buf, size_t bytes);
+    void join();
+    ~Prefault() { join(); }
+};
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

@@ -893,6 +893,10 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
     mxb_matrix *mix = nullptr;
     std::vector<double> acc((size_t)h, 0.0), cur((size_t)h);
     StageTimer tm(ctx->stream);
+    // the caller's result buffer is usually fresh pageable memory: fault its pages in
+    // from background threads while the GPU iterates
+    Prefault fault_mix;
+    if (read_mix_out) fault_mix.start(read_mix_out, (size_t)m->n_rows * (size_t)h * sizeof(double));
     int rc = mxb_em_create(ctx, m, weights, (flags & MXB_EM_SHARDED) != 0, &em);
     tm.mark("em_create (alloc+to_linear)");
     if (rc == MXB_OK && want_mix) rc = mxb_matrix_alloc(ctx, m->n_rows, h, &mix);
@@ -927,7 +931,11 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
             }
             props_out[j] = v;
         }
-        if (read_mix_out) { rc = mxb_matrix_download(ctx, mix, read_mix_out); tm.mark("download read_mix"); }
+        if (read_mix_out) {
+            fault_mix.join();
+            rc = mxb_matrix_download(ctx, mix, read_mix_out);
+            tm.mark("download read_mix");
+        }
         else if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
             set_error("mxb_run_em: stream sync failed");
             rc = MXB_ERR_CUDA;
