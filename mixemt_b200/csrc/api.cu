@@ -116,7 +116,12 @@ static int copy_threads() {
     if (n == 0) {
         const char *env = getenv("MXB_COPY_THREADS");
         int v = env ? atoi(env) : 0;
-        if (v <= 0) v = std::min(16, omp_get_num_procs());
+        if (v <= 0) {
+            // one process per GPU: share the host cores between the local ranks
+            const char *lw = getenv("LOCAL_WORLD_SIZE");
+            const int ranks = std::max(1, lw ? atoi(lw) : 1);
+            v = std::min(16, std::max(2, omp_get_num_procs() / ranks));
+        }
         n = std::max(1, v);
     }
     return n;

@@ -91,6 +91,28 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint3
         ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load_u32(uint32_t dst_smem, const void *src, uint32_t bytes,
+                                              uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -152,18 +174,29 @@ to_linear_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols, i
 }
 
 // ---- fused E+M pass (fast path) ----------------------------------------------
+// Rows are handled two at a time between block barriers.  The two partial dot
+// products of a thread are reduced together: the first shuffle step hands row 0
+// to lanes 0-15 and row 1 to lanes 16-31, so one 5-step butterfly serves both
+// rows; lanes 0 and 16 publish the warp totals, and after the barrier every
+// warp folds the 16 + 16 warp totals with a 4-step butterfly over its two
+// half-warps, divides once per row and broadcasts the two coefficients.  All
+// index arithmetic in the loop is 32-bit and incremental (no 64-bit division).
+__device__ __forceinline__ double shfl_xor_f64(double v, int off) {
+    return __shfl_xor_sync(0xffffffffu, v, off);
+}
+
 template <int NC>
 __global__ void __launch_bounds__(kPassThreads, 1)
 em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
                     const double *__restrict__ weights, const double *__restrict__ pi0,
                     const double *__restrict__ pi1, EmState *__restrict__ st,
                     double *__restrict__ partials, int n_stages) {
+    static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
     if (st->done) return;
     const double *__restrict__ pi = st->cur ? pi1 : pi0;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t row_bytes = (uint32_t)(ld * sizeof(double));
-    double *stages = reinterpret_cast<double *>(smem_raw);
     double *scratch = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * row_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
 
@@ -171,8 +204,11 @@ em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
     const int lane = tid & 31, warp = tid >> 5;
     const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
     const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
-    const int64_t n_my = r_end - r_begin;
-    const double *my_rows = lin + r_begin * ld;
+    const int n_my = (int)(r_end - r_begin);
+    const unsigned char *my_rows = reinterpret_cast<const unsigned char *>(lin + r_begin * ld);
+    const double *my_w = weights + r_begin;
+    const uint32_t stages_u32 = smem_u32(smem_raw);
+    const uint32_t full_u32 = smem_u32(full);
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
@@ -180,93 +216,115 @@ em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
     }
     __syncthreads();
     if (tid == 0) {
-        for (int64_t q = 0; q < n_my && q < n_stages; ++q) {
+        for (int q = 0; q < n_my && q < n_stages; ++q) {
             mbar_expect_tx(&full[q], row_bytes);
-            bulk_load(stages + q * ld, my_rows + q * ld, row_bytes, &full[q]);
+            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
+                      &full[q]);
         }
     }
 
     // Thread-private column slice: chunk c = tid + k*512 covers doubles 2c, 2c+1.
-    const int64_t n_chunks = ld >> 1;
+    const int n_chunks = (int)(ld >> 1);
     double2 pr[NC], tr[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        const int64_t c = tid + (int64_t)k * kPassThreads;
+        const int c = tid + k * kPassThreads;
         pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
         tr[k] = make_double2(0.0, 0.0);
     }
+    const bool last_live = tid + (NC - 1) * kPassThreads < n_chunks;  // only chunk NC-1 can be ragged
 
+    int stage = 0;          // ring slot of row q0
+    uint32_t phase = 0;     // its mbarrier parity
     int sbuf = 0;
     int bad = 0;
-    for (int64_t q0 = 0; q0 < n_my; q0 += kPassGroup) {
+    const bool upper = lane >= 16;
+    for (int q0 = 0; q0 < n_my; q0 += kPassGroup) {
         double2 lv[kPassGroup][NC];
-        double dot[kPassGroup], wv[kPassGroup];
+        double dot[kPassGroup];
+        const int q_mine = q0 + (upper ? 1 : 0);
+        const double w_mine = (q_mine < n_my) ? my_w[q_mine] : 0.0;
+        int s_of[kPassGroup];
+        int s = stage;
+        uint32_t ph = phase;
 #pragma unroll
         for (int g = 0; g < kPassGroup; ++g) {
-            const int64_t q = q0 + g;
-            dot[g] = 0.0;
-            wv[g] = 0.0;
-            if (q < n_my) {
-                wv[g] = weights[r_begin + q];
-                const int s = (int)(q % n_stages);
-                mbar_wait(&full[s], (uint32_t)((q / n_stages) & 1));
-                const double2 *srow = reinterpret_cast<const double2 *>(stages + (size_t)s * ld);
+            s_of[g] = s;
+            double dx = 0.0, dy = 0.0;
+            if (q0 + g < n_my) {
+                mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
+                const double2 *srow = reinterpret_cast<const double2 *>(
+                    smem_raw + (size_t)s * row_bytes) + tid;
 #pragma unroll
                 for (int k = 0; k < NC; ++k) {
-                    const int64_t c = tid + (int64_t)k * kPassThreads;
-                    lv[g][k] = (c < n_chunks) ? srow[c] : make_double2(0.0, 0.0);
-                    dot[g] = fma(lv[g][k].x, pr[k].x, dot[g]);
-                    dot[g] = fma(lv[g][k].y, pr[k].y, dot[g]);
+                    if (k < NC - 1 || last_live) lv[g][k] = srow[k * kPassThreads];
+                    else lv[g][k] = make_double2(0.0, 0.0);
+                    dx = fma(lv[g][k].x, pr[k].x, dx);
+                    dy = fma(lv[g][k].y, pr[k].y, dy);
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < NC; ++k) lv[g][k] = make_double2(0.0, 0.0);
             }
-            dot[g] = warp_sum(dot[g]);
+            dot[g] = dx + dy;
+            if (++s == n_stages) { s = 0; ph ^= 1u; }
         }
+        // both rows in one butterfly: lanes 0-15 end up with row 0, lanes 16-31 with row 1
+        double v = (upper ? dot[1] : dot[0]) + shfl_xor_f64(upper ? dot[0] : dot[1], 16);
+        v += shfl_xor_f64(v, 8);
+        v += shfl_xor_f64(v, 4);
+        v += shfl_xor_f64(v, 2);
+        v += shfl_xor_f64(v, 1);
         double *sc = scratch + sbuf * (kPassWarps * kPassGroup);
-        if (lane == 0) {
-#pragma unroll
-            for (int g = 0; g < kPassGroup; ++g) sc[warp * kPassGroup + g] = dot[g];
-        }
-        __syncthreads();  // all reads of this group's stages are done; partial dots visible
+        if ((lane & 15) == 0) sc[(lane >> 4) * kPassWarps + warp] = v;
+        __syncthreads();  // all reads of this group's stages are done; warp totals visible
         if (tid == 0) {
 #pragma unroll
             for (int g = 0; g < kPassGroup; ++g) {
-                const int64_t q = q0 + g + n_stages;
-                if (q0 + g < n_my && q < n_my) {
-                    const int s = (int)(q % n_stages);
-                    mbar_expect_tx(&full[s], row_bytes);
-                    bulk_load(stages + (size_t)s * ld, my_rows + q * ld, row_bytes, &full[s]);
+                const int q = q0 + g + n_stages;
+                if (q < n_my) {
+                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_of[g];
+                    mbar_expect_tx_u32(bar, row_bytes);
+                    bulk_load_u32(stages_u32 + (uint32_t)s_of[g] * row_bytes,
+                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
                 }
             }
         }
-#pragma unroll
-        for (int g = 0; g < kPassGroup; ++g) {
-            double s_row = 0.0;
-#pragma unroll
-            for (int wp = 0; wp < kPassWarps; ++wp) s_row += sc[wp * kPassGroup + g];
-            double coef = 0.0;
-            if (wv[g] != 0.0) {
-                coef = wv[g] / s_row;
-                bad |= (s_row == 0.0);
-            }
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                tr[k].x = fma(coef, lv[g][k].x, tr[k].x);
-                tr[k].y = fma(coef, lv[g][k].y, tr[k].y);
-            }
+        // 16 warp totals per row sit in sc[0..15] / sc[16..31]: one value per lane
+        double t = sc[lane];
+        t += shfl_xor_f64(t, 8);
+        t += shfl_xor_f64(t, 4);
+        t += shfl_xor_f64(t, 2);
+        t += shfl_xor_f64(t, 1);
+        double coef_mine = 0.0;
+        if (w_mine != 0.0) {
+            coef_mine = w_mine / t;
+            bad |= (t == 0.0);
         }
+        const double coef0 = __shfl_sync(0xffffffffu, coef_mine, 0);
+        const double coef1 = __shfl_sync(0xffffffffu, coef_mine, 16);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            tr[k].x = fma(coef0, lv[0][k].x, tr[k].x);
+            tr[k].y = fma(coef0, lv[0][k].y, tr[k].y);
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            tr[k].x = fma(coef1, lv[1][k].x, tr[k].x);
+            tr[k].y = fma(coef1, lv[1][k].y, tr[k].y);
+        }
+        stage = s;
+        phase = ph;
         sbuf ^= 1;
     }
 
     double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        const int64_t c = tid + (int64_t)k * kPassThreads;
+        const int c = tid + k * kPassThreads;
         if (c < n_chunks) out[c] = tr[k];
     }
-    if (bad && tid == 0) atomicAdd(&st->bad, 1);
+    if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
 }
 
 // ---- general path: any shape, two passes over L -------------------------------
