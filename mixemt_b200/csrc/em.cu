@@ -38,6 +38,8 @@
 #include <new>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace mxb {
@@ -450,6 +452,96 @@ em_update_kernel(const double *__restrict__ tsum, int64_t n_cols, int64_t ld,
     }
 }
 
+// ---- fused tail of an iteration (fast path) ------------------------------------
+// One launch replaces em_colreduce_kernel + em_update_kernel: a single cluster of
+// kFinCtas CTAs, one thread per column.  Each thread adds the per-CTA partial
+// sums of its column in fixed order, the two scalars of the M-step (the
+// normaliser sum_k pi_k T_k and the convergence distance sum_j |pi'_j - pi_j|,
+// em.py:89 and :39-54) are reduced across the cluster through distributed shared
+// memory, and CTA 0 advances the control block.  Deterministic: fixed summation
+// orders, no atomics.
+constexpr int kFinCtas = 8;
+constexpr int kFinThreads = 1024;
+
+// Sum of one double per thread over the whole cluster; every thread gets it.
+// slots: kFinCtas doubles in *every* CTA's shared memory, wsum: kFinThreads/32.
+__device__ __forceinline__ double cluster_sum(double v, double *wsum, double *slots) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = wsum[lane];  // kFinThreads / 32 == 32 warps
+        t = warp_sum(t);
+        if (lane < kFinCtas) {
+            // lane r publishes this CTA's total in CTA r's slot array
+            double *remote = cluster.map_shared_rank(slots, lane);
+            remote[cluster.block_rank()] = t;
+        }
+    }
+    cluster.sync();
+    double total = 0.0;
+#pragma unroll
+    for (int r = 0; r < kFinCtas; ++r) total += slots[r];
+    return total;
+}
+
+__global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(kFinThreads)
+em_finish_kernel(const double *__restrict__ partials, int n_part, int64_t n_cols, int64_t ld,
+                 double *__restrict__ lnp0, double *__restrict__ lnp1,
+                 double *__restrict__ pi0, double *__restrict__ pi1,
+                 EmState *__restrict__ st) {
+    static_assert(kFinThreads == 1024, "cluster_sum assumes 32 warps");
+    if (st->done) return;  // same answer in every CTA: the block below is the only writer
+    __shared__ double wsum[2][kFinThreads / 32];
+    __shared__ double slots[2][kFinCtas];
+    const int cur = st->cur;
+    const double *lnp_old = cur ? lnp1 : lnp0;
+    const double *pi_old = cur ? pi1 : pi0;
+    double *lnp_new = cur ? lnp0 : lnp1;
+    double *pi_new = cur ? pi0 : pi1;
+
+    const int64_t j = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
+    const bool live = j < n_cols;
+    double t = 0.0;
+    if (live) {
+        const double *col = partials + j;
+        int b = 0;
+        for (; b + 8 <= n_part; b += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = col[(size_t)(b + u) * ld];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t += v[u];
+        }
+        for (; b < n_part; ++b) t += col[(size_t)b * ld];
+    }
+    const double p = live ? pi_old[j] : 0.0;
+    const double total = cluster_sum(p * t, wsum[0], slots[0]);
+
+    double dl = 0.0;
+    if (live) {
+        double ln_new;
+        if (p >= 1e-290) ln_new = log(p * t / total);
+        else ln_new = lnp_old[j] + log(t / total);  // pi underflowed: stay in log space
+        const double p_new = exp(ln_new);
+        lnp_new[j] = ln_new;
+        pi_new[j] = p_new;
+        dl = fabs(p_new - p);
+    }
+    const double delta = cluster_sum(dl, wsum[1], slots[1]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->delta = delta;
+        const long long it = st->iters + 1;
+        st->iters = it;
+        if (delta < st->tol) st->done = 1;
+        else if (it >= st->max_iter) st->done = 2;
+        else st->cur = 1 - cur;
+    }
+}
+
 // ln pi -> (ln pi, pi) device buffers, padding zeroed.
 __global__ void em_set_props_kernel(const double *__restrict__ src, int64_t n_cols, int64_t ld,
                                     double *__restrict__ lnp, double *__restrict__ pi,
@@ -564,6 +656,7 @@ struct mxb_em {
     int grid_fast = 0;
     // general path
     int row_blocks = 0, col_blocks = 0;
+    bool fused_tail = false;  // colreduce + update in one cluster launch (em_finish_kernel)
     bool zero_iter = false;  // last iterate() ran no iteration
 };
 
@@ -607,6 +700,14 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
         ctx->launches += 2;
     }
     if (pass_end) MXB_CUDA(cudaEventRecord(pass_end, s));
+    if (em->fused_tail) {
+        em_finish_kernel<<<kFinCtas, kFinThreads, 0, s>>>(em->partials, em->n_part, em->n_cols,
+                                                          em->ld, em->lnp[0], em->lnp[1],
+                                                          em->pi[0], em->pi[1], em->state);
+        ctx->launches += 1;
+        MXB_CUDA(cudaGetLastError());
+        return MXB_OK;
+    }
     em_colreduce_kernel<<<(int)ceil_div(em->ld, 256), 256, 0, s>>>(em->partials, em->n_part,
                                                                   em->ld, em->state, em->tsum);
     ctx->launches += 1;
@@ -702,6 +803,8 @@ int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int 
             em->grid_fast = (int)std::min<int64_t>(ctx->num_sms, em->n_rows);
         }
     }
+    em->fused_tail = em->fast && em->ld <= (int64_t)kFinCtas * kFinThreads &&
+                     !(em->sharded && ctx->world > 1) && getenv("MXB_EM_SPLIT_TAIL") == nullptr;
     if (em->fast) {
         em->n_part = em->grid_fast;
         cudaError_t e = cudaFuncSetAttribute((const void *)pick_pass(em->nc),
