@@ -382,7 +382,9 @@ def run_b200(opts):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(opts.fragments, n, h),
                            "rows_per_gpu": n, "haplotypes": h, "parallelism":
-                           "rows sharded x%d, ncclAllReduce(H fp64) per iteration" % world
+                           ("rows sharded x%d, H column sums exchanged per iteration by %s"
+                            % (world, "peer stores inside the EM tail kernel (CUDA IPC over NVLink)"
+                               if lib.mxb_comm_p2p_enabled(ctx.handle) else "ncclAllReduce(fp64)"))
                            if world > 1 else "single GPU",
                            "l2_policy": "input (%.2f GB) larger than L2, no flush needed"
                            % (pass_bytes / 1e9)},

@@ -67,6 +67,10 @@ int64_t mxb_ctx_launch_count(const mxb_ctx *ctx);
 int mxb_comm_unique_id(void *id128);
 int mxb_comm_init(mxb_ctx *ctx, const void *id128, int rank, int world);
 int mxb_comm_destroy(mxb_ctx *ctx);
+/* 1 when the ranks of the comm mapped each other's mailboxes (CUDA IPC over
+ * NVLink) and the per-iteration exchange of the column sums is fused into the
+ * EM tail kernel as peer stores; 0 when ncclAllReduce is used instead. */
+int mxb_comm_p2p_enabled(const mxb_ctx *ctx);
 /* In-place sum / max all-reduce of a host fp64 vector across the comm
  * (restart fan-out: sum of log-proportions, reference em.py:155). */
 int mxb_comm_allreduce_host(mxb_ctx *ctx, double *buf, int64_t n, int op_is_max);

@@ -62,6 +62,7 @@ _PROTOS = {
     "mxb_comm_unique_id": (ctypes.c_int, [P]),
     "mxb_comm_init": (ctypes.c_int, [P, P, ctypes.c_int, ctypes.c_int]),
     "mxb_comm_destroy": (ctypes.c_int, [P]),
+    "mxb_comm_p2p_enabled": (ctypes.c_int, [P]),
     "mxb_comm_allreduce_host": (ctypes.c_int, [P, P, c_i64, ctypes.c_int]),
     "mxb_sig_count": (ctypes.c_int, [P, P, c_i64, P]),
     "mxb_sig_parse": (ctypes.c_int, [P, P, c_i64, P, c_i64, P, P, P, P,

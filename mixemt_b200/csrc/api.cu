@@ -33,6 +33,7 @@ typedef int (*fn_get_uid)(nccl_uid_t *);
 typedef int (*fn_comm_init_rank)(void **, int, nccl_uid_t, int);
 typedef int (*fn_comm_destroy)(void *);
 typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
 typedef const char *(*fn_error_string)(int);
 
 struct NcclApi {
@@ -41,6 +42,7 @@ struct NcclApi {
     fn_comm_init_rank init_rank = nullptr;
     fn_comm_destroy destroy = nullptr;
     fn_allreduce allreduce = nullptr;
+    fn_allgather allgather = nullptr;
     fn_error_string error_string = nullptr;
 };
 
@@ -63,6 +65,7 @@ static int load_nccl() {
     g_nccl.init_rank = (fn_comm_init_rank)dlsym(h, "ncclCommInitRank");
     g_nccl.destroy = (fn_comm_destroy)dlsym(h, "ncclCommDestroy");
     g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
+    g_nccl.allgather = (fn_allgather)dlsym(h, "ncclAllGather");
     g_nccl.error_string = (fn_error_string)dlsym(h, "ncclGetErrorString");
     if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.allreduce) {
         set_error("libnccl is missing a required symbol");
@@ -265,6 +268,72 @@ void Prefault::join() {
     impl = nullptr;
 }
 
+// ---------------------------------------------------------------------------
+// Peer mailboxes for the fused EM tail.  NCCL carries the 64-byte IPC handles
+// once (ncclAllGather) and the vote on whether every rank could map every peer;
+// after that the per-iteration exchange of the H column sums is plain stores
+// into peer memory from inside em_finish_kernel (em.cu).
+// ---------------------------------------------------------------------------
+static void p2p_teardown(mxb_ctx *ctx) {
+    for (int r = 0; r < kP2PMaxWorld; ++r) {
+        if (!ctx->p2p_block[r]) continue;
+        if (r == ctx->rank) cudaFree(ctx->p2p_block[r]);
+        else cudaIpcCloseMemHandle(ctx->p2p_block[r]);
+        ctx->p2p_block[r] = nullptr;
+    }
+    ctx->p2p_ready = false;
+}
+
+static int p2p_setup(mxb_ctx *ctx) {
+    ctx->p2p_ready = false;
+    if (ctx->world <= 1 || ctx->world > kP2PMaxWorld || !g_nccl.allgather || getenv("MXB_NO_P2P"))
+        return MXB_OK;
+    const int W = ctx->world;
+    cudaStream_t s = ctx->stream;
+    unsigned char *mine = nullptr;
+    MXB_CUDA(cudaMalloc(&mine, kP2PBlockBytes));
+    ctx->p2p_block[ctx->rank] = mine;
+    MXB_CUDA(cudaMemsetAsync(mine, 0, kP2PBlockBytes, s));
+    cudaIpcMemHandle_t handles[kP2PMaxWorld];
+    memset(handles, 0, sizeof(handles));
+    int ok = cudaIpcGetMemHandle(&handles[ctx->rank], mine) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    unsigned char *dh = nullptr;
+    double *vote = nullptr;
+    MXB_CUDA(cudaMalloc(&dh, sizeof(handles)));
+    MXB_CUDA(cudaMalloc(&vote, sizeof(double)));
+    MXB_CUDA(cudaMemcpyAsync(dh, handles, sizeof(handles), cudaMemcpyHostToDevice, s));
+    MXB_NCCL(g_nccl.allgather(dh + (size_t)ctx->rank * sizeof(cudaIpcMemHandle_t), dh,
+                              sizeof(cudaIpcMemHandle_t), 1 /* ncclUint8 */, ctx->nccl_comm, s));
+    MXB_CUDA(cudaMemcpyAsync(handles, dh, sizeof(handles), cudaMemcpyDeviceToHost, s));
+    MXB_CUDA(cudaStreamSynchronize(s));
+    for (int r = 0; r < W && ok; ++r) {
+        if (r == ctx->rank) continue;
+        void *peer = nullptr;
+        if (cudaIpcOpenMemHandle(&peer, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+        } else {
+            ctx->p2p_block[r] = (unsigned char *)peer;
+        }
+    }
+    // unanimous or not at all: a rank that fell back to NCCL would wait forever
+    double v = ok ? 0.0 : 1.0;
+    MXB_CUDA(cudaMemcpyAsync(vote, &v, sizeof(v), cudaMemcpyHostToDevice, s));
+    MXB_CUDA(cudaStreamSynchronize(s));
+    MXB_TRY(nccl_allreduce_f64(ctx, vote, 1, 0));
+    MXB_CUDA(cudaMemcpyAsync(&v, vote, sizeof(v), cudaMemcpyDeviceToHost, s));
+    MXB_CUDA(cudaStreamSynchronize(s));
+    cudaFree(dh);
+    cudaFree(vote);
+    if (v != 0.0) {
+        p2p_teardown(ctx);
+        return MXB_OK;  // NCCL all-reduce path stays in use
+    }
+    ctx->p2p_ready = true;
+    return MXB_OK;
+}
+
 // First maximum of every row (numpy.argmax semantics; NaN wins like numpy).
 __global__ void argmax_rows_kernel(const double *__restrict__ m, int64_t n_rows,
                                    int64_t n_cols, int64_t *__restrict__ out) {
@@ -392,13 +461,14 @@ int mxb_comm_init(mxb_ctx *ctx, const void *id128, int rank, int world) {
     ctx->nccl_comm = comm;
     ctx->rank = rank;
     ctx->world = world;
-    return MXB_OK;
+    return p2p_setup(ctx);
 }
 
 int mxb_comm_destroy(mxb_ctx *ctx) {
     MXB_REQUIRE(ctx != nullptr, "ctx is NULL");
     if (ctx->nccl_comm) {
         cudaStreamSynchronize(ctx->stream);
+        p2p_teardown(ctx);
         g_nccl.destroy(ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
     }
@@ -406,6 +476,8 @@ int mxb_comm_destroy(mxb_ctx *ctx) {
     ctx->world = 1;
     return MXB_OK;
 }
+
+int mxb_comm_p2p_enabled(const mxb_ctx *ctx) { return ctx && ctx->p2p_ready ? 1 : 0; }
 
 int mxb_comm_allreduce_host(mxb_ctx *ctx, double *buf, int64_t n, int op_is_max) {
     MXB_REQUIRE(ctx != nullptr && (buf != nullptr || n == 0) && n >= 0, "bad argument");

@@ -41,6 +41,10 @@ void set_error(const char *fmt, ...);
 struct NcclApi;
 
 constexpr int kNumSMsFallback = 148;  // B200
+constexpr int kP2PMaxWorld = 8;       // one NVSwitch domain
+constexpr int kP2PMaxLd = 8192;       // widest row of the fused EM tail
+constexpr size_t kP2PInboxOffset = 256;
+constexpr size_t kP2PBlockBytes = kP2PInboxOffset + (size_t)2 * kP2PMaxWorld * kP2PMaxLd * 8;
 
 }  // namespace mxb
 
@@ -59,6 +63,11 @@ struct mxb_ctx {
     void *nccl_comm = nullptr;
     int rank = 0;
     int world = 1;
+    // Peer-memory mailboxes of the fused EM tail (api.cu: p2p_setup).  Every rank owns one
+    // cudaMalloc'ed block [flags: 2 x world u64][seq u64][inbox: 2 x world x kP2PMaxLd doubles]
+    // and maps the blocks of its peers through CUDA IPC over NVLink.
+    bool p2p_ready = false;
+    unsigned char *p2p_block[mxb::kP2PMaxWorld] = {};  // [r] = rank r's block as seen from here
 };
 
 struct mxb_matrix {

@@ -488,15 +488,44 @@ __device__ __forceinline__ double cluster_sum(double v, double *wsum, double *sl
     return total;
 }
 
+// Multi-GPU form of the tail (kP2P): the ranks' column sums are exchanged through
+// peer memory instead of a separate collective.  Every rank stores its H sums
+// into slot (seq & 1) of each peer's inbox (NVLink P2P stores), fences, and
+// raises its flag there with the launch sequence number; it then waits until all
+// `world` flags in its own block carry that number and adds the inbox rows in
+// rank order, so that every rank forms bit-identical totals and takes the same
+// convergence decision.  Two slots suffice: a rank can be at most one launch
+// ahead of a peer, because it needs that peer's flag to finish a launch.
+struct P2PArgs {
+    int world, rank;
+    unsigned char *block[kP2PMaxWorld];  // [r] = rank r's mailbox block (own block at [rank])
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kP2PTimeoutNs = 120ull * 1000000000ull;
+
+template <bool kP2P>
 __global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(kFinThreads)
 em_finish_kernel(const double *__restrict__ partials, int n_part, int64_t n_cols, int64_t ld,
                  double *__restrict__ lnp0, double *__restrict__ lnp1,
                  double *__restrict__ pi0, double *__restrict__ pi1,
-                 EmState *__restrict__ st) {
+                 EmState *__restrict__ st, P2PArgs pa) {
     static_assert(kFinThreads == 1024, "cluster_sum assumes 32 warps");
     if (st->done) return;  // same answer in every CTA: the block below is the only writer
     __shared__ double wsum[2][kFinThreads / 32];
     __shared__ double slots[2][kFinCtas];
+    __shared__ int s_timeout;
     const int cur = st->cur;
     const double *lnp_old = cur ? lnp1 : lnp0;
     const double *pi_old = cur ? pi1 : pi0;
@@ -518,6 +547,41 @@ em_finish_kernel(const double *__restrict__ partials, int n_part, int64_t n_cols
         }
         for (; b < n_part; ++b) t += col[(size_t)b * ld];
     }
+    unsigned long long seq = 0;
+    if (kP2P) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        const int W = pa.world;
+        unsigned long long *my_flags = reinterpret_cast<unsigned long long *>(pa.block[pa.rank]);
+        unsigned long long *my_seq = my_flags + 2 * kP2PMaxWorld;
+        if (threadIdx.x == 0) s_timeout = 0;
+        seq = *my_seq + 1;  // advanced by CTA 0 at the very end of this launch
+        const int slot = (int)(seq & 1ull);
+        if (live) {
+            for (int r = 0; r < W; ++r) {
+                double *inbox = reinterpret_cast<double *>(pa.block[r] + kP2PInboxOffset);
+                inbox[((size_t)slot * kP2PMaxWorld + pa.rank) * kP2PMaxLd + j] = t;
+            }
+        }
+        __threadfence_system();
+        cluster.sync();  // every store of this rank is fenced
+        if (blockIdx.x == 0 && threadIdx.x < W) {
+            const int r = threadIdx.x;
+            unsigned long long *peer_flags = reinterpret_cast<unsigned long long *>(pa.block[r]);
+            st_release_sys(&peer_flags[slot * kP2PMaxWorld + pa.rank], seq);
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_sys(&my_flags[slot * kP2PMaxWorld + r]) != seq) {
+                if (global_timer_ns() - t0 > kP2PTimeoutNs) { s_timeout = 1; break; }
+            }
+        }
+        cluster.sync();  // all ranks' sums have landed in this rank's inbox
+        if (live) {
+            const double *inbox = reinterpret_cast<const double *>(pa.block[pa.rank] + kP2PInboxOffset);
+            t = 0.0;
+            for (int r = 0; r < W; ++r)
+                t += __ldcg(&inbox[((size_t)slot * kP2PMaxWorld + r) * kP2PMaxLd + j]);
+        }
+    }
     const double p = live ? pi_old[j] : 0.0;
     const double total = cluster_sum(p * t, wsum[0], slots[0]);
 
@@ -536,7 +600,12 @@ em_finish_kernel(const double *__restrict__ partials, int n_part, int64_t n_cols
         st->delta = delta;
         const long long it = st->iters + 1;
         st->iters = it;
-        if (delta < st->tol) st->done = 1;
+        if (kP2P) {
+            unsigned long long *my_flags = reinterpret_cast<unsigned long long *>(pa.block[pa.rank]);
+            my_flags[2 * kP2PMaxWorld] = seq;
+        }
+        if (kP2P && s_timeout) st->done = 3;  // a peer never showed up
+        else if (delta < st->tol) st->done = 1;
         else if (it >= st->max_iter) st->done = 2;
         else st->cur = 1 - cur;
     }
@@ -701,9 +770,20 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
     }
     if (pass_end) MXB_CUDA(cudaEventRecord(pass_end, s));
     if (em->fused_tail) {
-        em_finish_kernel<<<kFinCtas, kFinThreads, 0, s>>>(em->partials, em->n_part, em->n_cols,
-                                                          em->ld, em->lnp[0], em->lnp[1],
-                                                          em->pi[0], em->pi[1], em->state);
+        P2PArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        if (em->sharded && ctx->world > 1) {
+            pa.world = ctx->world;
+            pa.rank = ctx->rank;
+            for (int r = 0; r < ctx->world; ++r) pa.block[r] = ctx->p2p_block[r];
+            em_finish_kernel<true><<<kFinCtas, kFinThreads, 0, s>>>(
+                em->partials, em->n_part, em->n_cols, em->ld, em->lnp[0], em->lnp[1], em->pi[0],
+                em->pi[1], em->state, pa);
+        } else {
+            em_finish_kernel<false><<<kFinCtas, kFinThreads, 0, s>>>(
+                em->partials, em->n_part, em->n_cols, em->ld, em->lnp[0], em->lnp[1], em->pi[0],
+                em->pi[1], em->state, pa);
+        }
         ctx->launches += 1;
         MXB_CUDA(cudaGetLastError());
         return MXB_OK;
@@ -804,7 +884,8 @@ int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int 
         }
     }
     em->fused_tail = em->fast && em->ld <= (int64_t)kFinCtas * kFinThreads &&
-                     !(em->sharded && ctx->world > 1) && getenv("MXB_EM_SPLIT_TAIL") == nullptr;
+                     (!(em->sharded && ctx->world > 1) || ctx->p2p_ready) &&
+                     getenv("MXB_EM_SPLIT_TAIL") == nullptr;
     if (em->fast) {
         em->n_part = em->grid_fast;
         cudaError_t e = cudaFuncSetAttribute((const void *)pick_pass(em->nc),
@@ -930,6 +1011,11 @@ int mxb_em_iterate(mxb_em *em, int64_t max_iter, double tol, int64_t *iters_out,
     MXB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (iters_out) *iters_out = fin.iters;
     if (converged_out) *converged_out = (fin.done == 1);
+    if (fin.done == 3) {
+        set_error("EM: a peer rank did not deliver its column sums within %llu s",
+                  (unsigned long long)(kP2PTimeoutNs / 1000000000ull));
+        return MXB_ERR_CUDA;
+    }
     if (fin.bad) {
         set_error("EM: the mixture likelihood of %d row group(s) underflowed to 0 "
                   "(proportions left the fp64 range)", fin.bad);
@@ -958,7 +1044,13 @@ int mxb_em_iterate_fixed(mxb_em *em, int64_t n_iter, float *elapsed_ms, float *p
         else MXB_TRY(enqueue_iteration(em));
     }
     MXB_CUDA(cudaEventRecord(e1, ctx->stream));
+    MXB_CUDA(cudaMemcpyAsync(&em->host_state[0], em->state, sizeof(EmState),
+                             cudaMemcpyDeviceToHost, ctx->stream));
     MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (em->host_state[0].done == 3) {
+        set_error("EM: a peer rank did not deliver its column sums in time");
+        return MXB_ERR_CUDA;
+    }
     if (elapsed_ms) MXB_CUDA(cudaEventElapsedTime(elapsed_ms, e0, e1));
     if (pass_ms) {
         double total = 0.0;

@@ -71,7 +71,10 @@ def main():
 
     dist.barrier()
     if rank == 0:
-        print("MULTIGPU_OK world=%d rows:iters=%s restarts ok" % (world, info_rows["iterations"]))
+        from mixemt_b200._lib import lib
+        how = "p2p" if lib.mxb_comm_p2p_enabled(ctx.handle) else "nccl"
+        print("MULTIGPU_OK world=%d rows:iters=%s restarts ok exchange=%s"
+              % (world, info_rows["iterations"], how))
     dist.destroy_process_group()
 
 
