@@ -130,6 +130,28 @@ void *mxb_matrix_data(const mxb_matrix *m);
 int mxb_matrix_argmax_rows(mxb_ctx *ctx, const mxb_matrix *m, int64_t *out_host);
 int mxb_matrix_destroy(mxb_matrix *m);
 
+/* ---- consumers of the EM result, kept on the device ---- */
+/* preprocess.reduce_em_matrix (preprocess.py:230-251): out[i][k] = src[i][cols[k]]. */
+int mxb_matrix_gather_cols(mxb_ctx *ctx, const mxb_matrix *src, const int64_t *cols,
+                           int64_t n_out, mxb_matrix **out);
+/* assemble._find_contribs_from_reads (assemble.py:102-124) / stats.report_read_votes
+ * (stats.py:34-46): votes_out[j] = sum of weights[i] over rows whose first row maximum
+ * is column j; argmax_out (nullable) receives the row maxima positions. */
+int mxb_matrix_vote_count(mxb_ctx *ctx, const mxb_matrix *m, const int64_t *weights,
+                          int64_t *votes_out, int64_t *argmax_out);
+/* assemble.assign_read_indexes (assemble.py:267-334): per row the two contributor
+ * columns with the highest read_mix[i][c] - con_lnprops[k]; assign_out[i] = k of the
+ * best one when it leads the runner-up by at least ln_min_fold, else -1 (unassigned);
+ * with a single contributor every row is assigned to it. */
+int mxb_assign_reads(mxb_ctx *ctx, const mxb_matrix *read_mix, const int64_t *con_cols,
+                     const double *con_lnprops, int32_t n_con, double ln_min_fold,
+                     int32_t *assign_out);
+/* Row-range transfers (streaming .npy save/load, bin/mixemt:168-245). */
+int mxb_matrix_download_rows(mxb_ctx *ctx, const mxb_matrix *m, int64_t row0, int64_t n_rows,
+                             double *host);
+int mxb_matrix_upload_rows(mxb_ctx *ctx, mxb_matrix *m, int64_t row0, int64_t n_rows,
+                           const double *host);
+
 /* ---- kernel 2: EM (replaces em_step / run_em, em.py:57-165) ---------------- */
 /* Session over one matrix shard.  weights[n_rows] (fp64).  sharded != 0 and a
  * comm on ctx: rows are a shard, column sums are all-reduced every iteration. */

@@ -11,18 +11,27 @@ Importing this package loads the CUDA shared library and fails loudly when it
 has not been built; there is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (loads libmixemt_b200.so or raises)
-from . import em, preprocess, runtime  # noqa: F401
+from . import consumers, em, preprocess, runtime  # noqa: F401
 from .em import run_em, em_step, init_props, converged  # noqa: F401
 from .preprocess import build_em_matrix, HapVarBaseMatrix  # noqa: F401
 
 __version__ = "0.1.0"
 
 
-def install(mixemt_pkg=None):
-    """Monkeypatch the reference's hot-path entry points."""
+def install(mixemt_pkg=None, with_consumers=False):
+    """Monkeypatch the reference's hot-path entry points.
+
+    ``with_consumers=True`` also replaces the functions that walk the N x H
+    matrices right after the fit with their device-side
+    forms from :mod:`mixemt_b200.consumers`; together with resident mode
+    (``MIXEMT_B200_RESIDENT=1``) the matrices are then read where they live."""
     if mixemt_pkg is None:
         import mixemt as mixemt_pkg  # the unmodified reference
     mixemt_pkg.preprocess.build_em_matrix = preprocess.build_em_matrix
     mixemt_pkg.em.run_em = em.run_em
     mixemt_pkg.em.em_step = em.em_step
+    if with_consumers:
+        mixemt_pkg.preprocess.reduce_em_matrix = consumers.reduce_em_matrix
+        mixemt_pkg.assemble._find_contribs_from_reads = consumers.find_contribs_from_reads
+        mixemt_pkg.assemble.assign_read_indexes = consumers.assign_read_indexes
     return mixemt_pkg

@@ -78,6 +78,11 @@ _PROTOS = {
     "mxb_matrix_data": (P, [P]),
     "mxb_matrix_argmax_rows": (ctypes.c_int, [P, P, P]),
     "mxb_matrix_destroy": (ctypes.c_int, [P]),
+    "mxb_matrix_gather_cols": (ctypes.c_int, [P, P, P, c_i64, c_void_pp]),
+    "mxb_matrix_vote_count": (ctypes.c_int, [P, P, P, P, P]),
+    "mxb_assign_reads": (ctypes.c_int, [P, P, P, P, c_i32, c_dbl, P]),
+    "mxb_matrix_download_rows": (ctypes.c_int, [P, P, c_i64, c_i64, P]),
+    "mxb_matrix_upload_rows": (ctypes.c_int, [P, P, c_i64, c_i64, P]),
     "mxb_matrix_fold_ranks": (ctypes.c_int, [P, P, c_dbl]),
     "mxb_em_create": (ctypes.c_int, [P, P, P, ctypes.c_int, c_void_pp]),
     "mxb_em_destroy": (ctypes.c_int, [P]),

@@ -334,39 +334,6 @@ static int p2p_setup(mxb_ctx *ctx) {
     return MXB_OK;
 }
 
-// First maximum of every row (numpy.argmax semantics; NaN wins like numpy).
-__global__ void argmax_rows_kernel(const double *__restrict__ m, int64_t n_rows,
-                                   int64_t n_cols, int64_t *__restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t r = warp; r < n_rows; r += n_warps) {
-        const double *row = m + r * n_cols;
-        double best = 0.0;
-        int64_t best_j = INT64_MAX;
-        bool best_nan = false;
-        for (int64_t j = lane; j < n_cols; j += 32) {
-            double v = row[j];
-            bool v_nan = (v != v);
-            if (best_j == INT64_MAX || (!best_nan && (v_nan || v > best))) {
-                best = v; best_j = j; best_nan = v_nan;
-            }
-        }
-        for (int off = 16; off > 0; off >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, best, off);
-            long long oj = __shfl_xor_sync(0xffffffffu, (long long)best_j, off);
-            int on = __shfl_xor_sync(0xffffffffu, (int)best_nan, off);
-            if (oj == INT64_MAX) continue;
-            bool take;
-            if (best_j == INT64_MAX) take = true;
-            else if (best_nan || on) take = on && (!best_nan || oj < best_j);
-            else take = (ov > best) || (ov == best && oj < best_j);
-            if (take) { best = ov; best_j = oj; best_nan = on; }
-        }
-        if (lane == 0) out[r] = best_j == INT64_MAX ? 0 : best_j;
-    }
-}
-
 }  // namespace mxb
 
 using namespace mxb;
@@ -557,26 +524,6 @@ int mxb_matrix_shape(const mxb_matrix *m, int64_t *n_rows, int64_t *n_cols) {
 }
 
 void *mxb_matrix_data(const mxb_matrix *m) { return m ? (void *)m->data : nullptr; }
-
-int mxb_matrix_argmax_rows(mxb_ctx *ctx, const mxb_matrix *m, int64_t *out_host) {
-    MXB_REQUIRE(ctx != nullptr && m != nullptr, "NULL argument");
-    if (m->n_rows == 0) return MXB_OK;
-    MXB_REQUIRE(out_host != nullptr, "out_host is NULL");
-    MXB_REQUIRE(m->n_cols > 0, "argmax of empty rows");
-    MXB_CUDA(cudaSetDevice(ctx->device));
-    int64_t *d = nullptr;
-    MXB_CUDA(cudaMalloc(&d, m->n_rows * sizeof(int64_t)));
-    int blocks = (int)std::min<int64_t>(ceil_div(m->n_rows, 8), (int64_t)ctx->num_sms * 8);
-    argmax_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(m->data, m->n_rows, m->n_cols, d);
-    ctx->launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(out_host, d, m->n_rows * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
-    if (e != cudaSuccess) { set_error("argmax_rows: %s", cudaGetErrorString(e)); return MXB_ERR_CUDA; }
-    return MXB_OK;
-}
 
 int mxb_matrix_destroy(mxb_matrix *m) {
     if (!m) return MXB_OK;

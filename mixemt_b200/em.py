@@ -14,7 +14,7 @@ import numpy
 from . import _lib
 from ._lib import lib, check, ptr
 from . import sharding
-from .runtime import DeviceMatrix, get_context, lookup_resident
+from .runtime import DeviceMatrix, get_context, lookup_resident, remember_resident, resident_mode
 
 
 def init_props(nhaps, alpha=1.0):
@@ -159,9 +159,15 @@ def run_em(read_hap_mat, weights, args):
             raise ValueError("read_hap_mat must be 2-dimensional")
         dev = DeviceMatrix.from_host(ctx, mat)
         owned = True
+    keep = resident_mode(args)
     try:
-        props, read_mix, _, _ = run_em_device(dev, weights, args)
+        props, read_mix, _, mix_dev = run_em_device(dev, weights, args, keep_device=keep)
     finally:
         if owned:
             dev.free()
+    if keep and mix_dev is not None and read_mix is not None:
+        # opt-in residency: the consumers in mixemt_b200.consumers find the HBM copy of
+        # the result through the (read-only) host array, see runtime.remember_resident
+        read_mix.flags.writeable = False
+        remember_resident(read_mix, mix_dev)
     return props, read_mix

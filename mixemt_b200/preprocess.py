@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import lib, check, ptr
-from .runtime import DeviceMatrix, get_context, remember_resident
+from .runtime import DeviceMatrix, get_context, remember_resident, resident_mode
 
 
 def pos_from_var(var):
@@ -272,8 +272,7 @@ def build_em_matrix(refseq, phylo, reads, haplogroups, args):
     if error is not None and (error[1] == "value" or h > 0):
         _raise_like_reference(error, tables, reads)
 
-    keep = bool(getattr(args, "b200_resident", False)) or \
-        os.environ.get("MIXEMT_B200_RESIDENT", "0") == "1"
+    keep = resident_mode(args)
     out, _, dmat, _ = build_matrix_from_csr(tables, csr, want_host=True, keep_device=keep)
     if keep and dmat is not None:
         # The device copy stays valid only while the host array is untouched:

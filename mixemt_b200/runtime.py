@@ -161,6 +161,13 @@ class DeviceMatrix(object):
 _resident = {}
 
 
+def resident_mode(args=None):
+    """Opt-in residency (``args.b200_resident`` or ``MIXEMT_B200_RESIDENT=1``):
+    matrices handed to the caller keep their HBM copy and are read-only."""
+    return bool(getattr(args, "b200_resident", False)) or \
+        os.environ.get("MIXEMT_B200_RESIDENT", "0") == "1"
+
+
 def remember_resident(host_arr, dev):
     key = id(host_arr)
 

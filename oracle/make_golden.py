@@ -19,6 +19,9 @@ its source is copied.  Outputs are small input/output vectors:
   golden_build17_cfg5.npz  ... on the config-5 tables
   golden_em17.npz        run_em on Build-17 sub-problems (inputs are signature
                          strings; the matrix is rebuilt by the code under test)
+  golden_consumers.npz   assemble._find_contribs_from_reads / assign_read_indexes and
+                         preprocess.reduce_em_matrix on seeded stand-ins for run_em's
+                         output (oracle_np.synthetic_em_result)
 """
 import argparse
 import os
@@ -216,10 +219,41 @@ def cfg5():
                         reads=np.array("\n".join(reads)), mat=mat)
 
 
+def consumers():
+    """Reference outputs of the functions that consume run_em's result
+    (assemble.py:102-124, :267-334; preprocess.py:230-251) on seeded inputs."""
+    from mixemt import assemble
+    from oracle import oracle_np
+    out = {}
+    for seed in (71, 72):
+        props, mix, wts = oracle_np.synthetic_em_result(seed)
+        haps = ["hg%d" % j for j in range(mix.shape[1])]
+        for min_reads in (1, 60, 400):
+            cons = assemble._find_contribs_from_reads(mix, wts, ns(min_reads=min_reads))
+            out["s%d_contribs_r%d" % (seed, min_reads)] = np.asarray(cons, dtype=np.int64)
+        top = np.argsort(props)[::-1][:4]
+        contribs = [["hap%d" % (k + 1), haps[j], props[j]] for k, j in enumerate(top.tolist())]
+        out["s%d_top" % seed] = top.astype(np.int64)
+        for tag, fold, cons in (("f2", 2.0, contribs), ("f1p2", 1.2, contribs[:2]),
+                                ("single", 2.0, contribs[:1])):
+            res = assemble.assign_read_indexes(cons, (props, mix), haps, list(range(len(mix))), fold)
+            assign = np.full(len(mix), -2, dtype=np.int32)
+            for name, rows in res.items():
+                code = -1 if name == 'unassigned' else int(name[3:]) - 1
+                assign[sorted(rows)] = code
+            assert (assign > -2).all()
+            out["s%d_assign_%s" % (seed, tag)] = assign
+        red, new_haps = preprocess.reduce_em_matrix(mix, haps, contribs)
+        out["s%d_reduced" % seed] = red
+        out["s%d_reduced_cols" % seed] = np.asarray([haps.index(x) for x in new_haps])
+    np.savez_compressed(os.path.join(GOLD, "golden_consumers.npz"), **out)
+    print("golden_consumers.npz written")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["toy", "build17", "cfg5"]
+    which = sys.argv[1:] or ["toy", "build17", "cfg5", "consumers"]
     for name in which:
-        {"toy": toy, "build17": build17, "cfg5": cfg5}[name]()
+        {"toy": toy, "build17": build17, "cfg5": cfg5, "consumers": consumers}[name]()
     for f in sorted(os.listdir(GOLD)):
         print("%-28s %8.1f KB" % (f, os.path.getsize(os.path.join(GOLD, f)) / 1024.0))

@@ -204,3 +204,58 @@ def em_step_scipy(read_hap_mat, weights, ln_props, read_mix_mat):
     new_props = sp_logsumexp(read_mix_mat, axis=0, b=np.asarray(weights).reshape((-1, 1)))
     new_props -= sp_logsumexp(new_props)
     return read_mix_mat, new_props
+
+
+# ---------------------------------------------------------------------------
+# consumers of the EM result
+# ---------------------------------------------------------------------------
+def reduce_em_matrix(em_mat, haplogroups, contrib_props):
+    """preprocess.py:230-251."""
+    keep = {con[1] for con in contrib_props}
+    indexes = [i for i in range(len(haplogroups)) if haplogroups[i] in keep]
+    return em_mat[:, indexes], [haplogroups[i] for i in indexes]
+
+
+def find_contribs_from_reads(read_hap_mat, wts, min_reads):
+    """assemble.py:102-124: weighted votes of the row maxima, in dict order."""
+    best = np.argmax(read_hap_mat, 1)
+    votes = {}
+    for hap, count in zip(best.tolist(), np.asarray(wts).tolist()):
+        votes[hap] = votes.get(hap, 0) + count
+    return [con for con in votes if votes[con] >= min_reads]
+
+
+def assign_read_indexes(contribs, em_results, haps, n_reads, min_fold):
+    """assemble.py:267-334 (with _find_best_n_for_read, :267-281)."""
+    props, read_hap_mat = em_results
+    out = {}
+    ln_fold = np.log(min_fold)
+    log_props = np.log(props)
+    index_to_hap = {haps.index(group): hap_n for hap_n, group, _ in contribs}
+    for i in range(n_reads):
+        if len(contribs) > 1:
+            probs = read_hap_mat[i, ] - log_props
+            order = np.argsort(probs)[::-1]
+            top = [j for j in order.tolist() if j in index_to_hap][:2]
+            if probs[top[0]] - probs[top[1]] >= ln_fold:
+                out.setdefault(index_to_hap[top[0]], set()).add(i)
+            else:
+                out.setdefault('unassigned', set()).add(i)
+        else:
+            out.setdefault(contribs[0][0], set()).add(i)
+    return out
+
+
+def synthetic_em_result(seed, n=400, h=96):
+    """A seeded stand-in for run_em's output (props, log responsibilities,
+    weights) with exact ties between columns, shared by oracle/make_golden.py
+    and the tests so that only the reference's *outputs* are stored."""
+    rs = np.random.RandomState(seed)
+    lik = -rs.gamma(2.0, 6.0, size=(n, h))
+    lik[:, 7] = lik[:, 3]                      # tied columns: first maximum wins
+    lik[rs.rand(n, h) < 0.3] = 0.0             # many exact row-maximum ties
+    props = rs.dirichlet([0.3] * h)
+    z = lik + np.log(props)
+    z = z - logsumexp(z, axis=1).reshape((-1, 1))
+    wts = rs.randint(1, 40, size=n)
+    return props, z, wts

@@ -126,3 +126,48 @@ def test_against_live_reference(phylo17):
     p_c, m_c, _ = oracle_c.run_em(sub, mix.weights[:12], inits, 200, 1e-4)
     assert np.array_equal(p_np, p_ref) and np.array_equal(m_np, m_ref)
     assert np.abs(p_c - p_ref).max() < 1e-13 and np.abs(m_c - m_ref).max() < 1e-10
+
+
+# ---- consumers of the EM result ---------------------------
+def _decode_assign(res, n):
+    out = np.full(n, -2, dtype=np.int32)
+    for name, rows in res.items():
+        out[sorted(rows)] = -1 if name == 'unassigned' else int(name[3:]) - 1
+    return out
+
+
+@pytest.mark.parametrize("seed", [71, 72])
+def test_consumers_golden(seed):
+    g = load_golden("golden_consumers.npz")
+    props, mix, wts = oracle_np.synthetic_em_result(seed)
+    haps = ["hg%d" % j for j in range(mix.shape[1])]
+    for min_reads in (1, 60, 400):
+        got = oracle_np.find_contribs_from_reads(mix, wts, min_reads)
+        assert got == g["s%d_contribs_r%d" % (seed, min_reads)].tolist()
+    top = g["s%d_top" % seed].tolist()
+    contribs = [["hap%d" % (k + 1), haps[j], props[j]] for k, j in enumerate(top)]
+    for tag, fold, cons in (("f2", 2.0, contribs), ("f1p2", 1.2, contribs[:2]),
+                            ("single", 2.0, contribs[:1])):
+        res = oracle_np.assign_read_indexes(cons, (props, mix), haps, len(mix), fold)
+        assert np.array_equal(_decode_assign(res, len(mix)), g["s%d_assign_%s" % (seed, tag)])
+    red, new_haps = oracle_np.reduce_em_matrix(mix, haps, contribs)
+    assert np.array_equal(red, g["s%d_reduced" % seed])
+    assert [haps.index(x) for x in new_haps] == g["s%d_reduced_cols" % seed].tolist()
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference not mounted")
+def test_consumers_live_reference():
+    refload.load()
+    from mixemt import assemble, preprocess as ref_pre
+    props, mix, wts = oracle_np.synthetic_em_result(99, n=150, h=40)
+    haps = ["hg%d" % j for j in range(40)]
+    ns = make_args(min_reads=25)
+    assert assemble._find_contribs_from_reads(mix, wts, ns) == \
+        oracle_np.find_contribs_from_reads(mix, wts, 25)
+    top = np.argsort(props)[::-1][:3].tolist()
+    contribs = [["hap%d" % (k + 1), haps[j], props[j]] for k, j in enumerate(top)]
+    ref = assemble.assign_read_indexes(contribs, (props, mix), haps, list(range(150)), 2.0)
+    got = oracle_np.assign_read_indexes(contribs, (props, mix), haps, 150, 2.0)
+    assert dict(ref) == got
+    a, b = ref_pre.reduce_em_matrix(mix, haps, contribs), oracle_np.reduce_em_matrix(mix, haps, contribs)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1]
