@@ -93,6 +93,27 @@ int mxb_sig_parse(const char *buf, const int64_t *offsets, int64_t n_rows,
                   int32_t *pos_idx, uint8_t *base_code,
                   int64_t *bad_row, int64_t *bad_pos);
 
+/* ---- fragments -> unique signatures (host only; replaces the string round trip of
+ *      preprocess.read_signature / reduce_reads and the sorted()/weights of
+ *      build_em_input, mixemt/preprocess.py:142-148, :163-174, :218-220) ---------- */
+typedef struct mxb_sigset mxb_sigset;
+/* frag_ptr[n_frag+1] delimits each fragment's observations: pos[] 0-based reference
+ * positions ascending inside a fragment (like sorted(obs_by_pos)), base[] ASCII.
+ * Equal observation lists collapse into one signature; rows are ordered like the
+ * reference orders them (string sort of "pos:base,pos:base,..."). */
+int mxb_reduce_reads(const int64_t *frag_ptr, const int32_t *pos, const uint8_t *base,
+                     int64_t n_frag, mxb_sigset **out);
+int mxb_sigset_sizes(const mxb_sigset *ss, int64_t *n_sig, int64_t *n_obs, int64_t *n_chars);
+/* Every output is nullable.  row_ptr[n_sig+1], pos/base[n_obs]: CSR of the rows;
+ * weights[n_sig]: fragments per row; first_frag[n_sig]: lowest fragment index of the
+ * row; sig_of_frag[n_frag]: row of every fragment; frag_order[n_frag]: fragment
+ * indexes grouped by row (ascending inside a row, weights[] delimit the groups);
+ * strings[n_chars] + str_offsets[n_sig+1]: the signature strings, concatenated. */
+int mxb_sigset_export(const mxb_sigset *ss, int64_t *row_ptr, int32_t *pos, uint8_t *base,
+                      int64_t *weights, int64_t *first_frag, int64_t *sig_of_frag,
+                      int64_t *frag_order, char *strings, int64_t *str_offsets);
+int mxb_sigset_destroy(mxb_sigset *ss);
+
 /* ---- haplotype tables (replaces HapVarBaseMatrix, preprocess.py:23-96) ----- */
 /* n_sym symbols (codes 0..n_sym-1).  hit[p] = log(1-mut_prob), miss[p] =
  * log(mut_prob/3), computed by the host with math.log so they are

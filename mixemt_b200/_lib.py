@@ -67,6 +67,11 @@ _PROTOS = {
     "mxb_sig_count": (ctypes.c_int, [P, P, c_i64, P]),
     "mxb_sig_parse": (ctypes.c_int, [P, P, c_i64, P, c_i64, P, P, P, P,
                                      ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "mxb_reduce_reads": (ctypes.c_int, [P, P, P, c_i64, c_void_pp]),
+    "mxb_sigset_sizes": (ctypes.c_int, [P, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
+                                        ctypes.POINTER(c_i64)]),
+    "mxb_sigset_export": (ctypes.c_int, [P, P, P, P, P, P, P, P, P, P]),
+    "mxb_sigset_destroy": (ctypes.c_int, [P]),
     "mxb_phylo_pack": (ctypes.c_int, [P, c_i32, c_i32, c_i32, P, P, P, P, P, P, c_void_pp]),
     "mxb_phylo_destroy": (ctypes.c_int, [P]),
     "mxb_build_matrix": (ctypes.c_int, [P, P, c_i64, P, P, P, P, P, c_void_pp,

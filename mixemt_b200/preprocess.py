@@ -297,3 +297,154 @@ def build_em_matrix_device(refseq, phylo, reads, haplogroups, args=None, want_co
     _, counts, dmat, ms = build_matrix_from_csr(tables, csr, want_host=False,
                                                 want_counts=want_counts, keep_device=True)
     return dmat, counts, ms
+
+
+# ---- fragments -> signatures on binary observations ------------
+class ReducedReads(object):
+    """Unique signatures of a set of fragments, rows in the reference's order
+    (``sorted(read_sigs)``, preprocess.py:219).
+
+    ``row_ptr`` / ``pos`` / ``base`` are the rows' observations (0-based
+    reference positions, ASCII bases); ``weights[r]`` the number of fragments
+    carrying row ``r`` (preprocess.py:220); ``sig_of_frag[f]`` the row of fragment
+    ``f``; ``frag_order`` the fragment indexes grouped by row (fragment order
+    inside a row, like the id lists ``reduce_reads`` builds, :172-173)."""
+
+    def __init__(self, row_ptr, pos, base, weights, first_frag, sig_of_frag, frag_order,
+                 str_buf, str_off):
+        self.row_ptr, self.pos, self.base = row_ptr, pos, base
+        self.weights, self.first_frag = weights, first_frag
+        self.sig_of_frag, self.frag_order = sig_of_frag, frag_order
+        self._str_buf, self._str_off = str_buf, str_off
+        self._signatures = None
+
+    @property
+    def n_rows(self):
+        return len(self.weights)
+
+    @property
+    def signatures(self):
+        """The rows as the reference's signature strings (preprocess.py:142-148)."""
+        if self._signatures is None:
+            text = self._str_buf.tobytes().decode("ascii")
+            off = self._str_off.tolist()
+            self._signatures = [text[off[i]:off[i + 1]] for i in range(self.n_rows)]
+        return self._signatures
+
+    def fragments_of_rows(self):
+        """List (per row) of arrays of fragment indexes, fragment order."""
+        return np.split(self.frag_order, np.cumsum(self.weights)[:-1]) if self.n_rows else []
+
+    def csr(self, tables):
+        """``SignatureCSR`` against a packed ``HapVarBaseMatrix``; raises
+        ``KeyError(pos)`` for the first row holding a position that is not a
+        variant site, like ``mut_prob[pos]`` does (preprocess.py:79-84)."""
+        pos = self.pos.astype(np.int64)
+        ok = (pos >= 0) & (pos < len(tables.pos2idx))
+        idx = np.full(len(pos), -1, dtype=np.int32)
+        idx[ok] = tables.pos2idx[pos[ok]]
+        if (idx < 0).any():
+            raise KeyError(int(pos[int(np.argmax(idx < 0))]))
+        return SignatureCSR(self.row_ptr, idx, tables.sym2code[self.base])
+
+
+def reduce_reads_arrays(frag_ptr, pos, base):
+    """``reduce_reads`` + the ordering of ``build_em_input`` (preprocess.py:163-174,
+    :218-220) for fragments given as arrays: ``frag_ptr[F+1]`` delimits each
+    fragment's observations, ``pos`` (0-based, ascending inside a fragment) and
+    ``base`` (ASCII codes or a bytes object).  Returns :class:`ReducedReads`."""
+    frag_ptr = np.ascontiguousarray(frag_ptr, dtype=np.int64)
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    if isinstance(base, (bytes, bytearray)):
+        base = np.frombuffer(bytes(base), dtype=np.uint8)
+    base = np.ascontiguousarray(base, dtype=np.uint8)
+    n_frag = len(frag_ptr) - 1
+    if n_frag < 0 or (n_frag >= 0 and len(frag_ptr) and frag_ptr[0] != 0) or \
+            (n_frag > 0 and (np.diff(frag_ptr) < 0).any()) or \
+            (len(frag_ptr) and frag_ptr[-1] != len(pos)) or len(pos) != len(base):
+        raise ValueError("inconsistent fragment arrays")
+    handle = ctypes.c_void_p()
+    check(lib.mxb_reduce_reads(ptr(frag_ptr), ptr(pos), ptr(base), n_frag, ctypes.byref(handle)))
+    try:
+        n_sig, n_obs, n_chars = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(lib.mxb_sigset_sizes(handle, ctypes.byref(n_sig), ctypes.byref(n_obs),
+                                   ctypes.byref(n_chars)))
+        n_sig, n_obs, n_chars = n_sig.value, n_obs.value, n_chars.value
+        row_ptr = np.zeros(n_sig + 1, dtype=np.int64)
+        r_pos = np.empty(n_obs, dtype=np.int32)
+        r_base = np.empty(n_obs, dtype=np.uint8)
+        weights = np.empty(n_sig, dtype=np.int64)
+        first = np.empty(n_sig, dtype=np.int64)
+        sig_of_frag = np.empty(n_frag, dtype=np.int64)
+        frag_order = np.empty(n_frag, dtype=np.int64)
+        str_buf = np.empty(n_chars, dtype=np.uint8)
+        str_off = np.zeros(n_sig + 1, dtype=np.int64)
+        check(lib.mxb_sigset_export(handle, ptr(row_ptr), ptr(r_pos), ptr(r_base), ptr(weights),
+                                    ptr(first), ptr(sig_of_frag), ptr(frag_order), ptr(str_buf),
+                                    ptr(str_off)))
+    finally:
+        lib.mxb_sigset_destroy(handle)
+    return ReducedReads(row_ptr, r_pos, r_base, weights, first, sig_of_frag, frag_order, str_buf,
+                        str_off)
+
+
+def flatten_read_obs(read_obs):
+    """``{read_id: {pos: base}}`` (what process_reads returns, preprocess.py:99-139)
+    -> ``(ids, frag_ptr, pos, base)``; ``None`` for the arrays when an observation
+    is not a single ASCII character (the caller then keeps the string route)."""
+    ids = list(read_obs)
+    lens, pos, bases = [], [], []
+    for rid in ids:
+        obs = read_obs[rid]
+        keys = sorted(obs)
+        lens.append(len(keys))
+        pos.extend(keys)
+        bases.extend(map(obs.__getitem__, keys))
+    joined = "".join(bases)
+    if len(joined) != len(bases) or not joined.isascii() or \
+            (pos and (min(pos) < -2**31 or max(pos) >= 2**31)):
+        return ids, None, None, None
+    frag_ptr = np.zeros(len(ids) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(lens, dtype=np.int64), out=frag_ptr[1:])
+    return ids, frag_ptr, np.asarray(pos, dtype=np.int32), \
+        np.frombuffer(joined.encode("ascii"), dtype=np.uint8)
+
+
+def reduce_reads(read_obs):
+    """
+    Drop-in for reference preprocess.reduce_reads (preprocess.py:163-174):
+    signature string -> list of the read ids carrying it, signatures in order of
+    first appearance and ids in input order, like the reference's defaultdict.
+    """
+    ids, frag_ptr, pos, base = flatten_read_obs(read_obs)
+    if frag_ptr is None:     # exotic observations (multi-character / non-ASCII bases)
+        read_sigs = {}
+        for rid in ids:
+            obs = read_obs[rid]
+            sig = ','.join(["%d:%s" % (p, obs[p]) for p in sorted(obs)])
+            read_sigs.setdefault(sig, []).append(rid)
+        return read_sigs
+    red = reduce_reads_arrays(frag_ptr, pos, base)
+    sigs = red.signatures
+    groups = red.fragments_of_rows()
+    read_sigs = {}
+    for row in np.argsort(red.first_frag, kind="stable").tolist():
+        read_sigs[sigs[row]] = [ids[f] for f in groups[row].tolist()]
+    return read_sigs
+
+
+def build_em_input_arrays(frag_ptr, pos, base, refseq, phylo, args=None, keep_device=False):
+    """``build_em_input`` (preprocess.py:201-227) from binary observations, without
+    signature strings.  Returns ``(em_matrix, weights, haplogroups, reduced)``:
+    the matrix is a host ndarray (or a ``DeviceMatrix`` with ``keep_device``),
+    rows ordered like the reference's ``sorted(read_sigs)``; ``reduced`` is the
+    :class:`ReducedReads` that maps rows back to fragments."""
+    red = reduce_reads_arrays(frag_ptr, pos, base)
+    haplogroups = sorted(phylo.hap_var)
+    tables = HapVarBaseMatrix(refseq, phylo, haplogroups=haplogroups).pack()
+    if red.n_rows and (np.diff(red.row_ptr) == 0).any():
+        raise ValueError("empty read signature")        # ''.split(':') in preprocess.py:158
+    csr = red.csr(tables)
+    out, _, dmat, _ = build_matrix_from_csr(tables, csr, want_host=not keep_device,
+                                            keep_device=keep_device)
+    return (dmat if keep_device else out), red.weights, haplogroups, red

@@ -22,6 +22,8 @@ its source is copied.  Outputs are small input/output vectors:
   golden_consumers.npz   assemble._find_contribs_from_reads / assign_read_indexes and
                          preprocess.reduce_em_matrix on seeded stand-ins for run_em's
                          output (oracle_np.synthetic_em_result)
+  golden_reduce.npz      preprocess.reduce_reads and the row order / weights of
+                         build_em_input on seeded fragments (oracle_np.synthetic_read_obs)
 """
 import argparse
 import os
@@ -250,10 +252,28 @@ def consumers():
     print("golden_consumers.npz written")
 
 
+def reduce():
+    """Reference reduce_reads + the ordering of build_em_input (preprocess.py:163-174,
+    :218-220) on seeded fragments; only the outputs are stored."""
+    from oracle import oracle_np
+    out = {}
+    for seed in (81, 82):
+        read_obs = oracle_np.synthetic_read_obs(seed)
+        read_sigs = preprocess.reduce_reads(read_obs)
+        reads = sorted(read_sigs)
+        out["s%d_first_order" % seed] = np.array("\n".join(read_sigs))     # dict order
+        out["s%d_sorted" % seed] = np.array("\n".join(reads))
+        out["s%d_weights" % seed] = np.array([len(read_sigs[r]) for r in reads])
+        out["s%d_ids_of_row5" % seed] = np.array("\n".join(read_sigs[reads[5]]))
+    np.savez_compressed(os.path.join(GOLD, "golden_reduce.npz"), **out)
+    print("golden_reduce.npz written")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["toy", "build17", "cfg5", "consumers"]
+    which = sys.argv[1:] or ["toy", "build17", "cfg5", "consumers", "reduce"]
     for name in which:
-        {"toy": toy, "build17": build17, "cfg5": cfg5, "consumers": consumers}[name]()
+        {"toy": toy, "build17": build17, "cfg5": cfg5, "consumers": consumers,
+         "reduce": reduce}[name]()
     for f in sorted(os.listdir(GOLD)):
         print("%-28s %8.1f KB" % (f, os.path.getsize(os.path.join(GOLD, f)) / 1024.0))

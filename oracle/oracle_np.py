@@ -259,3 +259,38 @@ def synthetic_em_result(seed, n=400, h=96):
     z = z - logsumexp(z, axis=1).reshape((-1, 1))
     wts = rs.randint(1, 40, size=n)
     return props, z, wts
+
+
+# ---------------------------------------------------------------------------
+# fragments -> signatures
+# ---------------------------------------------------------------------------
+def read_signature(obs_by_pos):
+    """preprocess.py:142-148."""
+    return ','.join(["%d:%s" % (pos, obs_by_pos[pos]) for pos in sorted(obs_by_pos)])
+
+
+def reduce_reads(read_obs):
+    """preprocess.py:163-174."""
+    read_sigs = {}
+    for read_id in read_obs:
+        read_sigs.setdefault(read_signature(read_obs[read_id]), []).append(read_id)
+    return read_sigs
+
+
+def synthetic_read_obs(seed, n_frag=3000, n_pos=300, max_pos=16569):
+    """Seeded ``{read_id: {pos: base}}`` with duplicates, empty fragments and
+    positions of different digit counts (so that string order != numeric order)."""
+    rs = np.random.RandomState(seed)
+    positions = np.sort(rs.choice(max_pos, size=n_pos, replace=False))
+    positions[:3] = [7, 9, 10]
+    positions = np.unique(positions)
+    read_obs = {}
+    for f in range(n_frag):
+        a = rs.randint(0, len(positions) - 1)
+        k = rs.randint(0, 9)
+        obs = {}
+        for p in positions[a:a + k].tolist():
+            shift = rs.randint(1, 4) if rs.rand() < 0.03 else 0
+            obs[p] = "ACGT"[(p + shift) % 4]
+        read_obs["frag%d" % f] = obs
+    return read_obs
