@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--fragments", type=int, default=1000000,
                     help="fragments per GPU (config 2: 1M)")
+    ap.add_argument("--rows", type=int, default=0,
+                    help="signature rows per GPU drawn without dedupe (config-3 shard sizes, "
+                         "e.g. 1250000); 0 = the config-2 workload of --fragments")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -55,16 +58,27 @@ def parse_args():
     return ap.parse_args()
 
 
-def load_workload(fragments, seed, strings=False):
+MIXTURE5 = [("H1", 0.6), ("L3e", 0.25), ("U5a1", 0.1), ("M7", 0.04), ("D4a", 0.01)]
+
+
+def load_workload(fragments, seed, strings=False, rows=0):
     from mixemt_b200.phylo_tables import PhyloTables
     from mixemt_b200 import synth
     phylo = PhyloTables.load(os.path.join(GOLDEN, "phylotree17.npz"))
     haps = sorted(phylo.hap_var)
-    mix = synth.make_mixture(phylo, phylo.refseq, MIXTURE, fragments, seed=seed, strings=strings)
+    if rows > 0:
+        mix = synth.random_rows(phylo, phylo.refseq, MIXTURE5, rows, seed=seed)
+    else:
+        mix = synth.make_mixture(phylo, phylo.refseq, MIXTURE, fragments, seed=seed,
+                                 strings=strings)
     return phylo, haps, mix
 
 
-def workload_name(fragments, n_rows, n_hap):
+def workload_name(fragments, n_rows, n_hap, rows=0):
+    if rows > 0:
+        return ("config3 shard: 5-way mixture H1/L3e/U5a1/M7/D4a 60/25/10/4/1, %d signature rows "
+                "per GPU x %d Phylotree-17 haplotypes (fp64 matrix %.2f GB per GPU)"
+                % (n_rows, n_hap, n_rows * n_hap * 8 / 1e9))
     return ("config2: 3-way mixture H1/L3e/U5a1 50/30/20, %d fragments x 300bp -> %d unique "
             "signatures x %d Phylotree-17 haplotypes (fp64 matrix %.2f GB)"
             % (fragments, n_rows, n_hap, n_rows * n_hap * 8 / 1e9))
@@ -276,7 +290,9 @@ def run_b200(opts):
         return float(t.item())
 
     # ---- workload: every rank its own shard -------------------------------------
-    phylo, haps, mix = load_workload(opts.fragments, opts.seed + rank)
+    phylo, haps, mix = load_workload(opts.fragments, opts.seed + rank, rows=opts.rows)
+    if opts.rows > 400000:
+        opts.no_e2e = True      # the drop-in call needs two N x H host arrays
     tables = HapVarBaseMatrix(phylo.refseq, phylo, haps).pack()
     csr = mix.csr(tables)
     n, h = csr.n_rows, len(haps)
@@ -380,7 +396,7 @@ def run_b200(opts):
                 "steps": opts.steps, "warmup": opts.warmup,
                 "ms_per_step": 1e3 * dev_s / opts.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(opts.fragments, n, h),
+                "config": {"workload": workload_name(opts.fragments, n, h, opts.rows),
                            "rows_per_gpu": n, "haplotypes": h, "parallelism":
                            ("rows sharded x%d, H column sums exchanged per iteration by %s"
                             % (world, "peer stores inside the EM tail kernel (CUDA IPC over NVLink)"

@@ -329,6 +329,175 @@ em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
     if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
 }
 
+// ---- fused E+M pass for two restarts at once ---------------------------------------
+// Restarts of one run_em call share the matrix (em.py:117-156), so two of them can
+// share each read of L: the pass is HBM-bound and the fp64 pipe is ~20 % busy.  Same
+// streaming structure as em_pass_fast_kernel; a thread keeps the proportions and the
+// column sums of BOTH restarts in registers (96 of its 128), so a staged row is read
+// from shared memory twice -- once for the two dot products, once for the two
+// column-sum updates -- and a second block barrier per row pair releases the stages.
+// The four (row, restart) dot products of a row pair ride one butterfly.
+template <int NC>
+__global__ void __launch_bounds__(kPassThreads, 1)
+em_pass_pair_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
+                    const double *__restrict__ weights, const double *__restrict__ pi_a0,
+                    const double *__restrict__ pi_a1, const double *__restrict__ pi_b0,
+                    const double *__restrict__ pi_b1, EmState *__restrict__ st,
+                    double *__restrict__ partials_a, double *__restrict__ partials_b,
+                    int n_stages) {
+    static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
+    const int done_a = st[0].done, done_b = st[1].done;
+    if (done_a && done_b) return;
+    const double *__restrict__ pia = st[0].cur ? pi_a1 : pi_a0;
+    const double *__restrict__ pib = st[1].cur ? pi_b1 : pi_b0;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t row_bytes = (uint32_t)(ld * sizeof(double));
+    double *scratch = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * row_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int n_my = (int)(r_end - r_begin);
+    const unsigned char *my_rows = reinterpret_cast<const unsigned char *>(lin + r_begin * ld);
+    const double *my_w = weights + r_begin;
+    const uint32_t stages_u32 = smem_u32(smem_raw);
+    const uint32_t full_u32 = smem_u32(full);
+
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 0; q < n_my && q < n_stages; ++q) {
+            mbar_expect_tx(&full[q], row_bytes);
+            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
+                      &full[q]);
+        }
+    }
+
+    const int n_chunks = (int)(ld >> 1);
+    double2 pa[NC], pb[NC], ta[NC], tb[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int c = tid + k * kPassThreads;
+        const bool in = c < n_chunks;
+        pa[k] = in ? reinterpret_cast<const double2 *>(pia)[c] : make_double2(0.0, 0.0);
+        pb[k] = in ? reinterpret_cast<const double2 *>(pib)[c] : make_double2(0.0, 0.0);
+        ta[k] = make_double2(0.0, 0.0);
+        tb[k] = make_double2(0.0, 0.0);
+    }
+    const bool last_live = tid + (NC - 1) * kPassThreads < n_chunks;
+
+    int stage = 0;
+    uint32_t phase = 0;
+    int bad = 0;
+    // quarter q4 = lane >> 3 owns pair (row g = q4 >> 1, restart = q4 & 1) after the butterfly
+    const int q4 = lane >> 3;
+    const bool mine_done = (q4 & 1) ? done_b != 0 : done_a != 0;
+    for (int q0 = 0; q0 < n_my; q0 += kPassGroup) {
+        const int q_mine = q0 + (q4 >> 1);
+        const double w_mine = (q_mine < n_my) ? my_w[q_mine] : 0.0;
+        int s_of[kPassGroup];
+        double d[4];  // [row][restart]
+        int s = stage;
+        uint32_t ph = phase;
+#pragma unroll
+        for (int g = 0; g < kPassGroup; ++g) {
+            s_of[g] = s;
+            double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+            if (q0 + g < n_my) {
+                mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
+                const double2 *srow = reinterpret_cast<const double2 *>(
+                    smem_raw + (size_t)s * row_bytes) + tid;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    if (k < NC - 1 || last_live) {
+                        const double2 l = srow[k * kPassThreads];
+                        ax = fma(l.x, pa[k].x, ax);
+                        ay = fma(l.y, pa[k].y, ay);
+                        bx = fma(l.x, pb[k].x, bx);
+                        by = fma(l.y, pb[k].y, by);
+                    }
+                }
+            }
+            d[2 * g] = ax + ay;
+            d[2 * g + 1] = bx + by;
+            if (++s == n_stages) { s = 0; ph ^= 1u; }
+        }
+        // four sums in one butterfly: halves keep a row, quarters keep a restart
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        double e0 = (up16 ? d[2] : d[0]) + shfl_xor_f64(up16 ? d[0] : d[2], 16);
+        double e1 = (up16 ? d[3] : d[1]) + shfl_xor_f64(up16 ? d[1] : d[3], 16);
+        double v = (up8 ? e1 : e0) + shfl_xor_f64(up8 ? e0 : e1, 8);
+        v += shfl_xor_f64(v, 4);
+        v += shfl_xor_f64(v, 2);
+        v += shfl_xor_f64(v, 1);
+        // scratch[pair q4][warp]; the loop's second barrier separates consecutive groups
+        if ((lane & 7) == 0) scratch[q4 * kPassWarps + warp] = v;
+        __syncthreads();
+        // 16 warp totals per pair: lane reads two of them, 3-step butterfly inside its quarter
+        double t = scratch[q4 * kPassWarps + (lane & 7)] + scratch[q4 * kPassWarps + 8 + (lane & 7)];
+        t += shfl_xor_f64(t, 4);
+        t += shfl_xor_f64(t, 2);
+        t += shfl_xor_f64(t, 1);
+        double coef_mine = 0.0;
+        if (w_mine != 0.0) {
+            coef_mine = w_mine / t;
+            bad |= (t == 0.0 && !mine_done);
+        }
+        const double c0a = __shfl_sync(0xffffffffu, coef_mine, 0);
+        const double c0b = __shfl_sync(0xffffffffu, coef_mine, 8);
+        const double c1a = __shfl_sync(0xffffffffu, coef_mine, 16);
+        const double c1b = __shfl_sync(0xffffffffu, coef_mine, 24);
+#pragma unroll
+        for (int g = 0; g < kPassGroup; ++g) {
+            if (q0 + g < n_my) {
+                const double ca = g ? c1a : c0a, cb = g ? c1b : c0b;
+                const double2 *srow = reinterpret_cast<const double2 *>(
+                    smem_raw + (size_t)s_of[g] * row_bytes) + tid;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    if (k < NC - 1 || last_live) {
+                        const double2 l = srow[k * kPassThreads];
+                        ta[k].x = fma(ca, l.x, ta[k].x);
+                        ta[k].y = fma(ca, l.y, ta[k].y);
+                        tb[k].x = fma(cb, l.x, tb[k].x);
+                        tb[k].y = fma(cb, l.y, tb[k].y);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // both staged rows have been read twice: release them
+        if (tid == 0) {
+#pragma unroll
+            for (int g = 0; g < kPassGroup; ++g) {
+                const int q = q0 + g + n_stages;
+                if (q < n_my) {
+                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_of[g];
+                    mbar_expect_tx_u32(bar, row_bytes);
+                    bulk_load_u32(stages_u32 + (uint32_t)s_of[g] * row_bytes,
+                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
+                }
+            }
+        }
+        stage = s;
+        phase = ph;
+    }
+
+    double2 *out_a = reinterpret_cast<double2 *>(partials_a + (size_t)blockIdx.x * ld);
+    double2 *out_b = reinterpret_cast<double2 *>(partials_b + (size_t)blockIdx.x * ld);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int c = tid + k * kPassThreads;
+        if (c < n_chunks) { out_a[c] = ta[k]; out_b[c] = tb[k]; }
+    }
+    if (bad) atomicOr(&st[(q4 & 1)].bad, 1);
+}
+
 // ---- general path: any shape, two passes over L -------------------------------
 // coef_i = w_i / sum_j L_ij pi_j, one warp per row.
 __global__ void __launch_bounds__(256)
@@ -517,11 +686,16 @@ constexpr unsigned long long kP2PTimeoutNs = 120ull * 1000000000ull;
 
 template <bool kP2P>
 __global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(kFinThreads)
-em_finish_kernel(const double *__restrict__ partials, int n_part, int64_t n_cols, int64_t ld,
-                 double *__restrict__ lnp0, double *__restrict__ lnp1,
-                 double *__restrict__ pi0, double *__restrict__ pi1,
-                 EmState *__restrict__ st, P2PArgs pa) {
+em_finish_kernel(const double *partials, int n_part, int64_t n_cols, int64_t ld,
+                 double *lnp0, double *lnp1, double *pi0, double *pi1, EmState *st, P2PArgs pa) {
     static_assert(kFinThreads == 1024, "cluster_sum assumes 32 warps");
+    {   // blockIdx.y = restart slot of a batched session (one cluster per slot)
+        const size_t slot = blockIdx.y;
+        st += slot;
+        partials += slot * (size_t)n_part * ld;
+        lnp0 += slot * ld; lnp1 += slot * ld;
+        pi0 += slot * ld; pi1 += slot * ld;
+    }
     if (st->done) return;  // same answer in every CTA: the block below is the only writer
     __shared__ double wsum[2][kFinThreads / 32];
     __shared__ double slots[2][kFinCtas];
@@ -726,6 +900,9 @@ struct mxb_em {
     // general path
     int row_blocks = 0, col_blocks = 0;
     bool fused_tail = false;  // colreduce + update in one cluster launch (em_finish_kernel)
+    // Restart slots: a batched session (run_em with n_multi > 1) iterates two restarts per
+    // read of L.  Slot s lives at lnp[b] + s*ld, pi[b] + s*ld, partials + s*n_part*ld, state + s.
+    int n_slots = 1;
     bool zero_iter = false;  // last iterate() ran no iteration
 };
 
@@ -748,12 +925,45 @@ static pass_fn pick_pass(int nc) {
     return nullptr;
 }
 
+typedef void (*pair_fn)(const double *, int64_t, int64_t, const double *, const double *,
+                        const double *, const double *, const double *, EmState *, double *,
+                        double *, int);
+static pair_fn pick_pair(int nc) {
+    switch (nc) {
+        case 1: return em_pass_pair_kernel<1>;
+        case 2: return em_pass_pair_kernel<2>;
+        case 3: return em_pass_pair_kernel<3>;
+        case 4: return em_pass_pair_kernel<4>;
+        case 5: return em_pass_pair_kernel<5>;
+        case 6: return em_pass_pair_kernel<6>;
+    }
+    return nullptr;
+}
+constexpr int kMaxPairNC = 6;   // 2 restarts x (pi + T) x NC double2 must fit 128 registers
+constexpr int kMaxSlots = 2;
+
 // One EM iteration on em->ctx->stream (no host sync).
 static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
                              cudaEvent_t pass_end = nullptr) {
     mxb_ctx *ctx = em->ctx;
     cudaStream_t s = ctx->stream;
     if (pass_begin) MXB_CUDA(cudaEventRecord(pass_begin, s));
+    if (em->n_slots == 2) {
+        const size_t ps = (size_t)em->n_part * em->ld;
+        pick_pair(em->nc)<<<em->grid_fast, kPassThreads, em->smem_bytes, s>>>(
+            em->lin, em->ld, em->n_rows, em->weights, em->pi[0], em->pi[1], em->pi[0] + em->ld,
+            em->pi[1] + em->ld, em->state, em->partials, em->partials + ps, em->n_stages);
+        ctx->launches += 1;
+        if (pass_end) MXB_CUDA(cudaEventRecord(pass_end, s));
+        P2PArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        em_finish_kernel<false><<<dim3(kFinCtas, 2), kFinThreads, 0, s>>>(
+            em->partials, em->n_part, em->n_cols, em->ld, em->lnp[0], em->lnp[1], em->pi[0],
+            em->pi[1], em->state, pa);
+        ctx->launches += 1;
+        MXB_CUDA(cudaGetLastError());
+        return MXB_OK;
+    }
     if (em->fast) {
         pick_pass(em->nc)<<<em->grid_fast, kPassThreads, em->smem_bytes, s>>>(
             em->lin, em->ld, em->n_rows, em->weights, em->pi[0], em->pi[1], em->state,
@@ -817,13 +1027,15 @@ struct StageTimer {
     }
 };
 
-static int reset_state(mxb_em *em, long long max_iter, double tol) {
+static int reset_state(mxb_em *em, long long max_iter, double tol, int slot = 0, int done = 0) {
     EmState st;
     memset(&st, 0, sizeof(st));
     st.max_iter = max_iter;
     st.tol = tol;
+    st.done = done;
     // synchronous w.r.t. the host buffer: pageable copy of a stack struct
-    MXB_CUDA(cudaMemcpyAsync(em->state, &st, sizeof(st), cudaMemcpyHostToDevice, em->ctx->stream));
+    MXB_CUDA(cudaMemcpyAsync(em->state + slot, &st, sizeof(st), cudaMemcpyHostToDevice,
+                             em->ctx->stream));
     MXB_CUDA(cudaStreamSynchronize(em->ctx->stream));
     return MXB_OK;
 }
@@ -853,8 +1065,22 @@ int mxb_em_destroy(mxb_em *em) {
     return MXB_OK;
 }
 
-int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int sharded,
-                  mxb_em **out) {
+}  // extern "C"
+
+namespace mxb {
+
+__global__ void em_reset_state_kernel(EmState *st, long long max_iter, double tol) {
+    st->done = 0;
+    st->cur = 0;
+    st->bad = 0;
+    st->iters = 0;
+    st->max_iter = max_iter;
+    st->tol = tol;
+    st->delta = 0.0;
+}
+
+static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int sharded,
+                          int want_slots, mxb_em **out) {
     MXB_REQUIRE(ctx != nullptr && m != nullptr && out != nullptr, "NULL argument");
     MXB_REQUIRE(m->n_rows > 0 && m->n_cols > 0, "EM needs a non-empty matrix");
     MXB_REQUIRE(weights != nullptr, "weights is NULL");
@@ -886,11 +1112,17 @@ int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int 
     em->fused_tail = em->fast && em->ld <= (int64_t)kFinCtas * kFinThreads &&
                      (!(em->sharded && ctx->world > 1) || ctx->p2p_ready) &&
                      getenv("MXB_EM_SPLIT_TAIL") == nullptr;
+    if (want_slots == 2 && em->fast && em->fused_tail && em->nc <= kMaxPairNC && !em->sharded)
+        em->n_slots = 2;
     if (em->fast) {
         em->n_part = em->grid_fast;
         cudaError_t e = cudaFuncSetAttribute((const void *)pick_pass(em->nc),
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)em->smem_bytes);
+        if (e == cudaSuccess && em->n_slots == 2)
+            e = cudaFuncSetAttribute((const void *)pick_pair(em->nc),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)em->smem_bytes);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(smem=%zu): %s", em->smem_bytes, cudaGetErrorString(e));
             delete em;
@@ -909,16 +1141,18 @@ int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int 
     STEP(cudaMalloc(&em->lin, (size_t)em->n_rows * row_bytes));
     STEP(cudaMalloc(&em->weights, em->n_rows * sizeof(double)));
     if (!em->fast) STEP(cudaMalloc(&em->coef, em->n_rows * sizeof(double)));
+    const size_t ns = (size_t)em->n_slots;
     for (int i = 0; i < 2; ++i) {
-        STEP(cudaMalloc(&em->lnp[i], row_bytes));
-        STEP(cudaMalloc(&em->pi[i], row_bytes));
+        STEP(cudaMalloc(&em->lnp[i], ns * row_bytes));
+        STEP(cudaMalloc(&em->pi[i], ns * row_bytes));
         STEP(cudaEventCreateWithFlags(&em->poll_ev[i], cudaEventDisableTiming));
     }
-    STEP(cudaMalloc(&em->partials, (size_t)em->n_part * row_bytes));
+    STEP(cudaMalloc(&em->partials, ns * (size_t)em->n_part * row_bytes));
     STEP(cudaMalloc(&em->tsum, row_bytes));
     STEP(cudaMalloc(&em->props_in, em->n_cols * sizeof(double)));
-    STEP(cudaMalloc(&em->state, sizeof(EmState)));
-    STEP(cudaMallocHost(&em->host_state, 2 * sizeof(EmState)));
+    STEP(cudaMalloc(&em->state, ns * sizeof(EmState)));
+    STEP(cudaMemsetAsync(em->state, 0, ns * sizeof(EmState), ctx->stream));
+    STEP(cudaMallocHost(&em->host_state, 2 * kMaxSlots * sizeof(EmState)));
     STEP(cudaMemcpyAsync(em->weights, weights, em->n_rows * sizeof(double),
                          cudaMemcpyHostToDevice, ctx->stream));
     if (e == cudaSuccess) {
@@ -938,6 +1172,15 @@ int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int 
     }
     *out = em;
     return MXB_OK;
+}
+
+}  // namespace mxb
+
+extern "C" {
+
+int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int sharded,
+                  mxb_em **out) {
+    return em_create_impl(ctx, m, weights, sharded, 1, out);
 }
 
 int mxb_em_set_lnprops(mxb_em *em, const double *lnprops) {
@@ -1130,6 +1373,132 @@ int mxb_matrix_fold_ranks(mxb_ctx *ctx, mxb_matrix *m, double sub_log) {
     return rc;
 }
 
+}  // extern "C"
+
+namespace mxb {
+
+// run_em's restart loop (em.py:117-156) on a two-slot session: two restarts iterate per
+// read of L; a slot whose restart has finished is handed the next one while the other
+// keeps going.  The host polls the control blocks two chunks behind the device, exactly
+// like mxb_em_iterate does for one restart.  Results are combined as the reference
+// combines them: final log-proportions summed in restart order (em.py:145-155), read
+// matrices folded with logaddexp (em.py:156; in completion order).
+static int run_em_batched(mxb_em *em, const double *init_lnprops, int32_t n_multi,
+                          int64_t max_iter, double tol, bool raw, mxb_matrix *mix,
+                          double *props_out, int64_t *iters_out, int32_t *converged_out) {
+    mxb_ctx *ctx = em->ctx;
+    cudaStream_t s = ctx->stream;
+    const int64_t h = em->n_cols, ld = em->ld;
+    double *d_inits = nullptr, *h_fin = nullptr;
+    MXB_CUDA(cudaMalloc(&d_inits, (size_t)n_multi * h * sizeof(double)));
+    cudaError_t e = cudaMallocHost(&h_fin, (size_t)n_multi * h * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaFree(d_inits);
+        set_error("run_em: cudaMallocHost: %s", cudaGetErrorString(e));
+        return MXB_ERR_NOMEM;
+    }
+    int rc = copy_h2d(ctx, d_inits, init_lnprops, (size_t)n_multi * h * sizeof(double));
+
+    int slot_restart[kMaxSlots] = {-1, -1};
+    int slot_gen[kMaxSlots] = {0, 0};
+    int poll_gen[2][kMaxSlots] = {{0, 0}, {0, 0}};
+    int32_t next = 0, finished = 0, folded = 0;
+    auto start_slot = [&](int sl) {
+        const int32_t idx = next++;
+        slot_restart[sl] = idx;
+        slot_gen[sl]++;
+        em_set_props_kernel<<<(int)ceil_div(ld, 256), 256, 0, s>>>(
+            d_inits + (size_t)idx * h, h, ld, em->lnp[0] + sl * ld, em->pi[0] + sl * ld,
+            em->lnp[1] + sl * ld, em->pi[1] + sl * ld);
+        em_reset_state_kernel<<<1, 1, 0, s>>>(em->state + sl, (long long)max_iter, tol);
+        ctx->launches += 2;
+    };
+    for (int sl = 0; sl < em->n_slots && rc == MXB_OK; ++sl)
+        if (next < n_multi) start_slot(sl);
+
+    const int64_t kChunk = 16;
+    bool pending[2] = {false, false};
+    int which = 0;
+    const int grid_mix = (int)std::min<int64_t>(em->n_rows, (int64_t)ctx->num_sms * 8);
+    while (rc == MXB_OK && finished < n_multi) {
+        for (int64_t i = 0; i < kChunk && rc == MXB_OK; ++i) rc = enqueue_iteration(em);
+        if (rc != MXB_OK) break;
+        if (cudaMemcpyAsync(&em->host_state[which * kMaxSlots], em->state,
+                            em->n_slots * sizeof(EmState), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaEventRecord(em->poll_ev[which], s) != cudaSuccess) {
+            set_error("run_em: poll enqueue failed");
+            rc = MXB_ERR_CUDA;
+            break;
+        }
+        for (int sl = 0; sl < kMaxSlots; ++sl) poll_gen[which][sl] = slot_gen[sl];
+        pending[which] = true;
+        const int other = which ^ 1;
+        if (pending[other]) {
+            if (cudaEventSynchronize(em->poll_ev[other]) != cudaSuccess) {
+                set_error("run_em: poll wait failed");
+                rc = MXB_ERR_CUDA;
+                break;
+            }
+            pending[other] = false;
+            for (int sl = 0; sl < em->n_slots && rc == MXB_OK; ++sl) {
+                const EmState st = em->host_state[other * kMaxSlots + sl];
+                if (slot_restart[sl] < 0 || poll_gen[other][sl] != slot_gen[sl] || !st.done) continue;
+                const int32_t idx = slot_restart[sl];
+                if (st.bad) {
+                    set_error("EM: the mixture likelihood of some rows underflowed to 0 in "
+                              "restart %d (proportions left the fp64 range)", (int)idx);
+                    rc = MXB_ERR_RANGE;
+                    break;
+                }
+                if (iters_out) iters_out[idx] = st.iters;
+                if (converged_out) converged_out[idx] = (st.done == 1);
+                // lnp[cur] = proportions before the last step, lnp[1-cur] = after it
+                if (cudaMemcpyAsync(h_fin + (size_t)idx * h, em->lnp[1 - st.cur] + sl * ld,
+                                    h * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) {
+                    set_error("run_em: result copy failed");
+                    rc = MXB_ERR_CUDA;
+                    break;
+                }
+                ++finished;
+                if (mix) {
+                    const bool last = finished == n_multi;
+                    const double sub = (last && n_multi > 1 && !raw) ? log((double)n_multi) : 0.0;
+                    read_mix_kernel<<<grid_mix, kMixThreads, 0, s>>>(
+                        em->mat->data, em->n_rows, em->n_cols, em->lnp[st.cur] + sl * ld, mix->data,
+                        folded == 0 ? 0 : 1, sub);
+                    ctx->launches++;
+                    ++folded;
+                }
+                slot_restart[sl] = -1;
+                if (next < n_multi) start_slot(sl);
+            }
+        }
+        which = other;
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess && rc == MXB_OK) {
+        set_error("run_em: stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = MXB_ERR_CUDA;
+    }
+    if (rc == MXB_OK) {
+        for (int64_t j = 0; j < h; ++j) {
+            double v = h_fin[j];
+            for (int32_t i = 1; i < n_multi; ++i) v += h_fin[(size_t)i * h + j];  // em.py:155
+            if (!raw) {
+                if (n_multi > 1) v /= (double)n_multi;  // em.py:158-160
+                v = exp(v);                             // em.py:163
+            }
+            props_out[j] = v;
+        }
+    }
+    cudaFree(d_inits);
+    cudaFreeHost(h_fin);
+    return rc;
+}
+
+}  // namespace mxb
+
+extern "C" {
+
 int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
                    const double *init_lnprops, int32_t n_multi, int64_t max_iter, double tol,
                    int32_t flags, double *props_out, double *read_mix_out,
@@ -1150,11 +1519,20 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
     // from background threads while the GPU iterates
     Prefault fault_mix;
     if (read_mix_out) fault_mix.start(read_mix_out, (size_t)m->n_rows * (size_t)h * sizeof(double));
-    int rc = mxb_em_create(ctx, m, weights, (flags & MXB_EM_SHARDED) != 0, &em);
+    const bool sharded = (flags & MXB_EM_SHARDED) != 0;
+    const int want_slots = (n_multi >= 2 && max_iter > 0 && !sharded &&
+                            getenv("MXB_EM_NO_BATCH") == nullptr) ? 2 : 1;
+    int rc = em_create_impl(ctx, m, weights, sharded, want_slots, &em);
     tm.mark("em_create (alloc+to_linear)");
     if (rc == MXB_OK && want_mix) rc = mxb_matrix_alloc(ctx, m->n_rows, h, &mix);
     tm.mark("alloc read_mix");
-    for (int32_t i = 0; rc == MXB_OK && i < n_multi; ++i) {
+    const bool batched = rc == MXB_OK && em->n_slots == 2;
+    if (batched) {
+        rc = run_em_batched(em, init_lnprops, n_multi, max_iter, tol, raw, mix, props_out,
+                            iters_out, converged_out);
+        tm.mark("iterate (two restarts per pass)");
+    }
+    for (int32_t i = 0; rc == MXB_OK && !batched && i < n_multi; ++i) {
         int64_t iters = 0;
         int32_t conv = 0;
         rc = mxb_em_set_lnprops(em, init_lnprops + (size_t)i * h);
@@ -1176,7 +1554,7 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
         }
     }
     if (rc == MXB_OK) {
-        for (int64_t j = 0; j < h; ++j) {
+        for (int64_t j = 0; j < h && !batched; ++j) {
             double v = acc[j];
             if (!raw) {
                 if (n_multi > 1) v /= (double)n_multi;  // em.py:158-160

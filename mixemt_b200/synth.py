@@ -152,3 +152,47 @@ def synthetic_phylo(n_hap=512, n_pos=400, ref_len=4000, markers_per_hap=12, seed
         seen.add(key)
         hap_var["S%d" % j] = vs
     return PhyloTables(variants, hap_var, refseq), refseq
+
+
+def random_rows(phylo, refseq, mixture, n_rows, frag_len=300, err=0.002, seed=1):
+    """``n_rows`` fragment signatures drawn like :func:`make_mixture` draws
+    fragments, fully vectorised and *without* the reduction to unique signatures
+    (duplicates stay, every weight is 1).  For shard-sized workloads (millions of
+    rows per GPU, BASELINE.json config 3) where the Python dedupe loop of
+    ``make_mixture`` would take minutes.  Rows are in generation order."""
+    rs = np.random.RandomState(seed)
+    positions = sorted(phylo.variants)
+    pos_arr = np.asarray(positions, dtype=np.int64)
+    haps = [h for h, _ in mixture]
+    frac = np.asarray([f for _, f in mixture], dtype=np.float64)
+    frac = frac / frac.sum()
+    exp = np.stack([expected_bases(phylo, refseq, h, positions) for h in haps])
+    chunks = []
+    total_rows = 0
+    while total_rows < n_rows:
+        m = min(n_rows - total_rows + 1024, 2000000)
+        src = rs.choice(len(haps), size=m, p=frac)
+        start = rs.randint(0, len(refseq) - frag_len, size=m)
+        lo = np.searchsorted(pos_arr, start, side="left")
+        hi = np.searchsorted(pos_arr, start + frag_len, side="left")
+        keep = hi > lo
+        src, lo, hi = src[keep], lo[keep], hi[keep]
+        take = min(len(src), n_rows - total_rows)
+        src, lo, hi = src[:take], lo[:take], hi[:take]
+        lens = (hi - lo).astype(np.int64)
+        ptr = np.zeros(take + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        idx = (np.repeat(lo - ptr[:-1], lens) + np.arange(ptr[-1])).astype(np.int32)
+        base = exp[np.repeat(src, lens), idx]
+        flip = np.nonzero(rs.rand(len(base)) < err)[0]
+        if len(flip):
+            code = np.searchsorted(_BASES, base[flip])
+            base[flip] = _BASES[(code + rs.randint(1, 4, size=len(flip))) % 4]
+        chunks.append((lens, idx, base))
+        total_rows += take
+    lens = np.concatenate([c[0] for c in chunks])
+    row_ptr = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=row_ptr[1:])
+    return Mixture(row_ptr, np.concatenate([c[1] for c in chunks]),
+                   np.concatenate([c[2] for c in chunks]),
+                   np.ones(len(lens), dtype=np.int64), None, len(lens))

@@ -296,3 +296,36 @@ def test_install_patches_reference_entry_points():
     mixemt_b200.install(fake)
     assert fake.preprocess.build_em_matrix is mixemt_b200.preprocess.build_em_matrix
     assert fake.em.run_em is mixemt_b200.em.run_em and fake.em.em_step is mixemt_b200.em.em_step
+
+
+@pytest.mark.parametrize("n_multi", [2, 5])
+def test_batched_restarts_equal_sequential(n_multi):
+    """run_em with n_multi > 1 iterates two restarts per read of the matrix
+    (em_pass_pair_kernel); the results must equal the one-at-a-time path
+    (MXB_EM_NO_BATCH=1) and the oracle, restart by restart."""
+    import os
+    from mixemt_b200.runtime import DeviceMatrix, get_context
+    rs = np.random.RandomState(11)
+    n, h = 2500, 5408
+    mat = -rs.gamma(2.0, 8.0, size=(n, h))
+    mat[rs.rand(n, h) < 0.4] = 0.0
+    mat[:, :40] += 3.0                                  # a few strong components
+    wts = rs.randint(1, 50, size=n)
+    inits = np.log(rs.dirichlet([1.0] * h, size=n_multi))
+    a = make_args(n_multi=n_multi, max_iter=90, tolerance=3e-3)
+    dev = DeviceMatrix.from_host(get_context(), mat)
+    p_b, m_b, info_b, _ = em.run_em_device(dev, wts, a, inits=inits)
+    os.environ["MXB_EM_NO_BATCH"] = "1"
+    try:
+        p_s, m_s, info_s, _ = em.run_em_device(dev, wts, a, inits=inits)
+    finally:
+        del os.environ["MXB_EM_NO_BATCH"]
+    assert info_b["iterations"] == info_s["iterations"]
+    assert info_b["converged"] == info_s["converged"]
+    assert len(set(info_b["iterations"])) > 1 or n_multi == 2   # slots are refilled mid-run
+    assert np.abs(p_b - p_s).max() < 1e-13
+    assert close_mix(m_b, m_s, 1e-10)
+    o_p, o_m, o_it = oracle_c.run_em(mat, wts.astype(np.float64), inits, a.max_iter, a.tolerance)
+    assert list(o_it) == info_b["iterations"]
+    assert np.abs(p_b - o_p).max() < 1e-10
+    assert close_mix(m_b, o_m)
