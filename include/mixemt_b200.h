@@ -58,6 +58,10 @@ int mxb_ctx_destroy(mxb_ctx *ctx);
 /* Launch on an externally owned cudaStream_t (e.g. torch's current stream). */
 int mxb_ctx_set_stream(mxb_ctx *ctx, void *cuda_stream);
 int mxb_ctx_synchronize(mxb_ctx *ctx);
+/* Device blocks of >= 1 MiB freed through this context are kept for reuse,
+ * up to MXB_CACHE_MB (default: a quarter of the device memory; 0 disables) -- cudaMalloc
+ * and cudaFree of multi-GB blocks are slow and jittery.  mxb_ctx_trim hands them back. */
+int mxb_ctx_trim(mxb_ctx *ctx);
 /* Kernel launches issued through this context since creation (bench evidence). */
 int64_t mxb_ctx_launch_count(const mxb_ctx *ctx);
 /* Multi-GPU: one process per GPU.  Rank 0 calls mxb_comm_unique_id, the host

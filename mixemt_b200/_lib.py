@@ -58,6 +58,7 @@ _PROTOS = {
     "mxb_ctx_destroy": (ctypes.c_int, [P]),
     "mxb_ctx_set_stream": (ctypes.c_int, [P, P]),
     "mxb_ctx_synchronize": (ctypes.c_int, [P]),
+    "mxb_ctx_trim": (ctypes.c_int, [P]),
     "mxb_ctx_launch_count": (c_i64, [P]),
     "mxb_comm_unique_id": (ctypes.c_int, [P]),
     "mxb_comm_init": (ctypes.c_int, [P, P, ctypes.c_int, ctypes.c_int]),

@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <new>
 #include <thread>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -230,6 +232,105 @@ int copy_d2h(mxb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
     return MXB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Cache of large device blocks (see common.cuh).
+// ---------------------------------------------------------------------------
+struct BlockCache {
+    std::unordered_map<void *, size_t> live;           // blocks handed out by dev_alloc
+    std::vector<std::pair<size_t, void *>> free_list;  // cached blocks
+    size_t cached_bytes = 0;
+    size_t limit = 0;
+};
+constexpr size_t kCacheMinBlock = (size_t)1 << 20;
+
+void *pinned_scratch(mxb_ctx *ctx) {
+    if (!ctx->pinned && cudaHostAlloc(&ctx->pinned, kPinnedScratchBytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->pinned = nullptr;
+    }
+    return ctx->pinned;
+}
+
+static BlockCache *cache_of(mxb_ctx *ctx) {
+    if (!ctx->block_cache) {
+        BlockCache *bc = new (std::nothrow) BlockCache();
+        if (!bc) return nullptr;
+        const char *env = getenv("MXB_CACHE_MB");
+        if (env) {
+            bc->limit = (size_t)atoll(env) << 20;
+        } else {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) bc->limit = total_b / 4;
+            else cudaGetLastError();
+        }
+        ctx->block_cache = bc;
+    }
+    return (BlockCache *)ctx->block_cache;
+}
+
+void dev_cache_release(mxb_ctx *ctx) {
+    BlockCache *bc = (BlockCache *)ctx->block_cache;
+    if (!bc) return;
+    for (auto &ent : bc->free_list) cudaFree(ent.second);
+    bc->free_list.clear();
+    bc->cached_bytes = 0;
+}
+
+cudaError_t dev_alloc(mxb_ctx *ctx, void **out, size_t bytes) {
+    *out = nullptr;
+    if (bytes == 0) return cudaSuccess;
+    BlockCache *bc = bytes >= kCacheMinBlock ? cache_of(ctx) : nullptr;
+    if (bc) {
+        // smallest cached block that fits without wasting more than 1/8
+        int best = -1;
+        for (int i = 0; i < (int)bc->free_list.size(); ++i) {
+            const size_t sz = bc->free_list[i].first;
+            if (sz >= bytes && sz - bytes <= bytes / 8 &&
+                (best < 0 || sz < bc->free_list[best].first))
+                best = i;
+        }
+        if (best >= 0) {
+            *out = bc->free_list[best].second;
+            bc->cached_bytes -= bc->free_list[best].first;
+            bc->live[*out] = bc->free_list[best].first;
+            bc->free_list.erase(bc->free_list.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation && ctx->block_cache) {
+        cudaGetLastError();
+        dev_cache_release(ctx);
+        e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess && bc) {
+        try { bc->live[*out] = bytes; } catch (...) {}
+    }
+    return e;
+}
+
+void dev_free(mxb_ctx *ctx, void *ptr) {
+    if (!ptr) return;
+    BlockCache *bc = ctx ? (BlockCache *)ctx->block_cache : nullptr;
+    if (bc) {
+        auto it = bc->live.find(ptr);
+        if (it != bc->live.end()) {
+            const size_t sz = it->second;
+            bc->live.erase(it);
+            if (bc->cached_bytes + sz <= bc->limit) {
+                // the block may still be read by work queued on the context's stream
+                cudaStreamSynchronize(ctx->stream);
+                try {
+                    bc->free_list.emplace_back(sz, ptr);
+                    bc->cached_bytes += sz;
+                    return;
+                } catch (...) {}
+            }
+        }
+    }
+    cudaFree(ptr);
+}
+
 struct PrefaultImpl {
     std::vector<std::thread> threads;
 };
@@ -241,7 +342,9 @@ void Prefault::start(void *buf, size_t bytes) {
     char *lo = (char *)(((uintptr_t)buf + page - 1) & ~(uintptr_t)(page - 1));
     char *hi = (char *)(((uintptr_t)buf + bytes) & ~(uintptr_t)(page - 1));
     if (hi <= lo) return;
-    madvise(lo, (size_t)(hi - lo), MADV_HUGEPAGE);  // best effort
+    // transparent huge pages halve the fault time on an idle box but stall for compaction
+    // on a fragmented one (seen as 0.2-0.4 s outliers): opt-in only
+    if (getenv("MXB_PREFAULT_HUGEPAGE")) madvise(lo, (size_t)(hi - lo), MADV_HUGEPAGE);
     PrefaultImpl *pi = new (std::nothrow) PrefaultImpl();
     if (!pi) return;
     const char *env = getenv("MXB_PREFAULT_THREADS");
@@ -381,6 +484,11 @@ int mxb_ctx_destroy(mxb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->nccl_comm) mxb_comm_destroy(ctx);
     free_stage(ctx);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    dev_cache_release(ctx);
+    delete (BlockCache *)ctx->block_cache;
+    ctx->block_cache = nullptr;
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MXB_OK;
@@ -401,6 +509,14 @@ int mxb_ctx_synchronize(mxb_ctx *ctx) {
     MXB_REQUIRE(ctx != nullptr, "ctx is NULL");
     MXB_CUDA(cudaSetDevice(ctx->device));
     MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MXB_OK;
+}
+
+int mxb_ctx_trim(mxb_ctx *ctx) {
+    MXB_REQUIRE(ctx != nullptr, "ctx is NULL");
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    dev_cache_release(ctx);
     return MXB_OK;
 }
 
@@ -479,7 +595,7 @@ int mxb_matrix_alloc(mxb_ctx *ctx, int64_t n_rows, int64_t n_cols, mxb_matrix **
     m->n_cols = n_cols;
     size_t bytes = (size_t)n_rows * (size_t)n_cols * sizeof(double);
     if (bytes) {
-        cudaError_t e = cudaMalloc(&m->data, bytes);
+        cudaError_t e = dev_alloc(ctx, (void **)&m->data, bytes);
         if (e != cudaSuccess) {
             set_error("cudaMalloc(%zu bytes) for %lld x %lld matrix: %s", bytes,
                       (long long)n_rows, (long long)n_cols, cudaGetErrorString(e));
@@ -529,7 +645,7 @@ int mxb_matrix_destroy(mxb_matrix *m) {
     if (!m) return MXB_OK;
     if (m->data) {
         cudaSetDevice(m->ctx->device);
-        cudaFree(m->data);
+        dev_free(m->ctx, m->data);
     }
     delete m;
     return MXB_OK;

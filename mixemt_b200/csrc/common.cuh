@@ -59,6 +59,9 @@ struct mxb_ctx {
     void *stage_buf[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t stage_chunk = 0;
+    // cache of large freed device blocks (api.cu: dev_alloc / dev_free)
+    void *block_cache = nullptr;
+    void *pinned = nullptr;  // small pinned host scratch (control-block polling), lazily allocated
     // NCCL (optional)
     void *nccl_comm = nullptr;
     int rank = 0;
@@ -103,6 +106,18 @@ int nccl_allreduce_f64(mxb_ctx *ctx, double *dev_buf, int64_t n, int op_is_max);
 // registered host memory is copied directly.  Both return after completion.
 int copy_h2d(mxb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int copy_d2h(mxb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+// Device memory for matrix-sized buffers.  cudaMalloc / cudaFree of multi-GB blocks
+// cost 1-10 ms each and now and then 0.1-1 s (measured on the B200 boxes), which is
+// visible next to a 1.4 s run_em call; freed blocks of >= 1 MiB are therefore kept
+// per context (up to MXB_CACHE_MB, default a quarter of the device memory) and
+// handed out again to requests of about the same size.  An allocation that fails
+// releases the cache and retries.  Not thread-safe: one host thread per context.
+constexpr size_t kPinnedScratchBytes = 4096;
+void *pinned_scratch(mxb_ctx *ctx);  // kPinnedScratchBytes of pinned host memory, NULL on failure
+cudaError_t dev_alloc(mxb_ctx *ctx, void **out, size_t bytes);
+void dev_free(mxb_ctx *ctx, void *ptr);
+void dev_cache_release(mxb_ctx *ctx);
+
 // Touch every page of a caller-owned *output* buffer from background threads
 // while the GPU works, so that the final copy does not pay first-touch faults.
 struct Prefault {

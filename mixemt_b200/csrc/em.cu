@@ -903,6 +903,7 @@ struct mxb_em {
     // Restart slots: a batched session (run_em with n_multi > 1) iterates two restarts per
     // read of L.  Slot s lives at lnp[b] + s*ld, pi[b] + s*ld, partials + s*n_part*ld, state + s.
     int n_slots = 1;
+    unsigned char *small = nullptr;  // one device block behind weights ... state (fewer driver calls)
     bool zero_iter = false;  // last iterate() ran no iteration
 };
 
@@ -1048,20 +1049,11 @@ int mxb_em_destroy(mxb_em *em) {
     if (!em) return MXB_OK;
     cudaSetDevice(em->ctx->device);
     cudaStreamSynchronize(em->ctx->stream);
-    cudaFree(em->lin);
-    cudaFree(em->weights);
-    cudaFree(em->coef);
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(em->lnp[i]);
-        cudaFree(em->pi[i]);
+    dev_free(em->ctx, em->lin);
+    dev_free(em->ctx, em->small);
+    for (int i = 0; i < 2; ++i)
         if (em->poll_ev[i]) cudaEventDestroy(em->poll_ev[i]);
-    }
-    cudaFree(em->partials);
-    cudaFree(em->tsum);
-    cudaFree(em->props_in);
-    cudaFree(em->state);
-    if (em->host_state) cudaFreeHost(em->host_state);
-    delete em;
+    delete em;  // host_state points into the context's pinned scratch
     return MXB_OK;
 }
 
@@ -1138,21 +1130,37 @@ static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weigh
 
     cudaError_t e = cudaSuccess;
 #define STEP(call) do { if (e == cudaSuccess) e = (call); } while (0)
-    STEP(cudaMalloc(&em->lin, (size_t)em->n_rows * row_bytes));
-    STEP(cudaMalloc(&em->weights, em->n_rows * sizeof(double)));
-    if (!em->fast) STEP(cudaMalloc(&em->coef, em->n_rows * sizeof(double)));
+    STEP(dev_alloc(ctx, (void **)&em->lin, (size_t)em->n_rows * row_bytes));
     const size_t ns = (size_t)em->n_slots;
-    for (int i = 0; i < 2; ++i) {
-        STEP(cudaMalloc(&em->lnp[i], ns * row_bytes));
-        STEP(cudaMalloc(&em->pi[i], ns * row_bytes));
-        STEP(cudaEventCreateWithFlags(&em->poll_ev[i], cudaEventDisableTiming));
+    {   // everything else of the session in one block: [weights][coef][lnp x2][pi x2][partials]
+        // [tsum][props_in][state], each 256-byte aligned
+        auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t b_rows = up((size_t)em->n_rows * sizeof(double));
+        const size_t b_vec = up(ns * row_bytes);
+        const size_t b_part = up(ns * (size_t)em->n_part * row_bytes);
+        const size_t total = b_rows * (em->fast ? 1 : 2) + 4 * b_vec + b_part + up(row_bytes) +
+                             up((size_t)em->n_cols * sizeof(double)) + up(ns * sizeof(EmState));
+        STEP(dev_alloc(ctx, (void **)&em->small, total));
+        if (e == cudaSuccess) {
+            unsigned char *p = em->small;
+            em->weights = (double *)p; p += b_rows;
+            if (!em->fast) { em->coef = (double *)p; p += b_rows; }
+            for (int i = 0; i < 2; ++i) { em->lnp[i] = (double *)p; p += b_vec; }
+            for (int i = 0; i < 2; ++i) { em->pi[i] = (double *)p; p += b_vec; }
+            em->partials = (double *)p; p += b_part;
+            em->tsum = (double *)p; p += up(row_bytes);
+            em->props_in = (double *)p; p += up((size_t)em->n_cols * sizeof(double));
+            em->state = (EmState *)p;
+        }
     }
-    STEP(cudaMalloc(&em->partials, ns * (size_t)em->n_part * row_bytes));
-    STEP(cudaMalloc(&em->tsum, row_bytes));
-    STEP(cudaMalloc(&em->props_in, em->n_cols * sizeof(double)));
-    STEP(cudaMalloc(&em->state, ns * sizeof(EmState)));
+    for (int i = 0; i < 2; ++i)
+        STEP(cudaEventCreateWithFlags(&em->poll_ev[i], cudaEventDisableTiming));
     STEP(cudaMemsetAsync(em->state, 0, ns * sizeof(EmState), ctx->stream));
-    STEP(cudaMallocHost(&em->host_state, 2 * kMaxSlots * sizeof(EmState)));
+    if (e == cudaSuccess) {
+        static_assert(2 * kMaxSlots * sizeof(EmState) <= kPinnedScratchBytes, "pinned scratch");
+        em->host_state = (EmState *)pinned_scratch(ctx);
+        if (!em->host_state) e = cudaErrorMemoryAllocation;
+    }
     STEP(cudaMemcpyAsync(em->weights, weights, em->n_rows * sizeof(double),
                          cudaMemcpyHostToDevice, ctx->stream));
     if (e == cudaSuccess) {
@@ -1389,15 +1397,25 @@ static int run_em_batched(mxb_em *em, const double *init_lnprops, int32_t n_mult
     mxb_ctx *ctx = em->ctx;
     cudaStream_t s = ctx->stream;
     const int64_t h = em->n_cols, ld = em->ld;
-    double *d_inits = nullptr, *h_fin = nullptr;
-    MXB_CUDA(cudaMalloc(&d_inits, (size_t)n_multi * h * sizeof(double)));
-    cudaError_t e = cudaMallocHost(&h_fin, (size_t)n_multi * h * sizeof(double));
-    if (e != cudaSuccess) {
-        cudaFree(d_inits);
-        set_error("run_em: cudaMallocHost: %s", cudaGetErrorString(e));
+    // device: [inits n_multi x h][final log-proportions n_multi x h]; the finals are read
+    // back in one copy at the end (no pinned host buffer, no blocking copy mid-run)
+    const size_t vec_bytes = (size_t)n_multi * h * sizeof(double);
+    double *d_inits = nullptr;
+    if (dev_alloc(ctx, (void **)&d_inits, 2 * vec_bytes) != cudaSuccess) {
+        set_error("run_em: device allocation of %zu bytes failed", 2 * vec_bytes);
+        cudaGetLastError();
         return MXB_ERR_NOMEM;
     }
-    int rc = copy_h2d(ctx, d_inits, init_lnprops, (size_t)n_multi * h * sizeof(double));
+    double *d_fin = d_inits + (size_t)n_multi * h;
+    std::vector<double> h_fin;
+    try {
+        h_fin.resize((size_t)n_multi * h);
+    } catch (const std::bad_alloc &) {
+        dev_free(ctx, d_inits);
+        set_error("run_em: out of host memory");
+        return MXB_ERR_NOMEM;
+    }
+    int rc = copy_h2d(ctx, d_inits, init_lnprops, vec_bytes);
 
     int slot_restart[kMaxSlots] = {-1, -1};
     int slot_gen[kMaxSlots] = {0, 0};
@@ -1453,8 +1471,8 @@ static int run_em_batched(mxb_em *em, const double *init_lnprops, int32_t n_mult
                 if (iters_out) iters_out[idx] = st.iters;
                 if (converged_out) converged_out[idx] = (st.done == 1);
                 // lnp[cur] = proportions before the last step, lnp[1-cur] = after it
-                if (cudaMemcpyAsync(h_fin + (size_t)idx * h, em->lnp[1 - st.cur] + sl * ld,
-                                    h * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) {
+                if (cudaMemcpyAsync(d_fin + (size_t)idx * h, em->lnp[1 - st.cur] + sl * ld,
+                                    h * sizeof(double), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
                     set_error("run_em: result copy failed");
                     rc = MXB_ERR_CUDA;
                     break;
@@ -1479,6 +1497,7 @@ static int run_em_batched(mxb_em *em, const double *init_lnprops, int32_t n_mult
         set_error("run_em: stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = MXB_ERR_CUDA;
     }
+    if (rc == MXB_OK) rc = copy_d2h(ctx, h_fin.data(), d_fin, vec_bytes);
     if (rc == MXB_OK) {
         for (int64_t j = 0; j < h; ++j) {
             double v = h_fin[j];
@@ -1490,8 +1509,7 @@ static int run_em_batched(mxb_em *em, const double *init_lnprops, int32_t n_mult
             props_out[j] = v;
         }
     }
-    cudaFree(d_inits);
-    cudaFreeHost(h_fin);
+    dev_free(ctx, d_inits);
     return rc;
 }
 
@@ -1518,7 +1536,6 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
     // the caller's result buffer is usually fresh pageable memory: fault its pages in
     // from background threads while the GPU iterates
     Prefault fault_mix;
-    if (read_mix_out) fault_mix.start(read_mix_out, (size_t)m->n_rows * (size_t)h * sizeof(double));
     const bool sharded = (flags & MXB_EM_SHARDED) != 0;
     const int want_slots = (n_multi >= 2 && max_iter > 0 && !sharded &&
                             getenv("MXB_EM_NO_BATCH") == nullptr) ? 2 : 1;
@@ -1526,6 +1543,10 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
     tm.mark("em_create (alloc+to_linear)");
     if (rc == MXB_OK && want_mix) rc = mxb_matrix_alloc(ctx, m->n_rows, h, &mix);
     tm.mark("alloc read_mix");
+    // (started after the device allocations: page faults and cudaMalloc contend for the
+    // process's mmap lock)
+    if (rc == MXB_OK && read_mix_out)
+        fault_mix.start(read_mix_out, (size_t)m->n_rows * (size_t)h * sizeof(double));
     const bool batched = rc == MXB_OK && em->n_slots == 2;
     if (batched) {
         rc = run_em_batched(em, init_lnprops, n_multi, max_iter, tol, raw, mix, props_out,

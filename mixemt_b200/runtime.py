@@ -72,6 +72,10 @@ class Context(object):
     def synchronize(self):
         check(lib.mxb_ctx_synchronize(self.handle))
 
+    def trim(self):
+        """Give cached device blocks back to the driver (see mxb_ctx_trim)."""
+        check(lib.mxb_ctx_trim(self.handle))
+
     @property
     def launch_count(self):
         return int(lib.mxb_ctx_launch_count(self.handle))
