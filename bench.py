@@ -9,7 +9,8 @@ resident read-signature x haplotype matrix of BASELINE.json config 2: a 3-way
 synthetic mixture (H1 50% / L3e 30% / U5a1 20%), 1M fragments of 300 bp reduced
 to unique signatures, against all 5408 Phylotree Build 17 haplotypes.  Under
 torchrun every rank builds its own 1M-fragment shard (weak scaling) and the H
-column sums are all-reduced over NCCL once per iteration.
+column sums are exchanged once per iteration by peer stores inside the tail
+kernel (ncclAllReduce when peer access is missing).
 
 One JSON line is printed by rank 0:
   value     matrix cells per second through EM iterations, inputs resident in HBM
@@ -17,9 +18,12 @@ One JSON line is printed by rank 0:
             weights, args) run to convergence with the reference's default
             options: host->device copy of the matrix, all iterations, read-matrix
             materialisation and the device->host copy of the N x H result inside
-            the timed region
+            the timed region (after one short untimed call)
   roofline  the fused E/M pass kernel against the measured HBM copy bandwidth
+  restart_sweep  4 restarts x 100 iterations (BASELINE.json config 4), two restarts
+            per read of the matrix and one at a time
   cpu_baseline  the CPU oracle port (C + OpenMP, all host threads) on a row sample
+--rows N replaces the workload by N undeduplicated rows per GPU (config-3 shards).
 """
 import argparse
 import json
