@@ -721,6 +721,9 @@ em_finish_kernel(const double *partials, int n_part, int64_t n_cols, int64_t ld,
         }
         for (; b < n_part; ++b) t += col[(size_t)b * ld];
     }
+    // a peer CTA's shared memory may only be written once that CTA is known to have
+    // started: one cluster barrier before the first distributed-shared-memory store
+    cooperative_groups::this_cluster().sync();
     unsigned long long seq = 0;
     if (kP2P) {
         namespace cg = cooperative_groups;
