@@ -974,7 +974,8 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
             em->partials, em->n_stages);
         ctx->launches += 1;
     } else {
-        const int rd_blocks = (int)std::min<int64_t>(ceil_div(em->n_rows, 8), (int64_t)ctx->num_sms * 8);
+        const int rd_blocks = (int)std::max<int64_t>(
+            1, std::min<int64_t>(ceil_div(em->n_rows, 8), (int64_t)ctx->num_sms * 8));
         em_rowdot_kernel<<<rd_blocks, 256, 0, s>>>(em->lin, em->ld, em->n_rows, em->weights,
                                                    em->pi[0], em->pi[1], em->state, em->coef);
         dim3 grid(em->row_blocks, em->col_blocks);
@@ -1077,8 +1078,9 @@ __global__ void em_reset_state_kernel(EmState *st, long long max_iter, double to
 static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int sharded,
                           int want_slots, mxb_em **out) {
     MXB_REQUIRE(ctx != nullptr && m != nullptr && out != nullptr, "NULL argument");
-    MXB_REQUIRE(m->n_rows > 0 && m->n_cols > 0, "EM needs a non-empty matrix");
-    MXB_REQUIRE(weights != nullptr, "weights is NULL");
+    // a rank of a row-sharded run may hold no rows at all (fewer signatures than GPUs)
+    MXB_REQUIRE((m->n_rows > 0 || sharded) && m->n_cols > 0, "EM needs a non-empty matrix");
+    MXB_REQUIRE(weights != nullptr || m->n_rows == 0, "weights is NULL");
     *out = nullptr;
     MXB_CUDA(cudaSetDevice(ctx->device));
     mxb_em *em = new (std::nothrow) mxb_em();
@@ -1101,7 +1103,7 @@ static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weigh
             em->fast = true;
             em->n_stages = stages;
             em->smem_bytes = (size_t)stages * row_bytes + fixed;
-            em->grid_fast = (int)std::min<int64_t>(ctx->num_sms, em->n_rows);
+            em->grid_fast = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, em->n_rows));
         }
     }
     em->fused_tail = em->fast && em->ld <= (int64_t)kFinCtas * kFinThreads &&
@@ -1164,9 +1166,10 @@ static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weigh
         em->host_state = (EmState *)pinned_scratch(ctx);
         if (!em->host_state) e = cudaErrorMemoryAllocation;
     }
-    STEP(cudaMemcpyAsync(em->weights, weights, em->n_rows * sizeof(double),
-                         cudaMemcpyHostToDevice, ctx->stream));
-    if (e == cudaSuccess) {
+    if (em->n_rows > 0)
+        STEP(cudaMemcpyAsync(em->weights, weights, em->n_rows * sizeof(double),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    if (e == cudaSuccess && em->n_rows > 0) {
         const int grid = (int)std::min<int64_t>(em->n_rows, (int64_t)ctx->num_sms * 8);
         to_linear_kernel<<<grid, 256, 0, ctx->stream>>>(m->data, em->n_rows, em->n_cols, em->ld,
                                                         em->lin);
@@ -1346,6 +1349,7 @@ int mxb_em_read_mix(mxb_em *em, mxb_matrix *dst, int mode, double sub_log) {
     EmState st;
     MXB_CUDA(cudaMemcpyAsync(&st, em->state, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
     MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (em->n_rows == 0) return MXB_OK;
     const int grid = (int)std::min<int64_t>(em->n_rows, (int64_t)ctx->num_sms * 8);
     read_mix_kernel<<<grid, kMixThreads, 0, ctx->stream>>>(em->mat->data, em->n_rows, em->n_cols,
                                                            em->lnp[st.cur], dst->data, mode,

@@ -58,6 +58,17 @@ def main():
     dist.all_gather_object(gathered, p_rows.tobytes())
     assert all(g == gathered[0] for g in gathered), "ranks disagree on the proportions"
 
+    # rows mode with an empty shard: fewer signature rows than ranks
+    tiny = mat[:world - 1]
+    lo, hi = sharding.row_shard(len(tiny), rank, world)
+    a_t = make_args(max_iter=6, tolerance=1e-12, n_multi=1, b200_shard="rows")
+    p_t, m_t, info_t, _ = em.run_em_device(DeviceMatrix.from_host(ctx, tiny[lo:hi]),
+                                           wts[:world - 1][lo:hi], a_t, inits=inits[:1])
+    p_t1, _, info_t1, _ = em.run_em_device(DeviceMatrix.from_host(ctx, tiny), wts[:world - 1],
+                                           make_args(max_iter=6, tolerance=1e-12), inits=inits[:1])
+    assert info_t["iterations"] == info_t1["iterations"] and m_t.shape == (hi - lo, h)
+    assert np.abs(p_t - p_t1).max() < 1e-12, np.abs(p_t - p_t1).max()
+
     # restarts mode
     a5 = make_args(max_iter=60, tolerance=1e-7, n_multi=5)
     p_all, m_all, _, _ = em.run_em_device(full, wts, a5, inits=inits)
