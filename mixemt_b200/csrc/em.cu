@@ -115,6 +115,14 @@ __device__ __forceinline__ void bulk_load_u32(uint32_t dst_smem, const void *src
         ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with the stream-serialization attribute
+// may start while its predecessor in the stream is still running; it must not touch what the
+// predecessor writes before pdl_wait().  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -194,8 +202,7 @@ em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
                     const double *__restrict__ pi1, EmState *__restrict__ st,
                     double *__restrict__ partials, int n_stages) {
     static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
-    if (st->done) return;
-    const double *__restrict__ pi = st->cur ? pi1 : pi0;
+    pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t row_bytes = (uint32_t)(ld * sizeof(double));
@@ -212,6 +219,8 @@ em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
     const uint32_t stages_u32 = smem_u32(smem_raw);
     const uint32_t full_u32 = smem_u32(full);
 
+    // Prologue: L and the weights do not depend on the previous iteration's tail, so the
+    // ring is primed before waiting for it (the loads overlap the tail kernel).
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -224,6 +233,13 @@ em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
                       &full[q]);
         }
     }
+    pdl_wait();  // proportions and control block of the previous iteration are final
+    if (st->done) {
+        // finished run: the primed loads must land before this CTA's shared memory is released
+        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
+        return;
+    }
+    const double *__restrict__ pi = st->cur ? pi1 : pi0;
 
     // Thread-private column slice: chunk c = tid + k*512 covers doubles 2c, 2c+1.
     const int n_chunks = (int)(ld >> 1);
@@ -346,10 +362,7 @@ em_pass_pair_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
                     double *__restrict__ partials_a, double *__restrict__ partials_b,
                     int n_stages) {
     static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
-    const int done_a = st[0].done, done_b = st[1].done;
-    if (done_a && done_b) return;
-    const double *__restrict__ pia = st[0].cur ? pi_a1 : pi_a0;
-    const double *__restrict__ pib = st[1].cur ? pi_b1 : pi_b0;
+    pdl_launch_dependents();
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t row_bytes = (uint32_t)(ld * sizeof(double));
@@ -378,6 +391,15 @@ em_pass_pair_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
                       &full[q]);
         }
     }
+
+    pdl_wait();
+    const int done_a = st[0].done, done_b = st[1].done;
+    if (done_a && done_b) {
+        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
+        return;
+    }
+    const double *__restrict__ pia = st[0].cur ? pi_a1 : pi_a0;
+    const double *__restrict__ pib = st[1].cur ? pi_b1 : pi_b0;
 
     const int n_chunks = (int)(ld >> 1);
     double2 pa[NC], pb[NC], ta[NC], tb[NC];
@@ -689,6 +711,8 @@ __global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(kFinThreads)
 em_finish_kernel(const double *partials, int n_part, int64_t n_cols, int64_t ld,
                  double *lnp0, double *lnp1, double *pi0, double *pi1, EmState *st, P2PArgs pa) {
     static_assert(kFinThreads == 1024, "cluster_sum assumes 32 warps");
+    pdl_wait();               // the pass kernel's partial sums are complete and visible
+    pdl_launch_dependents();  // the next pass may prime its ring while this tail runs
     {   // blockIdx.y = restart slot of a batched session (one cluster per slot)
         const size_t slot = blockIdx.y;
         st += slot;
@@ -946,6 +970,26 @@ static pair_fn pick_pair(int nc) {
 constexpr int kMaxPairNC = 6;   // 2 restarts x (pi + T) x NC double2 must fit 128 registers
 constexpr int kMaxSlots = 2;
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait): the kernel may
+// be scheduled before its predecessor in the stream has finished.  MXB_EM_NO_PDL=1 turns the
+// attribute off (plain stream order).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t s, Args... args) {
+    static const bool use_pdl = getenv("MXB_EM_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // One EM iteration on em->ctx->stream (no host sync).
 static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
                              cudaEvent_t pass_end = nullptr) {
@@ -954,24 +998,24 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
     if (pass_begin) MXB_CUDA(cudaEventRecord(pass_begin, s));
     if (em->n_slots == 2) {
         const size_t ps = (size_t)em->n_part * em->ld;
-        pick_pair(em->nc)<<<em->grid_fast, kPassThreads, em->smem_bytes, s>>>(
-            em->lin, em->ld, em->n_rows, em->weights, em->pi[0], em->pi[1], em->pi[0] + em->ld,
-            em->pi[1] + em->ld, em->state, em->partials, em->partials + ps, em->n_stages);
+        MXB_CUDA(launch_pdl(pick_pair(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
+                            em->smem_bytes, s, em->lin, em->ld, em->n_rows, em->weights,
+                            em->pi[0], em->pi[1], em->pi[0] + em->ld, em->pi[1] + em->ld,
+                            em->state, em->partials, em->partials + ps, em->n_stages));
         ctx->launches += 1;
         if (pass_end) MXB_CUDA(cudaEventRecord(pass_end, s));
         P2PArgs pa;
         memset(&pa, 0, sizeof(pa));
-        em_finish_kernel<false><<<dim3(kFinCtas, 2), kFinThreads, 0, s>>>(
-            em->partials, em->n_part, em->n_cols, em->ld, em->lnp[0], em->lnp[1], em->pi[0],
-            em->pi[1], em->state, pa);
+        MXB_CUDA(launch_pdl(em_finish_kernel<false>, dim3(kFinCtas, 2), dim3(kFinThreads), 0, s,
+                            em->partials, em->n_part, em->n_cols, em->ld, em->lnp[0], em->lnp[1],
+                            em->pi[0], em->pi[1], em->state, pa));
         ctx->launches += 1;
-        MXB_CUDA(cudaGetLastError());
         return MXB_OK;
     }
     if (em->fast) {
-        pick_pass(em->nc)<<<em->grid_fast, kPassThreads, em->smem_bytes, s>>>(
-            em->lin, em->ld, em->n_rows, em->weights, em->pi[0], em->pi[1], em->state,
-            em->partials, em->n_stages);
+        MXB_CUDA(launch_pdl(pick_pass(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
+                            em->smem_bytes, s, em->lin, em->ld, em->n_rows, em->weights,
+                            em->pi[0], em->pi[1], em->state, em->partials, em->n_stages));
         ctx->launches += 1;
     } else {
         const int rd_blocks = (int)std::max<int64_t>(
@@ -991,16 +1035,15 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
             pa.world = ctx->world;
             pa.rank = ctx->rank;
             for (int r = 0; r < ctx->world; ++r) pa.block[r] = ctx->p2p_block[r];
-            em_finish_kernel<true><<<kFinCtas, kFinThreads, 0, s>>>(
-                em->partials, em->n_part, em->n_cols, em->ld, em->lnp[0], em->lnp[1], em->pi[0],
-                em->pi[1], em->state, pa);
+            MXB_CUDA(launch_pdl(em_finish_kernel<true>, dim3(kFinCtas), dim3(kFinThreads), 0, s,
+                                em->partials, em->n_part, em->n_cols, em->ld, em->lnp[0],
+                                em->lnp[1], em->pi[0], em->pi[1], em->state, pa));
         } else {
-            em_finish_kernel<false><<<kFinCtas, kFinThreads, 0, s>>>(
-                em->partials, em->n_part, em->n_cols, em->ld, em->lnp[0], em->lnp[1], em->pi[0],
-                em->pi[1], em->state, pa);
+            MXB_CUDA(launch_pdl(em_finish_kernel<false>, dim3(kFinCtas), dim3(kFinThreads), 0, s,
+                                em->partials, em->n_part, em->n_cols, em->ld, em->lnp[0],
+                                em->lnp[1], em->pi[0], em->pi[1], em->state, pa));
         }
         ctx->launches += 1;
-        MXB_CUDA(cudaGetLastError());
         return MXB_OK;
     }
     em_colreduce_kernel<<<(int)ceil_div(em->ld, 256), 256, 0, s>>>(em->partials, em->n_part,
