@@ -730,20 +730,36 @@ em_finish_kernel(const double *partials, int n_part, int64_t n_cols, int64_t ld,
     double *lnp_new = cur ? lnp0 : lnp1;
     double *pi_new = cur ? pi0 : pi1;
 
-    const int64_t j = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
-    const bool live = j < n_cols;
-    double t = 0.0;
-    if (live) {
-        const double *col = partials + j;
-        int b = 0;
-        for (; b + 8 <= n_part; b += 8) {
-            double v[8];
+    // Column sums.  A CTA owns ld/16 column pairs; its 1024 threads split the per-CTA
+    // partials of a pair into n_grp contiguous ranges (three at H=5408) that are summed
+    // concurrently and then added in range order: fixed order, a third of the latency.
+    __shared__ double2 red[kFinThreads];
+    const int ppc = (int)(ld >> 4);                       // column pairs per CTA
+    const int n_grp = min(8, kFinThreads / ppc);
+    const int pair_local = threadIdx.x % ppc, grp = threadIdx.x / ppc;
+    const int64_t c = (int64_t)blockIdx.x * ppc + pair_local;   // columns 2c, 2c+1
+    if (grp < n_grp) {
+        const int b0 = (int)((int64_t)n_part * grp / n_grp), b1 = (int)((int64_t)n_part * (grp + 1) / n_grp);
+        const double2 *col = reinterpret_cast<const double2 *>(partials) + c;
+        const size_t stride = (size_t)(ld >> 1);
+        double2 acc = make_double2(0.0, 0.0);
+        int b = b0;
+        for (; b + 4 <= b1; b += 4) {
+            double2 v[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = col[(size_t)(b + u) * ld];
+            for (int u = 0; u < 4; ++u) v[u] = col[(size_t)(b + u) * stride];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) t += v[u];
+            for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
         }
-        for (; b < n_part; ++b) t += col[(size_t)b * ld];
+        for (; b < b1; ++b) { const double2 v = col[(size_t)b * stride]; acc.x += v.x; acc.y += v.y; }
+        red[grp * ppc + pair_local] = acc;
+    }
+    __syncthreads();
+    const bool owner = grp == 0;                          // one thread per column pair from here on
+    const bool live_x = owner && 2 * c < n_cols, live_y = owner && 2 * c + 1 < n_cols;
+    double2 t = make_double2(0.0, 0.0);
+    if (owner) {
+        for (int g = 0; g < n_grp; ++g) { t.x += red[g * ppc + pair_local].x; t.y += red[g * ppc + pair_local].y; }
     }
     // a peer CTA's shared memory may only be written once that CTA is known to have
     // started: one cluster barrier before the first distributed-shared-memory store
@@ -758,10 +774,10 @@ em_finish_kernel(const double *partials, int n_part, int64_t n_cols, int64_t ld,
         if (threadIdx.x == 0) s_timeout = 0;
         seq = *my_seq + 1;  // advanced by CTA 0 at the very end of this launch
         const int slot = (int)(seq & 1ull);
-        if (live) {
+        if (owner) {
             for (int r = 0; r < W; ++r) {
-                double *inbox = reinterpret_cast<double *>(pa.block[r] + kP2PInboxOffset);
-                inbox[((size_t)slot * kP2PMaxWorld + pa.rank) * kP2PMaxLd + j] = t;
+                double2 *inbox = reinterpret_cast<double2 *>(pa.block[r] + kP2PInboxOffset);
+                inbox[((size_t)slot * kP2PMaxWorld + pa.rank) * (kP2PMaxLd / 2) + c] = t;
             }
         }
         __threadfence_system();
@@ -776,25 +792,40 @@ em_finish_kernel(const double *partials, int n_part, int64_t n_cols, int64_t ld,
             }
         }
         cluster.sync();  // all ranks' sums have landed in this rank's inbox
-        if (live) {
-            const double *inbox = reinterpret_cast<const double *>(pa.block[pa.rank] + kP2PInboxOffset);
-            t = 0.0;
-            for (int r = 0; r < W; ++r)
-                t += __ldcg(&inbox[((size_t)slot * kP2PMaxWorld + r) * kP2PMaxLd + j]);
+        if (owner) {
+            const double2 *inbox = reinterpret_cast<const double2 *>(pa.block[pa.rank] + kP2PInboxOffset);
+            t = make_double2(0.0, 0.0);
+            for (int r = 0; r < W; ++r) {
+                const double2 v = __ldcg(&inbox[((size_t)slot * kP2PMaxWorld + r) * (kP2PMaxLd / 2) + c]);
+                t.x += v.x;
+                t.y += v.y;
+            }
         }
     }
-    const double p = live ? pi_old[j] : 0.0;
-    const double total = cluster_sum(p * t, wsum[0], slots[0]);
+    double2 p = make_double2(0.0, 0.0);
+    if (owner) p = reinterpret_cast<const double2 *>(pi_old)[c];
+    if (!live_x) p.x = 0.0;
+    if (!live_y) p.y = 0.0;
+    const double total = cluster_sum((live_x ? p.x * t.x : 0.0) + (live_y ? p.y * t.y : 0.0),
+                                     wsum[0], slots[0]);
 
     double dl = 0.0;
-    if (live) {
-        double ln_new;
-        if (p >= 1e-290) ln_new = log(p * t / total);
-        else ln_new = lnp_old[j] + log(t / total);  // pi underflowed: stay in log space
-        const double p_new = exp(ln_new);
-        lnp_new[j] = ln_new;
-        pi_new[j] = p_new;
-        dl = fabs(p_new - p);
+    if (owner) {
+        double2 ln_new = make_double2(-INFINITY, -INFINITY), p_new = make_double2(0.0, 0.0);
+        if (live_x) {
+            if (p.x >= 1e-290) ln_new.x = log(p.x * t.x / total);
+            else ln_new.x = lnp_old[2 * c] + log(t.x / total);  // pi underflowed: stay in log space
+            p_new.x = exp(ln_new.x);
+            dl += fabs(p_new.x - p.x);
+        }
+        if (live_y) {
+            if (p.y >= 1e-290) ln_new.y = log(p.y * t.y / total);
+            else ln_new.y = lnp_old[2 * c + 1] + log(t.y / total);
+            p_new.y = exp(ln_new.y);
+            dl += fabs(p_new.y - p.y);
+        }
+        reinterpret_cast<double2 *>(lnp_new)[c] = ln_new;   // padding columns: (-inf, 0) as set_props left them
+        reinterpret_cast<double2 *>(pi_new)[c] = p_new;
     }
     const double delta = cluster_sum(dl, wsum[1], slots[1]);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
