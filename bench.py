@@ -20,8 +20,9 @@ One JSON line is printed by rank 0:
             materialisation and the device->host copy of the N x H result inside
             the timed region (after one short untimed call)
   roofline  the fused E/M pass kernel against the measured HBM copy bandwidth
-  restart_sweep  4 restarts x 100 iterations (BASELINE.json config 4), two restarts
-            per read of the matrix and one at a time
+  restart_sweep  4 restarts x 100 iterations per GPU (BASELINE.json config 4), two restarts
+            per read of the matrix and one at a time; under torchrun the matrix is
+            replicated and 4 N restarts are dealt over the N GPUs
   cpu_baseline  the CPU oracle port (C + OpenMP, all host threads) on a row sample
 --rows N replaces the workload by N undeduplicated rows per GPU (config-3 shards).
 """
@@ -359,26 +360,43 @@ def run_b200(opts):
                 if opts.rows == 0 and opts.fragments == 1000000 else None}
 
     # ---- restart sweep (config 4): two restarts share every read of the matrix ----
+    # One GPU: 4 restarts, two per pass and one per pass.  N GPUs: the matrix of rank 0 is
+    # replicated (every rank rebuilds it from rank 0's seed), 4 N restarts are dealt round
+    # robin (args.b200_shard = "restarts") and the log-proportions are combined by all-reduce.
     sweep = None
-    if world == 1 and not opts.no_sweep:
-        n_multi, sweep_iters = 4, min(100, max(10, opts.steps))
+    if not opts.no_sweep and (world == 1 or opts.rows == 0):
+        n_multi, sweep_iters = 4 * world, min(100, max(10, opts.steps))
         inits = np.log(np.random.RandomState(3).dirichlet([1.0] * h, size=n_multi))
         sargs = argparse.Namespace(verbose=False, init_alpha=1.0, tolerance=-1.0,
-                                   max_iter=sweep_iters, n_multi=n_multi)
+                                   max_iter=sweep_iters, n_multi=n_multi,
+                                   b200_shard="restarts" if world > 1 else None)
         sweep = {"n_multi": n_multi, "iterations_per_restart": sweep_iters}
-        for mode in ("two_per_pass", "one_per_pass"):
+        smat, swts = dmat, weights
+        if world > 1 and rank != 0:
+            _, _, mix0 = load_workload(opts.fragments, opts.seed)
+            _, _, smat, _ = build_matrix_from_csr(tables, mix0.csr(tables), ctx=ctx,
+                                                  want_host=False, keep_device=True)
+            swts = mix0.weights.astype(np.float64)
+        sn = smat.shape[0]
+        for mode in ("two_per_pass", "one_per_pass") if world == 1 else ("two_per_pass",):
             if mode == "one_per_pass":
                 os.environ["MXB_EM_NO_BATCH"] = "1"
             try:
                 barrier()
                 t0 = time.perf_counter()
-                b200_em.run_em_device(dmat, weights, sargs, want_host=False, inits=inits)
+                b200_em.run_em_device(smat, swts, sargs, want_host=False, inits=inits)
                 barrier()
-                dt = time.perf_counter() - t0
+                dt = max_over_ranks(time.perf_counter() - t0)
             finally:
                 os.environ.pop("MXB_EM_NO_BATCH", None)
-            sweep[mode + "_cell_updates_per_s"] = float(n) * h * n_multi * sweep_iters / dt
+            sweep[mode + "_cell_updates_per_s"] = float(sn) * h * n_multi * sweep_iters / dt
             sweep[mode + "_seconds"] = dt
+        if world > 1:
+            sweep["parallelism"] = ("matrix replicated, %d restarts dealt round robin over %d GPUs, "
+                                    "log-proportions and read matrices combined over NCCL"
+                                    % (n_multi, world))
+        if smat is not dmat:
+            smat.free()
 
     # ---- e2e: the drop-in call with host buffers ---------------------------------
     e2e = None

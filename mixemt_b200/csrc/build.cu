@@ -160,7 +160,7 @@ build_matrix_dense_kernel(const uint32_t *__restrict__ bits, const double2 *__re
 struct BuildTables {
     const uint32_t *bits;      // dense [n_pos][n_planes][n_words]
     const double2 *hitmiss;    // [n_pos]
-    const uint8_t *ref_code;   // [n_pos]
+    const uint8_t *plane_base; // [n_pos * n_planes] outcome of the baseline pattern: 1 = match
     const int32_t *dev_ptr;    // [n_pos * n_planes + 1]
     const uint2 *dev_ent;      // {word index, D}
     int n_planes, n_words, n_hap, n_groups;
@@ -272,7 +272,7 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
             int c = base_code[k0 + k];
             if (c >= tb.n_planes - 1) c = tb.n_planes - 1;
             const double2 hm = tb.hitmiss[p];
-            const bool base_match = (c == (int)tb.ref_code[p]);
+            const bool base_match = tb.plane_base[p * tb.n_planes + c] != 0;
             s_term[k] = base_match ? hm : make_double2(hm.y, hm.x);
             s_plane[k] = p * tb.n_planes + c;
             // the match flag rides in s_pcnt[k + 1] until the prefix pass
@@ -397,6 +397,19 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                     if (lane == 0) { s_gbase[g] = (uint16_t)kDenseGroup; atomicAdd(&s_ndense, 1); }
                     continue;
                 }
+                if (a == 1) {  // a third of the groups: one deviating observation, one class
+                    const uint32_t d = s_ew[s_goff[g]];
+                    int base_idx = 0;
+                    if (lane == 0) base_idx = atomicAdd(&s_nitems, 1);
+                    base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
+                    if (lane == 0) {
+                        if (base_idx + 1 > Tier::kItems) s_overflow = 1;
+                        else s_item[base_idx] = make_uint2(1u, (uint32_t)g);
+                        s_gbase[g] = (uint16_t)base_idx;
+                    }
+                    s_cell[g * 32 + lane] = (uint8_t)((d >> lane) & 1u);
+                    continue;
+                }
                 const uint32_t *w = s_ew + s_goff[g];
                 uint32_t pattern = 0;
 #pragma unroll 4
@@ -440,30 +453,69 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
             s_val[0] = s_prefix[n_obs];
             if (kCounts) s_icnt[0] = s_pcnt[n_obs];
         }
+        // A warp takes 32 consecutive items and walks k in lock step from the 8-aligned
+        // block of its earliest first deviation: a lane that has not deviated yet adds the
+        // marker-free terms, i.e. it retraces P[] exactly, so starting every lane at
+        // P[k_start] is the same chain as starting it at P[its own first deviation].  The
+        // deviations of a lane inside the current 32-observation block are gathered into
+        // one mask word up front, which leaves (shared load, bit test, select, add) per step.
+        constexpr int kNoDev = 0x7FFFFFFF;
 #pragma unroll 1
-        for (int it = 1 + tid; it < n_items; it += kClassThreads) {
-            const uint2 item = s_item[it];
-            uint32_t rem = item.x;   // bit e: deviates at the group's e-th deviating observation
-            const uint16_t *ek = s_ek + s_goff[item.y];
-            int nk = ek[__ffs(rem) - 1];
-            double acc = s_prefix[nk];
-            int cnt = kCounts ? (int)s_pcnt[nk] : 0;
-#pragma unroll 2
-            for (int k = nk; k < n_obs; ++k) {
-                const double2 t = s_term[k];
-                const bool dev = (k == nk);
-                acc += dev ? t.y : t.x;
-                if (kCounts) {
-                    const int bm = (int)s_pcnt[k + 1] - (int)s_pcnt[k];
-                    cnt += dev ? 1 - bm : bm;
-                }
-                if (dev) {
+        for (int it0 = 1 + warp * 32; it0 < n_items; it0 += kClassThreads) {
+            const int it = it0 + lane;
+            uint32_t rem = 0u;   // bit e: deviates at the group's e-th deviating observation
+            const uint16_t *ek = s_ek;
+            int nk = kNoDev;
+            if (it < n_items) {
+                const uint2 item = s_item[it];
+                rem = item.x;
+                ek = s_ek + s_goff[item.y];
+                nk = ek[__ffs(rem) - 1];
+                rem &= rem - 1;
+            }
+            int k = __reduce_min_sync(0xffffffffu, nk) & ~7;   // warp-uniform
+            double acc = s_prefix[k];
+            int cnt = kCounts ? (int)s_pcnt[k] : 0;
+            while (k < n_obs) {
+                const int kb = k & ~31;
+                uint32_t word = 0u;   // bit (k' - kb): this lane deviates at observation k'
+                while (nk < kb + 32) {
+                    word |= 1u << (nk - kb);
+                    nk = rem ? (int)ek[__ffs(rem) - 1] : kNoDev;
                     rem &= rem - 1;
-                    nk = rem ? (int)ek[__ffs(rem) - 1] : 0x7FFFFFFF;
+                }
+                const int k_end = min(kb + 32, n_obs);
+#pragma unroll 1
+                for (; k + 8 <= k_end; k += 8) {
+                    const uint32_t w8 = word >> (k - kb);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const double2 t = s_term[k + u];
+                        const bool dev = (w8 >> u) & 1u;
+                        acc += dev ? t.y : t.x;
+                        if (kCounts) {
+                            const int bm = (int)s_pcnt[k + u + 1] - (int)s_pcnt[k + u];
+                            cnt += dev ? 1 - bm : bm;
+                        }
+                    }
+                }
+                if (k_end == n_obs) {   // the last, partial group of eight
+#pragma unroll 1
+                    for (; k < k_end; ++k) {
+                        const double2 t = s_term[k];
+                        const bool dev = (word >> (k - kb)) & 1u;
+                        acc += dev ? t.y : t.x;
+                        if (kCounts) {
+                            const int bm = (int)s_pcnt[k + 1] - (int)s_pcnt[k];
+                            cnt += dev ? 1 - bm : bm;
+                        }
+                    }
                 }
             }
-            s_val[it] = acc;
-            if (kCounts) s_icnt[it] = cnt;
+            if (it < n_items) {
+                s_val[it] = acc;
+                if (kCounts) s_icnt[it] = cnt;
+            }
         }
         // groups with more than 32 deviating positions: walk the dense table, one warp each
 #pragma unroll 1
@@ -566,16 +618,27 @@ int mxb_phylo_pack(mxb_ctx *ctx, int32_t n_pos, int32_t n_hap, int32_t n_sym,
             bits[((size_t)p * n_planes + c) * n_words + (j >> 5)] |= 1u << (j & 31);
         }
     }
-    // sparse deviation lists: D = bits XOR (marker-free outcome), non-zero words only
+    // sparse deviation lists: D = bits XOR (baseline outcome), non-zero words only.  The
+    // baseline outcome of a plane is the one most haplotypes have: the marker-free outcome
+    // (a == ref[p]) except where a derived allele is carried by more than half of them.
     std::vector<int32_t> dev_ptr;
     std::vector<uint2> dev_ent;
+    std::vector<uint8_t> plane_base;
     try {
         dev_ptr.assign((size_t)n_pos * n_planes + 1, 0);
+        plane_base.assign((size_t)n_pos * n_planes, 0);
         const int n_groups = (int)ceil_div(std::max(n_hap, 1), 32);
+        const bool majority = getenv("MXB_BUILD_BASE_REF") == nullptr;
         for (int p = 0; p < n_pos; ++p) {
             for (int a = 0; a < n_planes; ++a) {
                 const uint32_t *plane = &bits[((size_t)p * n_planes + a) * n_words];
-                const bool base_match = (a == (int)ref_code[p]);
+                bool base_match = (a == (int)ref_code[p]);
+                if (majority) {
+                    int64_t n_match = 0;
+                    for (int g = 0; g < n_groups; ++g) n_match += __builtin_popcount(plane[g]);
+                    base_match = 2 * n_match > (int64_t)n_hap;
+                }
+                plane_base[(size_t)p * n_planes + a] = base_match ? 1 : 0;
                 for (int g = 0; g < n_groups; ++g) {
                     const int valid = std::min(32, n_hap - g * 32);
                     const uint32_t vmask = valid >= 32 ? 0xFFFFFFFFu
@@ -604,7 +667,7 @@ int mxb_phylo_pack(mxb_ctx *ctx, int32_t n_pos, int32_t n_hap, int32_t n_sym,
         const size_t ent_bytes = std::max<size_t>(1, dev_ent.size()) * sizeof(uint2);
         e = cudaMalloc(&ph->bits, bits.size() * sizeof(uint32_t));
         if (e == cudaSuccess) e = cudaMalloc(&ph->hitmiss, hm.size() * sizeof(double2));
-        if (e == cudaSuccess) e = cudaMalloc(&ph->ref_code, (size_t)n_pos);
+        if (e == cudaSuccess) e = cudaMalloc(&ph->plane_base, std::max<size_t>(1, plane_base.size()));
         if (e == cudaSuccess) e = cudaMalloc(&ph->dev_ptr, dev_ptr.size() * sizeof(int32_t));
         if (e == cudaSuccess) e = cudaMalloc(&ph->dev_ent, ent_bytes);
         if (e == cudaSuccess)
@@ -614,8 +677,8 @@ int mxb_phylo_pack(mxb_ctx *ctx, int32_t n_pos, int32_t n_hap, int32_t n_sym,
             e = cudaMemcpyAsync(ph->hitmiss, hm.data(), hm.size() * sizeof(double2),
                                 cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess)
-            e = cudaMemcpyAsync(ph->ref_code, ref_code, (size_t)n_pos, cudaMemcpyHostToDevice,
-                                ctx->stream);
+            e = cudaMemcpyAsync(ph->plane_base, plane_base.data(), plane_base.size(),
+                                cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(ph->dev_ptr, dev_ptr.data(), dev_ptr.size() * sizeof(int32_t),
                                 cudaMemcpyHostToDevice, ctx->stream);
@@ -638,7 +701,7 @@ int mxb_phylo_destroy(mxb_phylo *ph) {
     cudaSetDevice(ph->ctx->device);
     if (ph->bits) cudaFree(ph->bits);
     if (ph->hitmiss) cudaFree(ph->hitmiss);
-    if (ph->ref_code) cudaFree(ph->ref_code);
+    if (ph->plane_base) cudaFree(ph->plane_base);
     if (ph->dev_ptr) cudaFree(ph->dev_ptr);
     if (ph->dev_ent) cudaFree(ph->dev_ent);
     delete ph;
@@ -722,7 +785,7 @@ int mxb_build_matrix(mxb_ctx *ctx, const mxb_phylo *ph, int64_t n_rows,
                 BuildTables tb;
                 tb.bits = ph->bits;
                 tb.hitmiss = ph->hitmiss;
-                tb.ref_code = ph->ref_code;
+                tb.plane_base = ph->plane_base;
                 tb.dev_ptr = ph->dev_ptr;
                 tb.dev_ent = ph->dev_ent;
                 tb.n_planes = ph->n_sym + 1;

@@ -89,7 +89,7 @@ struct mxb_phylo {
     uint32_t *bits = nullptr;   // [n_pos][n_sym+1][n_words]
     double2 *hitmiss = nullptr; // [n_pos] (hit, miss)
     // sparse deviation form of `bits` (see build.cu)
-    uint8_t *ref_code = nullptr;  // [n_pos]
+    uint8_t *plane_base = nullptr;  // [n_pos * (n_sym+1)] baseline outcome of the plane
     int32_t *dev_ptr = nullptr;   // [n_pos * (n_sym+1) + 1]
     uint2 *dev_ent = nullptr;     // {word index, D}
     int64_t n_dev = 0;
