@@ -57,6 +57,7 @@
 // the plain kernel that is also used when H is too large for the class
 // kernel's shared-memory layout (or MXB_BUILD_DENSE=1 is set).
 #include <new>
+#include <string.h>
 #include <vector>
 
 #include "common.cuh"
@@ -170,39 +171,37 @@ constexpr int kMaxObs = 512;         // observations per row (longer rows: dense
 constexpr unsigned kDenseGroup = 0xFFFFu;
 static_assert(kMaxObs == kBuildObsChunk, "the dense row path reuses the class kernel's staging area");
 
-// Pool sizes of the two launches: tier 1 serves the common rows at 5 CTAs/SM,
-// tier 2 re-runs the few rows that overflowed tier 1's pools with larger ones.
-// kObsWords * 32 = observations per row the tier accepts.
+// Pool sizes of the launches: tier 1 serves the common rows at 5 CTAs/SM, tier 2 re-runs
+// the few rows that overflowed tier 1's pools with larger ones.  kObsWords * 32 =
+// observations per row the tier accepts.
 struct Tier1 {
     static constexpr int kThreads = 256, kEntries = 1536, kItems = 1024, kObsWords = 8, kMinBlocks = 5;
 };
 struct Tier2 {
-    static constexpr int kThreads = 512, kEntries = 8192, kItems = 4096, kObsWords = 16, kMinBlocks = 2;
+    static constexpr int kThreads = 512, kEntries = 8064, kItems = 4096, kObsWords = 16, kMinBlocks = 2;
 };
 static_assert(Tier2::kObsWords * 32 == kMaxObs, "tier 2 takes every row the staging area holds");
 
-// Shared-memory layout of the class kernel (bytes), shared by host and device.
+// Shared-memory layout of the class kernel (bytes).  Every offset is a compile-time
+// constant (the group arrays are sized for kMaxGroups 32-column groups), so shared-memory
+// addresses are immediates instead of values recomputed around every loop.
+template <class Tier, int kMaxGroups, bool kCounts>
 struct BuildSmem {
-    size_t term, prefix, item, ew, plane, gmap, gcnt, goff, icnt, ek, pcnt, gbase, cell, total;
-    __host__ __device__ BuildSmem(int n_groups, bool counts, int n_entries, int n_items,
-                                  int obs_words) {
-        const int n_obs = obs_words * 32;
-        size_t o = 0;
-        term = o;   o += sizeof(double2) * n_obs;                // (marker-free, deviating) terms
-        prefix = o; o += sizeof(double) * (n_obs + 1);           // marker-free prefix sums
-        item = o;   o += sizeof(uint2) * n_items;                // (pattern, group) -> value
-        ew = o;     o += sizeof(uint32_t) * (n_entries > n_obs ? n_entries : n_obs);  // entry pool: D words
-        plane = o;  o += sizeof(int) * n_obs;                    // (position, symbol) plane per k
-        gmap = o;   o += sizeof(uint32_t) * (size_t)n_groups * obs_words;  // deviating k per group
-        gcnt = o;   o += sizeof(int) * (size_t)n_groups;         // entries per group
-        goff = o;   o += sizeof(int) * (size_t)n_groups;         // pool offset of the group
-        icnt = o;   o += counts ? sizeof(int) * n_items : 0;     // match count per item
-        ek = o;     o += sizeof(uint16_t) * n_entries;           // entry pool: observation index
-        pcnt = o;   o += sizeof(uint16_t) * (n_obs + 2);         // marker-free match prefix
-        gbase = o;  o += sizeof(uint16_t) * (size_t)n_groups;    // first item of the group
-        cell = o;   o += (size_t)n_groups * 32;                  // class of the cell in its group
-        total = (o + 15) & ~(size_t)15;
-    }
+    static constexpr int kObs = Tier::kObsWords * 32;
+    static constexpr size_t term = 0;                                    // (baseline, deviating) terms
+    static constexpr size_t prefix = term + sizeof(double2) * kObs;      // baseline prefix sums
+    static constexpr size_t item = prefix + sizeof(double) * (kObs + 1); // (pattern, group) -> value
+    static constexpr size_t ew = item + sizeof(uint2) * Tier::kItems;    // entry pool: D words
+    static constexpr size_t plane = ew + sizeof(uint32_t) * (Tier::kEntries > kObs ? Tier::kEntries : kObs);
+    static constexpr size_t gmap = plane + sizeof(int) * kObs;           // deviating k per group
+    static constexpr size_t gcnt = gmap + sizeof(uint32_t) * kMaxGroups * Tier::kObsWords;
+    static constexpr size_t goff = gcnt + sizeof(int) * kMaxGroups;      // pool offset of the group
+    static constexpr size_t icnt = goff + sizeof(int) * kMaxGroups;      // match count per item
+    static constexpr size_t ek = icnt + (kCounts ? sizeof(int) * Tier::kItems : 0);  // entry pool: k
+    static constexpr size_t pcnt = ek + sizeof(uint16_t) * Tier::kEntries;  // baseline match prefix
+    static constexpr size_t gbase = pcnt + sizeof(uint16_t) * (kObs + 2);   // first item of the group
+    static constexpr size_t cell = gbase + sizeof(uint16_t) * kMaxGroups;   // class of the cell in its group
+    static constexpr size_t total = (cell + (size_t)kMaxGroups * 32 + 15) & ~(size_t)15;
 };
 
 // Barrier among the scatter/classify warps only (all but the last warp, which
@@ -212,42 +211,46 @@ __device__ __forceinline__ void work_warps_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");
 }
 
-
 // Rows come from row_list[0 .. *n_list) when row_list != NULL, else 0 .. n_rows.
 // Rows that do not fit the pools are appended to overflow_list when there is
 // one (tier 1), else they take the dense path (tier 2).
-template <bool kCounts, class Tier>
+template <bool kCounts, class Tier, int kMaxGroups>
 __global__ void __launch_bounds__(Tier::kThreads, kCounts ? 1 : Tier::kMinBlocks)
 build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ row_list,
                     const int *__restrict__ n_list, int32_t *__restrict__ overflow_list,
-                    int *__restrict__ overflow_count, const int64_t *__restrict__ row_ptr,
+                    int *__restrict__ overflow_count, int *__restrict__ work_counter,
+                    const int64_t *__restrict__ row_ptr,
                     const int32_t *__restrict__ pos_idx, const uint8_t *__restrict__ base_code,
                     double *__restrict__ out, int32_t *__restrict__ match_out) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_nitems;
+    __shared__ int s_next[2];
     __shared__ int s_overflow;
+    __shared__ int s_ndense;
+    __shared__ int s_prefix_ready;
+    using L = BuildSmem<Tier, kMaxGroups, kCounts>;
     constexpr int W = Tier::kObsWords;
     constexpr int kClassThreads = Tier::kThreads;
     constexpr int kClassWarps = kClassThreads / 32;
     constexpr int kWorkWarps = kClassWarps - 1;  // the last warp runs the prefix chain
-    __shared__ int s_ndense;
-    const BuildSmem L(tb.n_groups, kCounts, Tier::kEntries, Tier::kItems, W);
-    double2 *s_term = reinterpret_cast<double2 *>(smem + L.term);
-    double *s_prefix = reinterpret_cast<double *>(smem + L.prefix);
-    uint2 *s_item = reinterpret_cast<uint2 *>(smem + L.item);
-    double *s_val = reinterpret_cast<double *>(smem + L.item);  // overwrites the item
-    uint32_t *s_ew = reinterpret_cast<uint32_t *>(smem + L.ew);
-    int *s_plane = reinterpret_cast<int *>(smem + L.plane);
-    uint32_t *s_gmap = reinterpret_cast<uint32_t *>(smem + L.gmap);
-    int *s_gcnt = reinterpret_cast<int *>(smem + L.gcnt);
-    int *s_goff = reinterpret_cast<int *>(smem + L.goff);
-    int *s_icnt = reinterpret_cast<int *>(smem + L.icnt);
-    uint16_t *s_ek = reinterpret_cast<uint16_t *>(smem + L.ek);
-    uint16_t *s_pcnt = reinterpret_cast<uint16_t *>(smem + L.pcnt);
-    uint16_t *s_gbase = reinterpret_cast<uint16_t *>(smem + L.gbase);
-    uint8_t *s_cell = reinterpret_cast<uint8_t *>(smem + L.cell);
+    // every work warp allocates chain items from its own pool: no atomics, and the warp
+    // that found a class also evaluates it (item 0 is the baseline class)
+    constexpr int kPool = (Tier::kItems - 1) / kWorkWarps;
+    double2 *s_term = reinterpret_cast<double2 *>(smem + L::term);
+    double *s_prefix = reinterpret_cast<double *>(smem + L::prefix);
+    uint2 *s_item = reinterpret_cast<uint2 *>(smem + L::item);
+    double *s_val = reinterpret_cast<double *>(smem + L::item);  // overwrites the item
+    uint32_t *s_ew = reinterpret_cast<uint32_t *>(smem + L::ew);
+    int *s_plane = reinterpret_cast<int *>(smem + L::plane);
+    uint32_t *s_gmap = reinterpret_cast<uint32_t *>(smem + L::gmap);
+    int *s_gcnt = reinterpret_cast<int *>(smem + L::gcnt);
+    int *s_goff = reinterpret_cast<int *>(smem + L::goff);
+    int *s_icnt = reinterpret_cast<int *>(smem + L::icnt);
+    uint16_t *s_ek = reinterpret_cast<uint16_t *>(smem + L::ek);
+    uint16_t *s_pcnt = reinterpret_cast<uint16_t *>(smem + L::pcnt);
+    uint16_t *s_gbase = reinterpret_cast<uint16_t *>(smem + L::gbase);
+    uint8_t *s_cell = reinterpret_cast<uint8_t *>(smem + L::cell);
     // the dense row path reuses the staging areas: (hit, miss) and plane offsets
-    uint32_t *s_off = reinterpret_cast<uint32_t *>(smem + L.ew);
+    uint32_t *s_off = reinterpret_cast<uint32_t *>(smem + L::ew);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -255,8 +258,14 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
     const int n_hap = tb.n_hap;
     const int n_groups = tb.n_groups;
     const int64_t n_work = row_list ? (int64_t)*n_list : n_rows;
+    constexpr int kNoDev = 0x7FFFFFFF;
 
-    for (int64_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    // Rows cost between 0.2x and 10x the average: after its first row a CTA takes rows from
+    // a device-wide counter.  The next index is fetched while the current row is processed
+    // and handed over through s_next[parity] behind the row's closing barrier.
+    int parity = 0;
+    for (int64_t wi = blockIdx.x; wi < n_work; wi = s_next[parity], parity ^= 1) {
+        if (tid == 0) s_next[parity] = (int)gridDim.x + atomicAdd(work_counter, 1);
         const int64_t row = row_list ? (int64_t)row_list[wi] : wi;
         const int64_t k0 = row_ptr[row];
         const int64_t k1 = row_ptr[row + 1];
@@ -279,11 +288,11 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
             s_pcnt[k + 1] = base_match ? 1 : 0;
         }
         for (int i = tid; i < n_groups * W; i += kClassThreads) s_gmap[i] = 0u;
-        if (tid == 0) { s_nitems = 1; s_overflow = 0; s_ndense = 0; }
+        if (tid == 0) { s_overflow = 0; s_ndense = 0; s_prefix_ready = 0; }
         __syncthreads();
 
         if (warp == kWorkWarps) {
-            // ---- 1'. marker-free prefix sums (one dependent-add chain), off the others' path
+            // ---- 1'. baseline prefix sums (one dependent-add chain), off the others' path
             if (lane == 0) {
                 double acc = 0.0;
                 int cnt = 0;
@@ -309,6 +318,10 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                     s_prefix[k + 1] = acc;
                     s_pcnt[k + 1] = (uint16_t)cnt;
                 }
+                s_val[0] = acc;   // class 0: the baseline pattern
+                if (kCounts) s_icnt[0] = cnt;
+                __threadfence_block();
+                *reinterpret_cast<volatile int *>(&s_prefix_ready) = 1;
             }
         } else {
             // ---- 1. deviation entries of the row, grouped by 32-column group ------------------
@@ -385,6 +398,8 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
             work_warps_sync<kWorkWarps * 32>();
 
             // ---- 2. classes of every 32-column group ------------------------------------------
+            const int pool_base = 1 + warp * kPool;
+            int my_items = 0;       // warp-uniform; items past kPool are counted but not stored
 #pragma unroll 1
             for (int g = warp; g < n_groups && !too_many_entries; g += kWorkWarps) {
                 const int a = s_gcnt[g];
@@ -397,20 +412,16 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                     if (lane == 0) { s_gbase[g] = (uint16_t)kDenseGroup; atomicAdd(&s_ndense, 1); }
                     continue;
                 }
+                const uint32_t *w = s_ew + s_goff[g];
+                const int base_idx = pool_base + my_items;
                 if (a == 1) {  // a third of the groups: one deviating observation, one class
-                    const uint32_t d = s_ew[s_goff[g]];
-                    int base_idx = 0;
-                    if (lane == 0) base_idx = atomicAdd(&s_nitems, 1);
-                    base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
-                    if (lane == 0) {
-                        if (base_idx + 1 > Tier::kItems) s_overflow = 1;
-                        else s_item[base_idx] = make_uint2(1u, (uint32_t)g);
-                        s_gbase[g] = (uint16_t)base_idx;
-                    }
+                    const uint32_t d = w[0];
+                    if (lane == 0 && my_items < kPool) s_item[base_idx] = make_uint2(1u, (uint32_t)g);
+                    my_items += 1;
                     s_cell[g * 32 + lane] = (uint8_t)((d >> lane) & 1u);
+                    if (lane == 0) s_gbase[g] = (uint16_t)base_idx;
                     continue;
                 }
-                const uint32_t *w = s_ew + s_goff[g];
                 uint32_t pattern = 0;
 #pragma unroll 4
                 for (int e = a - 1; e >= 0; --e) pattern = (pattern << 1) | ((w[e] >> lane) & 1u);
@@ -419,18 +430,89 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                 const bool leader = (lane == leader_lane) && pattern != 0u;
                 const uint32_t lead_mask = __ballot_sync(0xffffffffu, leader);
                 const int n_lead = __popc(lead_mask);
-                int base_idx = 0;
-                if (lane == 0 && n_lead) base_idx = atomicAdd(&s_nitems, n_lead);
-                base_idx = __shfl_sync(0xffffffffu, base_idx, 0);
                 int local = 1 + __popc(lead_mask & ((1u << lane) - 1u));  // 1-based within the group
-                if (base_idx + n_lead > Tier::kItems) {
-                    if (lane == 0) s_overflow = 1;
-                } else if (leader) {
+                if (leader && my_items + n_lead <= kPool)
                     s_item[base_idx + local - 1] = make_uint2(pattern, (uint32_t)g);
-                }
+                my_items += n_lead;
                 local = __shfl_sync(0xffffffffu, local, leader_lane);
                 s_cell[g * 32 + lane] = (uint8_t)(pattern ? local : 0);
                 if (lane == 0) s_gbase[g] = (uint16_t)base_idx;
+            }
+            if (my_items > kPool) {   // the warp's pool is full: the row goes to the next tier
+                if (lane == 0) s_overflow = 1;
+                my_items = 0;
+            }
+
+            // ---- 3. one dependent-add chain per class, by the warp that found it --------------
+            // The warp takes 32 of its items at a time and walks k in lock step from the
+            // 8-aligned block of their earliest first deviation: a lane that has not deviated
+            // yet adds the baseline terms, i.e. it retraces P[] exactly, so starting every
+            // lane at P[k_start] is the same chain as starting it at P[its own first
+            // deviation].  The deviations of a lane inside the current 32-observation block
+            // are gathered into one mask word up front, which leaves (shared load, bit test,
+            // select, add) per step.
+            if (my_items > 0) {
+                while (*reinterpret_cast<volatile int *>(&s_prefix_ready) == 0) { }
+                __threadfence_block();
+            }
+#pragma unroll 1
+            for (int i0 = 0; i0 < my_items; i0 += 32) {
+                const int it = pool_base + i0 + lane;
+                const bool valid = i0 + lane < my_items;
+                uint32_t rem = 0u;   // bit e: deviates at the group's e-th deviating observation
+                const uint16_t *ek = s_ek;
+                int nk = kNoDev;
+                if (valid) {
+                    const uint2 item = s_item[it];
+                    rem = item.x;
+                    ek = s_ek + s_goff[item.y];
+                    nk = ek[__ffs(rem) - 1];
+                    rem &= rem - 1;
+                }
+                int k = __reduce_min_sync(0xffffffffu, nk) & ~7;   // warp-uniform
+                double acc = s_prefix[k];
+                int cnt = kCounts ? (int)s_pcnt[k] : 0;
+                while (k < n_obs) {
+                    const int kb = k & ~31;
+                    uint32_t word = 0u;   // bit (k' - kb): this lane deviates at observation k'
+                    while (nk < kb + 32) {
+                        word |= 1u << (nk - kb);
+                        nk = rem ? (int)ek[__ffs(rem) - 1] : kNoDev;
+                        rem &= rem - 1;
+                    }
+                    const int k_end = min(kb + 32, n_obs);
+#pragma unroll 1
+                    for (; k + 8 <= k_end; k += 8) {
+                        const uint32_t w8 = word >> (k - kb);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const double2 t = s_term[k + u];
+                            const bool dev = (w8 >> u) & 1u;
+                            acc += dev ? t.y : t.x;
+                            if (kCounts) {
+                                const int bm = (int)s_pcnt[k + u + 1] - (int)s_pcnt[k + u];
+                                cnt += dev ? 1 - bm : bm;
+                            }
+                        }
+                    }
+                    if (k_end == n_obs) {   // the last, partial group of eight
+#pragma unroll 1
+                        for (; k < k_end; ++k) {
+                            const double2 t = s_term[k];
+                            const bool dev = (word >> (k - kb)) & 1u;
+                            acc += dev ? t.y : t.x;
+                            if (kCounts) {
+                                const int bm = (int)s_pcnt[k + 1] - (int)s_pcnt[k];
+                                cnt += dev ? 1 - bm : bm;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();   // every lane has read its item before the slots become values
+                if (valid) {
+                    s_val[it] = acc;
+                    if (kCounts) s_icnt[it] = cnt;
+                }
             }
         }
         __syncthreads();
@@ -443,108 +525,40 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                                                k0, k1, pos_idx, base_code, out_row, match_row,
                                                s_term, s_off);
             }
-            __syncthreads();
+            __syncthreads();  // the row's shared state is reused by the next row
             continue;
         }
 
-        // ---- 3. one dependent-add chain per class ----------------------------------------------
-        const int n_items = s_nitems;
-        if (tid == 0) {
-            s_val[0] = s_prefix[n_obs];
-            if (kCounts) s_icnt[0] = s_pcnt[n_obs];
-        }
-        // A warp takes 32 consecutive items and walks k in lock step from the 8-aligned
-        // block of its earliest first deviation: a lane that has not deviated yet adds the
-        // marker-free terms, i.e. it retraces P[] exactly, so starting every lane at
-        // P[k_start] is the same chain as starting it at P[its own first deviation].  The
-        // deviations of a lane inside the current 32-observation block are gathered into
-        // one mask word up front, which leaves (shared load, bit test, select, add) per step.
-        constexpr int kNoDev = 0x7FFFFFFF;
-#pragma unroll 1
-        for (int it0 = 1 + warp * 32; it0 < n_items; it0 += kClassThreads) {
-            const int it = it0 + lane;
-            uint32_t rem = 0u;   // bit e: deviates at the group's e-th deviating observation
-            const uint16_t *ek = s_ek;
-            int nk = kNoDev;
-            if (it < n_items) {
-                const uint2 item = s_item[it];
-                rem = item.x;
-                ek = s_ek + s_goff[item.y];
-                nk = ek[__ffs(rem) - 1];
-                rem &= rem - 1;
-            }
-            int k = __reduce_min_sync(0xffffffffu, nk) & ~7;   // warp-uniform
-            double acc = s_prefix[k];
-            int cnt = kCounts ? (int)s_pcnt[k] : 0;
-            while (k < n_obs) {
-                const int kb = k & ~31;
-                uint32_t word = 0u;   // bit (k' - kb): this lane deviates at observation k'
-                while (nk < kb + 32) {
-                    word |= 1u << (nk - kb);
-                    nk = rem ? (int)ek[__ffs(rem) - 1] : kNoDev;
-                    rem &= rem - 1;
-                }
-                const int k_end = min(kb + 32, n_obs);
-#pragma unroll 1
-                for (; k + 8 <= k_end; k += 8) {
-                    const uint32_t w8 = word >> (k - kb);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const double2 t = s_term[k + u];
-                        const bool dev = (w8 >> u) & 1u;
-                        acc += dev ? t.y : t.x;
-                        if (kCounts) {
-                            const int bm = (int)s_pcnt[k + u + 1] - (int)s_pcnt[k + u];
-                            cnt += dev ? 1 - bm : bm;
-                        }
-                    }
-                }
-                if (k_end == n_obs) {   // the last, partial group of eight
-#pragma unroll 1
-                    for (; k < k_end; ++k) {
-                        const double2 t = s_term[k];
-                        const bool dev = (word >> (k - kb)) & 1u;
-                        acc += dev ? t.y : t.x;
-                        if (kCounts) {
-                            const int bm = (int)s_pcnt[k + 1] - (int)s_pcnt[k];
-                            cnt += dev ? 1 - bm : bm;
-                        }
-                    }
-                }
-            }
-            if (it < n_items) {
-                s_val[it] = acc;
-                if (kCounts) s_icnt[it] = cnt;
-            }
-        }
         // groups with more than 32 deviating positions: walk the dense table, one warp each
+        if (s_ndense > 0) {   // block-uniform
 #pragma unroll 1
-        for (int g = warp; g < n_groups && s_ndense > 0; g += kClassWarps) {
-            if (s_gbase[g] != kDenseGroup) continue;
-            const int j = g * 32 + lane;
-            double acc = 0.0;
-            int cnt = 0;
-            for (int k = 0; k < n_obs; ++k) {
-                const uint32_t w = __ldg(tb.bits + (size_t)s_plane[k] * tb.n_words + g);
-                const uint32_t d = (w >> lane) & 1u;   // 1 = match
-                const double2 t = s_term[k];
-                const bool bm = s_pcnt[k + 1] != s_pcnt[k];
-                acc += (d != 0) == bm ? t.x : t.y;
-                cnt += d;
-            }
-            if (j < n_hap) {
-                out_row[j] = acc;
-                if (kCounts) match_row[j] = cnt;
+            for (int g = warp; g < n_groups; g += kClassWarps) {
+                if (s_gbase[g] != kDenseGroup) continue;
+                const int j = g * 32 + lane;
+                double acc = 0.0;
+                int cnt = 0;
+                for (int k = 0; k < n_obs; ++k) {
+                    const uint32_t w = __ldg(tb.bits + (size_t)s_plane[k] * tb.n_words + g);
+                    const uint32_t d = (w >> lane) & 1u;   // 1 = match
+                    const double2 t = s_term[k];
+                    const bool bm = s_pcnt[k + 1] != s_pcnt[k];
+                    acc += (d != 0) == bm ? t.x : t.y;
+                    cnt += d;
+                }
+                if (j < n_hap) {
+                    out_row[j] = acc;
+                    if (kCounts) match_row[j] = cnt;
+                }
             }
         }
-        __syncthreads();
 
         // ---- 4. write the row -----------------------------------------------------------------
         if ((n_hap & 1) == 0) {
             for (int j = tid * 2; j < n_hap; j += kClassThreads * 2) {
                 const unsigned gb = s_gbase[j >> 5];
                 if (gb == kDenseGroup) continue;
-                const unsigned c0 = s_cell[j], c1 = s_cell[j + 1];
+                const unsigned cc = *reinterpret_cast<const uint16_t *>(s_cell + j);
+                const unsigned c0 = cc & 0xFFu, c1 = cc >> 8;
                 const unsigned i0 = c0 ? gb + c0 - 1 : 0, i1 = c1 ? gb + c1 - 1 : 0;
                 *reinterpret_cast<double2 *>(out_row + j) = make_double2(s_val[i0], s_val[i1]);
                 if (kCounts)
@@ -562,6 +576,50 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
         }
         __syncthreads();  // the row's shared state is reused by the next row
     }
+}
+
+// One launch of the cascade: rows come from list_in (all rows when NULL), rows that do not
+// fit the tier's pools go to list_out (dense path when NULL: last tier only).
+template <bool kCounts, class Tier, int kMaxGroups>
+static cudaError_t launch_tier(mxb_ctx *ctx, const BuildTables &tb, int64_t n_rows,
+                               const int32_t *list_in, const int *n_in, int32_t *list_out,
+                               int *n_out, int *work_counter, const int64_t *row_ptr,
+                               const int32_t *pos_idx, const uint8_t *base_code, double *out,
+                               int32_t *match_out) {
+    constexpr size_t smem_bytes = BuildSmem<Tier, kMaxGroups, kCounts>::total;
+    auto fn = build_matrix_kernel<kCounts, Tier, kMaxGroups>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes);
+    int per_sm = 0;
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, Tier::kThreads, smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    const int grid = (int)std::min<int64_t>(n_rows, (int64_t)ctx->num_sms * per_sm);
+    fn<<<grid, Tier::kThreads, smem_bytes, ctx->stream>>>(tb, n_rows, list_in, n_in, list_out,
+                                                          n_out, work_counter, row_ptr, pos_idx,
+                                                          base_code, out, match_out);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+// kMaxGroups sizes the group arrays of the shared-memory layout: 176 groups hold
+// Phylotree Build 17 (5408 haplotypes -> 169 groups), 256 groups everything up to 8192.
+constexpr int kGroupsSmall = 176, kGroupsLarge = 256;
+
+template <bool kCounts, class Tier>
+static cudaError_t launch_tier_groups(mxb_ctx *ctx, const BuildTables &tb, int64_t n_rows,
+                                      const int32_t *list_in, const int *n_in, int32_t *list_out,
+                                      int *n_out, int *work_counter, const int64_t *row_ptr,
+                                      const int32_t *pos_idx, const uint8_t *base_code, double *out,
+                                      int32_t *match_out) {
+    if (tb.n_groups <= kGroupsSmall)
+        return launch_tier<kCounts, Tier, kGroupsSmall>(ctx, tb, n_rows, list_in, n_in, list_out,
+                                                        n_out, work_counter, row_ptr, pos_idx,
+                                                        base_code, out, match_out);
+    return launch_tier<kCounts, Tier, kGroupsLarge>(ctx, tb, n_rows, list_in, n_in, list_out, n_out,
+                                                    work_counter, row_ptr, pos_idx, base_code, out,
+                                                    match_out);
 }
 
 }  // namespace mxb
@@ -756,29 +814,16 @@ int mxb_build_matrix(mxb_ctx *ctx, const mxb_phylo *ph, int64_t n_rows,
             // class kernel (two tiers) when its shared-memory layouts fit, else the dense kernel
             const bool counts = d_match != nullptr;
             const int n_groups = (int)ceil_div(ph->n_hap, 32);
-            const BuildSmem lay1(n_groups, counts, Tier1::kEntries, Tier1::kItems, Tier1::kObsWords);
-            const BuildSmem lay2(n_groups, counts, Tier2::kEntries, Tier2::kItems, Tier2::kObsWords);
-            const void *fn1 = counts ? (const void *)build_matrix_kernel<true, Tier1>
-                                     : (const void *)build_matrix_kernel<false, Tier1>;
-            const void *fn2 = counts ? (const void *)build_matrix_kernel<true, Tier2>
-                                     : (const void *)build_matrix_kernel<false, Tier2>;
-            bool use_class = getenv("MXB_BUILD_DENSE") == nullptr &&
-                             lay2.total + 1024 <= ctx->smem_optin && n_rows < ((int64_t)1 << 31);
-            int per_sm1 = 0, per_sm2 = 0;
+            const bool use_class = getenv("MXB_BUILD_DENSE") == nullptr &&
+                                   n_groups <= kGroupsLarge && n_rows < ((int64_t)1 << 31);
+            // MXB_BUILD_TIERS=2 skips tier 1 (cross-check of the large-pool launch)
+            const char *tiers_env = getenv("MXB_BUILD_TIERS");
+            const bool two_tiers = !(tiers_env && strcmp(tiers_env, "2") == 0);
             if (use_class) {
-                STEP(cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)lay1.total));
-                STEP(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)lay2.total));
-                STEP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fn1, Tier1::kThreads,
-                                                                   lay1.total));
-                STEP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, fn2, Tier2::kThreads,
-                                                                   lay2.total));
-                if (e == cudaSuccess && (per_sm1 < 1 || per_sm2 < 1)) use_class = false;
-            }
-            if (use_class) {
-                STEP(cudaMalloc(&d_overflow, (n_rows + 1) * sizeof(int32_t)));
-                STEP(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), ctx->stream));
+                // d_overflow[0] = number of rows deferred to tier 2, [1], [2] = the work counters
+                // of the two launches, [3..] = the deferred rows
+                STEP(cudaMalloc(&d_overflow, (n_rows + 3) * sizeof(int32_t)));
+                STEP(cudaMemsetAsync(d_overflow, 0, 3 * sizeof(int32_t), ctx->stream));
             }
             STEP(cudaEventRecord(ev0, ctx->stream));
             if (e == cudaSuccess && use_class) {
@@ -792,27 +837,28 @@ int mxb_build_matrix(mxb_ctx *ctx, const mxb_phylo *ph, int64_t n_rows,
                 tb.n_words = ph->n_words;
                 tb.n_hap = ph->n_hap;
                 tb.n_groups = n_groups;
-                // d_overflow[0] = number of rows deferred to tier 2, d_overflow[1..] = the rows
                 int *ov_count = reinterpret_cast<int *>(d_overflow);
-                int32_t *ov_list = d_overflow + 1;
-                const int grid1 = (int)std::min<int64_t>(n_rows, (int64_t)ctx->num_sms * per_sm1);
-                const int grid2 = (int)std::min<int64_t>(n_rows, (int64_t)ctx->num_sms * per_sm2);
-                if (counts) {
-                    build_matrix_kernel<true, Tier1><<<grid1, Tier1::kThreads, lay1.total, ctx->stream>>>(
-                        tb, n_rows, nullptr, nullptr, ov_list, ov_count, d_row_ptr, d_pos, d_code,
-                        m->data, d_match);
-                    build_matrix_kernel<true, Tier2><<<grid2, Tier2::kThreads, lay2.total, ctx->stream>>>(
-                        tb, n_rows, ov_list, ov_count, nullptr, nullptr, d_row_ptr, d_pos, d_code,
-                        m->data, d_match);
-                } else {
-                    build_matrix_kernel<false, Tier1><<<grid1, Tier1::kThreads, lay1.total, ctx->stream>>>(
-                        tb, n_rows, nullptr, nullptr, ov_list, ov_count, d_row_ptr, d_pos, d_code,
-                        m->data, d_match);
-                    build_matrix_kernel<false, Tier2><<<grid2, Tier2::kThreads, lay2.total, ctx->stream>>>(
-                        tb, n_rows, ov_list, ov_count, nullptr, nullptr, d_row_ptr, d_pos, d_code,
-                        m->data, d_match);
+                int32_t *ov_list = d_overflow + 3;
+                if (two_tiers) {
+                    e = counts ? launch_tier_groups<true, Tier1>(ctx, tb, n_rows, nullptr, nullptr,
+                                                                 ov_list, ov_count, ov_count + 1,
+                                                                 d_row_ptr, d_pos, d_code, m->data,
+                                                                 d_match)
+                               : launch_tier_groups<false, Tier1>(ctx, tb, n_rows, nullptr, nullptr,
+                                                                  ov_list, ov_count, ov_count + 1,
+                                                                  d_row_ptr, d_pos, d_code, m->data,
+                                                                  d_match);
                 }
-                ctx->launches++;
+                const int32_t *in2 = two_tiers ? ov_list : nullptr;
+                const int *n_in2 = two_tiers ? ov_count : nullptr;
+                if (e == cudaSuccess)
+                    e = counts ? launch_tier_groups<true, Tier2>(ctx, tb, n_rows, in2, n_in2, nullptr,
+                                                                 nullptr, ov_count + 2, d_row_ptr,
+                                                                 d_pos, d_code, m->data, d_match)
+                               : launch_tier_groups<false, Tier2>(ctx, tb, n_rows, in2, n_in2, nullptr,
+                                                                  nullptr, ov_count + 2, d_row_ptr,
+                                                                  d_pos, d_code, m->data, d_match);
+                ctx->launches--;  // counted once more below
             } else if (e == cudaSuccess) {
                 const int grid = (int)std::min<int64_t>(n_rows, (int64_t)ctx->num_sms * 4);
                 build_matrix_dense_kernel<<<grid, kBuildThreads, 0, ctx->stream>>>(
