@@ -168,7 +168,8 @@ struct BuildTables {
 };
 
 constexpr int kMaxObs = 512;         // observations per row (longer rows: dense path)
-constexpr unsigned kDenseGroup = 0xFFFFu;
+constexpr unsigned kDenseGroup = 0xFFFFu;   // s_gbase marker: group walked densely
+constexpr unsigned kEmptyGroup = 0xFFFEu;   // s_gbase marker: no deviation, every cell in class 0
 static_assert(kMaxObs == kBuildObsChunk, "the dense row path reuses the class kernel's staging area");
 
 // Pool sizes of the launches: tier 1 serves the common rows at 5 CTAs/SM, tier 2 re-runs
@@ -200,7 +201,8 @@ struct BuildSmem {
     static constexpr size_t ek = icnt + (kCounts ? sizeof(int) * Tier::kItems : 0);  // entry pool: k
     static constexpr size_t pcnt = ek + sizeof(uint16_t) * Tier::kEntries;  // baseline match prefix
     static constexpr size_t gbase = pcnt + sizeof(uint16_t) * (kObs + 2);   // first item of the group
-    static constexpr size_t cell = gbase + sizeof(uint16_t) * kMaxGroups;   // class of the cell in its group
+    static constexpr size_t glist = gbase + sizeof(uint16_t) * kMaxGroups;  // groups with entries
+    static constexpr size_t cell = (glist + sizeof(uint16_t) * kMaxGroups + 3) & ~(size_t)3;  // class of the cell in its group
     static constexpr size_t total = (cell + (size_t)kMaxGroups * 32 + 15) & ~(size_t)15;
 };
 
@@ -209,6 +211,105 @@ struct BuildSmem {
 template <int kWorkThreads>
 __device__ __forceinline__ void work_warps_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");
+}
+
+// Dependent-add chains of up to 32 (64 with kDual) chain items starting at s_item[first]:
+// lane l evaluates item first + l (and first + 32 + l).  The warp walks k in lock step from
+// the 8-aligned block of the earliest first deviation among its items: a lane that has not
+// deviated yet adds the baseline terms, i.e. it retraces P[] exactly, so starting every
+// lane at P[k_start] is the same chain as starting it at P[its own first deviation].  The
+// deviations of an item inside the current 32-observation block are gathered into one mask
+// word up front, which leaves (shared load, bit test, select, add) per step.
+template <bool kCounts, bool kDual>
+__device__ __forceinline__ void run_chains(int first, int n_left, int lane, int n_obs,
+                                           uint2 *s_item, double *s_val, int *s_icnt,
+                                           const uint16_t *s_ek, const int *s_goff,
+                                           const double2 *s_term, const double *s_prefix,
+                                           const uint16_t *s_pcnt) {
+    constexpr int kNoDev = 0x7FFFFFFF;
+    constexpr int kChains = kDual ? 2 : 1;
+    uint32_t rem[kChains];   // bit e: deviates at the group's e-th deviating observation
+    int ek[kChains];         // pool offset of the group's entries
+    int nk[kChains];         // next deviating observation
+    bool valid[kChains];
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) {
+        valid[c] = c * 32 + lane < n_left;
+        rem[c] = 0u;
+        ek[c] = 0;
+        nk[c] = kNoDev;
+        if (valid[c]) {
+            const uint2 item = s_item[first + c * 32 + lane];
+            rem[c] = item.x;
+            ek[c] = s_goff[item.y];
+            nk[c] = s_ek[ek[c] + __ffs(rem[c]) - 1];
+            rem[c] &= rem[c] - 1;
+        }
+    }
+    int k = __reduce_min_sync(0xffffffffu, kDual ? min(nk[0], nk[kChains - 1]) : nk[0]) & ~7;
+    double acc[kChains];
+    int cnt[kChains];
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) {
+        acc[c] = s_prefix[k];
+        cnt[c] = kCounts ? (int)s_pcnt[k] : 0;
+    }
+    while (k < n_obs) {   // warp-uniform
+        const int kb = k & ~31;
+        uint32_t word[kChains];   // bit (k' - kb): the item deviates at observation k'
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) {
+            word[c] = 0u;
+            while (nk[c] < kb + 32) {
+                word[c] |= 1u << (nk[c] - kb);
+                nk[c] = rem[c] ? (int)s_ek[ek[c] + __ffs(rem[c]) - 1] : kNoDev;
+                rem[c] &= rem[c] - 1;
+            }
+        }
+        const int k_end = min(kb + 32, n_obs);
+#pragma unroll 1
+        for (; k + 8 <= k_end; k += 8) {
+            uint32_t w8[kChains];
+#pragma unroll
+            for (int c = 0; c < kChains; ++c) w8[c] = word[c] >> (k - kb);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double2 t = s_term[k + u];
+#pragma unroll
+                for (int c = 0; c < kChains; ++c) {
+                    const bool dev = (w8[c] >> u) & 1u;
+                    acc[c] += dev ? t.y : t.x;
+                    if (kCounts) {
+                        const int bm = (int)s_pcnt[k + u + 1] - (int)s_pcnt[k + u];
+                        cnt[c] += dev ? 1 - bm : bm;
+                    }
+                }
+            }
+        }
+        if (k_end == n_obs) {   // the last, partial group of eight
+#pragma unroll 1
+            for (; k < k_end; ++k) {
+                const double2 t = s_term[k];
+#pragma unroll
+                for (int c = 0; c < kChains; ++c) {
+                    const bool dev = (word[c] >> (k - kb)) & 1u;
+                    acc[c] += dev ? t.y : t.x;
+                    if (kCounts) {
+                        const int bm = (int)s_pcnt[k + 1] - (int)s_pcnt[k];
+                        cnt[c] += dev ? 1 - bm : bm;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();   // every lane has read its items before the slots become values
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) {
+        if (valid[c]) {
+            s_val[first + c * 32 + lane] = acc[c];
+            if (kCounts) s_icnt[first + c * 32 + lane] = cnt[c];
+        }
+    }
 }
 
 // Rows come from row_list[0 .. *n_list) when row_list != NULL, else 0 .. n_rows.
@@ -227,6 +328,7 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
     __shared__ int s_overflow;
     __shared__ int s_ndense;
     __shared__ int s_prefix_ready;
+    __shared__ int s_nlist;
     using L = BuildSmem<Tier, kMaxGroups, kCounts>;
     constexpr int W = Tier::kObsWords;
     constexpr int kClassThreads = Tier::kThreads;
@@ -248,6 +350,7 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
     uint16_t *s_ek = reinterpret_cast<uint16_t *>(smem + L::ek);
     uint16_t *s_pcnt = reinterpret_cast<uint16_t *>(smem + L::pcnt);
     uint16_t *s_gbase = reinterpret_cast<uint16_t *>(smem + L::gbase);
+    uint16_t *s_glist = reinterpret_cast<uint16_t *>(smem + L::glist);
     uint8_t *s_cell = reinterpret_cast<uint8_t *>(smem + L::cell);
     // the dense row path reuses the staging areas: (hit, miss) and plane offsets
     uint32_t *s_off = reinterpret_cast<uint32_t *>(smem + L::ew);
@@ -258,7 +361,6 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
     const int n_hap = tb.n_hap;
     const int n_groups = tb.n_groups;
     const int64_t n_work = row_list ? (int64_t)*n_list : n_rows;
-    constexpr int kNoDev = 0x7FFFFFFF;
 
     // Rows cost between 0.2x and 10x the average: after its first row a CTA takes rows from
     // a device-wide counter.  The next index is fetched while the current row is processed
@@ -344,8 +446,8 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                 }
             }
             work_warps_sync<kWorkWarps * 32>();
-            if (warp == 0) {  // entries per group and their exclusive scan
-                int carry = 0;
+            if (warp == 0) {  // entries per group, their exclusive scan, list of the groups with any
+                int carry = 0, n_list = 0;
                 for (int g0 = 0; g0 < n_groups; g0 += 32) {
                     const int g = g0 + lane;
                     int c = 0;
@@ -353,7 +455,11 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
 #pragma unroll
                         for (int w = 0; w < W; ++w) c += __popc(s_gmap[g * W + w]);
                         s_gcnt[g] = c;
+                        if (c == 0) s_gbase[g] = (uint16_t)kEmptyGroup;
                     }
+                    const uint32_t some = __ballot_sync(0xffffffffu, c > 0);
+                    if (c > 0) s_glist[n_list + __popc(some & ((1u << lane) - 1u))] = (uint16_t)g;
+                    n_list += __popc(some);
                     int incl = c;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -363,7 +469,10 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                     if (g < n_groups) s_goff[g] = carry + incl - c;
                     carry += __shfl_sync(0xffffffffu, incl, 31);
                 }
-                if (lane == 0 && carry > Tier::kEntries) s_overflow = 1;
+                if (lane == 0) {
+                    s_nlist = n_list;
+                    if (carry > Tier::kEntries) s_overflow = 1;
+                }
             }
             work_warps_sync<kWorkWarps * 32>();
             // read once, before any warp can raise the flag again: the branch and the
@@ -400,14 +509,11 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
             // ---- 2. classes of every 32-column group ------------------------------------------
             const int pool_base = 1 + warp * kPool;
             int my_items = 0;       // warp-uniform; items past kPool are counted but not stored
+            const int n_list = too_many_entries ? 0 : s_nlist;
 #pragma unroll 1
-            for (int g = warp; g < n_groups && !too_many_entries; g += kWorkWarps) {
+            for (int gi = warp; gi < n_list; gi += kWorkWarps) {
+                const int g = s_glist[gi];
                 const int a = s_gcnt[g];
-                if (a == 0) {
-                    s_cell[g * 32 + lane] = 0;
-                    if (lane == 0) s_gbase[g] = 0;
-                    continue;
-                }
                 if (a > 32) {  // handled after the prefix pass
                     if (lane == 0) { s_gbase[g] = (uint16_t)kDenseGroup; atomicAdd(&s_ndense, 1); }
                     continue;
@@ -422,9 +528,17 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                     if (lane == 0) s_gbase[g] = (uint16_t)base_idx;
                     continue;
                 }
-                uint32_t pattern = 0;
+                uint32_t pattern;   // bit e: this lane's column deviates at the group's e-th entry
+                if (a <= 4) {       // nine groups in ten
+                    const uint32_t w0 = w[0], w1 = w[1];
+                    pattern = ((w0 >> lane) & 1u) | (((w1 >> lane) & 1u) << 1);
+                    if (a > 2) pattern |= ((w[2] >> lane) & 1u) << 2;
+                    if (a > 3) pattern |= ((w[3] >> lane) & 1u) << 3;
+                } else {
+                    pattern = 0;
 #pragma unroll 4
-                for (int e = a - 1; e >= 0; --e) pattern = (pattern << 1) | ((w[e] >> lane) & 1u);
+                    for (int e = a - 1; e >= 0; --e) pattern = (pattern << 1) | ((w[e] >> lane) & 1u);
+                }
                 const uint32_t peers = __match_any_sync(0xffffffffu, pattern);
                 const int leader_lane = __ffs(peers) - 1;
                 const bool leader = (lane == leader_lane) && pattern != 0u;
@@ -443,77 +557,21 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                 my_items = 0;
             }
 
-            // ---- 3. one dependent-add chain per class, by the warp that found it --------------
-            // The warp takes 32 of its items at a time and walks k in lock step from the
-            // 8-aligned block of their earliest first deviation: a lane that has not deviated
-            // yet adds the baseline terms, i.e. it retraces P[] exactly, so starting every
-            // lane at P[k_start] is the same chain as starting it at P[its own first
-            // deviation].  The deviations of a lane inside the current 32-observation block
-            // are gathered into one mask word up front, which leaves (shared load, bit test,
-            // select, add) per step.
+            // ---- 3. one dependent-add chain per class, by the warp that found it (run_chains)
             if (my_items > 0) {
                 while (*reinterpret_cast<volatile int *>(&s_prefix_ready) == 0) { }
                 __threadfence_block();
             }
+            // 64 items at a time (two independent chains per lane share every term load)
+            // while the warp has more than 32 left, then one chain per lane
+            int i0 = 0;
 #pragma unroll 1
-            for (int i0 = 0; i0 < my_items; i0 += 32) {
-                const int it = pool_base + i0 + lane;
-                const bool valid = i0 + lane < my_items;
-                uint32_t rem = 0u;   // bit e: deviates at the group's e-th deviating observation
-                const uint16_t *ek = s_ek;
-                int nk = kNoDev;
-                if (valid) {
-                    const uint2 item = s_item[it];
-                    rem = item.x;
-                    ek = s_ek + s_goff[item.y];
-                    nk = ek[__ffs(rem) - 1];
-                    rem &= rem - 1;
-                }
-                int k = __reduce_min_sync(0xffffffffu, nk) & ~7;   // warp-uniform
-                double acc = s_prefix[k];
-                int cnt = kCounts ? (int)s_pcnt[k] : 0;
-                while (k < n_obs) {
-                    const int kb = k & ~31;
-                    uint32_t word = 0u;   // bit (k' - kb): this lane deviates at observation k'
-                    while (nk < kb + 32) {
-                        word |= 1u << (nk - kb);
-                        nk = rem ? (int)ek[__ffs(rem) - 1] : kNoDev;
-                        rem &= rem - 1;
-                    }
-                    const int k_end = min(kb + 32, n_obs);
-#pragma unroll 1
-                    for (; k + 8 <= k_end; k += 8) {
-                        const uint32_t w8 = word >> (k - kb);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const double2 t = s_term[k + u];
-                            const bool dev = (w8 >> u) & 1u;
-                            acc += dev ? t.y : t.x;
-                            if (kCounts) {
-                                const int bm = (int)s_pcnt[k + u + 1] - (int)s_pcnt[k + u];
-                                cnt += dev ? 1 - bm : bm;
-                            }
-                        }
-                    }
-                    if (k_end == n_obs) {   // the last, partial group of eight
-#pragma unroll 1
-                        for (; k < k_end; ++k) {
-                            const double2 t = s_term[k];
-                            const bool dev = (word >> (k - kb)) & 1u;
-                            acc += dev ? t.y : t.x;
-                            if (kCounts) {
-                                const int bm = (int)s_pcnt[k + 1] - (int)s_pcnt[k];
-                                cnt += dev ? 1 - bm : bm;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();   // every lane has read its item before the slots become values
-                if (valid) {
-                    s_val[it] = acc;
-                    if (kCounts) s_icnt[it] = cnt;
-                }
-            }
+            for (; my_items - i0 > 32; i0 += 64)
+                run_chains<kCounts, true>(pool_base + i0, my_items - i0, lane, n_obs, s_item, s_val,
+                                          s_icnt, s_ek, s_goff, s_term, s_prefix, s_pcnt);
+            if (i0 < my_items)
+                run_chains<kCounts, false>(pool_base + i0, my_items - i0, lane, n_obs, s_item, s_val,
+                                           s_icnt, s_ek, s_goff, s_term, s_prefix, s_pcnt);
         }
         __syncthreads();
         }  // !too_long
@@ -553,22 +611,28 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
         }
 
         // ---- 4. write the row -----------------------------------------------------------------
-        if ((n_hap & 1) == 0) {
-            for (int j = tid * 2; j < n_hap; j += kClassThreads * 2) {
+        if ((n_hap & 3) == 0) {   // four cells per thread: one group, one 32-bit load of the classes
+            for (int j = tid * 4; j < n_hap; j += kClassThreads * 4) {
                 const unsigned gb = s_gbase[j >> 5];
                 if (gb == kDenseGroup) continue;
-                const unsigned cc = *reinterpret_cast<const uint16_t *>(s_cell + j);
-                const unsigned c0 = cc & 0xFFu, c1 = cc >> 8;
-                const unsigned i0 = c0 ? gb + c0 - 1 : 0, i1 = c1 ? gb + c1 - 1 : 0;
-                *reinterpret_cast<double2 *>(out_row + j) = make_double2(s_val[i0], s_val[i1]);
+                const unsigned cc = gb == kEmptyGroup ? 0u : *reinterpret_cast<const uint32_t *>(s_cell + j);
+                unsigned idx[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned c = (cc >> (8 * u)) & 0xFFu;
+                    idx[u] = c ? gb + c - 1 : 0;
+                }
+                *reinterpret_cast<double2 *>(out_row + j) = make_double2(s_val[idx[0]], s_val[idx[1]]);
+                *reinterpret_cast<double2 *>(out_row + j + 2) = make_double2(s_val[idx[2]], s_val[idx[3]]);
                 if (kCounts)
-                    *reinterpret_cast<int2 *>(match_row + j) = make_int2(s_icnt[i0], s_icnt[i1]);
+                    *reinterpret_cast<int4 *>(match_row + j) =
+                        make_int4(s_icnt[idx[0]], s_icnt[idx[1]], s_icnt[idx[2]], s_icnt[idx[3]]);
             }
         } else {
             for (int j = tid; j < n_hap; j += kClassThreads) {
                 const unsigned gb = s_gbase[j >> 5];
                 if (gb == kDenseGroup) continue;
-                const unsigned c0 = s_cell[j];
+                const unsigned c0 = gb == kEmptyGroup ? 0u : s_cell[j];
                 const unsigned i0 = c0 ? gb + c0 - 1 : 0;
                 out_row[j] = s_val[i0];
                 if (kCounts) match_row[j] = s_icnt[i0];
