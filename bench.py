@@ -378,6 +378,11 @@ def run_b200(opts):
                                                   want_host=False, keep_device=True)
             swts = mix0.weights.astype(np.float64)
         sn = smat.shape[0]
+        # one short untimed call first (first-use costs of the restart path: result blocks,
+        # pinned polling scratch), like the warm-up steps of the kernel leg
+        wargs = argparse.Namespace(**vars(sargs))
+        wargs.max_iter, wargs.n_multi = 3, 2 * world
+        b200_em.run_em_device(smat, swts, wargs, want_host=False, inits=inits[:2 * world])
         for mode in ("two_per_pass", "one_per_pass") if world == 1 else ("two_per_pass",):
             if mode == "one_per_pass":
                 os.environ["MXB_EM_NO_BATCH"] = "1"

@@ -10,12 +10,13 @@
 // or the reference base when it carries none: preprocess.py:75-83).  A 32-bit
 // word is a ready-made ballot over 32 haplotypes for one observed
 // (position, base); plane n_sym is all zero and serves bases that can never
-// match.  99 % of the expected bases are the reference base, so the table is
+// match.  Nearly all haplotypes agree on the outcome of a plane, so the table is
 // also kept in *sparse deviation* form: for plane (p, a) the list of
-// (word index g, D) with D = bits[p][a][g] XOR (a == ref[p] ? all ones : 0)
-// != 0, i.e. the haplotypes whose match/mismatch outcome differs from that of
-// a marker-free haplotype.  Build 17: 4070 x 5 x 172 dense words (14 MB) against
-// ~0.3 M sparse entries.
+// (word index g, D) with D = bits[p][a][g] XOR (baseline ? all ones : 0) != 0,
+// where the baseline outcome of the plane is the one the majority of the
+// haplotypes has (the marker-free outcome a == ref[p], except for the few dozen
+// planes whose derived allele is carried by more than half of the tree).
+// Build 17: 4070 x 5 x 172 dense words (14 MB) against ~0.3 M sparse entries.
 //
 // Bit-exactness.  A cell is the fp64 sum, in signature order, of hit[p] on a
 // match and miss[p] on a mismatch -- the same values in the same order as the
@@ -23,39 +24,45 @@
 // not associative, so the K terms of a cell cannot be re-grouped; what can be
 // shared is whole chains: two haplotypes with the same match pattern over the
 // row's K positions get the same sum, and a chain whose first deviation from
-// the marker-free pattern is at k0 may start from the marker-free prefix sum
-// P[k0] (the same additions in the same order).  A 300 bp fragment separates
-// the 5408 Build-17 haplotypes into only ~450 (32-column group, pattern)
-// classes, so the class kernel evaluates ~12x fewer dependent-add chains than
-// cells, each about half as long.
+// the baseline pattern is at k0 may start from the baseline prefix sum P[k0]
+// (the same additions in the same order).  A 300 bp fragment separates the 5408
+// Build-17 haplotypes into only ~300 (32-column group, pattern) classes, so the
+// class kernel evaluates ~15x fewer dependent-add chains than cells.
 //
-// build_matrix_kernel (class kernel), one CTA per row at a time:
-//   0. stage the row: per observation k the (marker-free, deviating) term pair,
-//      its (position, symbol) plane and whether the marker-free outcome matches;
-//   1. the last warp forms the marker-free prefix sums P[0..K] (one dependent
+// build_matrix_kernel (class kernel), one CTA per row at a time, rows handed
+// out by a device-wide counter (they cost 0.2x .. 10x the average):
+//   0. stage the row: per observation k the (baseline, deviating) term pair,
+//      its (position, symbol) plane and whether the baseline outcome matches;
+//   1. the last warp forms the baseline prefix sums P[0..K] (one dependent
 //      chain) while the other warps collect the row's deviation entries per
 //      32-column group: a first walk over the sparse lists sets bit k in the
 //      group's observation bitmap (shared-memory atomicOr), a scan of the
-//      popcounts sizes the groups, and a second walk drops every (k, D) at
-//      offset[group] + rank of k in the bitmap -- sorted by k without a sort;
-//   2. one warp per group: every lane reads its pattern over the group's
-//      entries (bit e = "deviates at the e-th deviating observation"),
-//      match.any finds the distinct patterns and one chain item is allocated
-//      per distinct non-empty pattern; a cell remembers its class within the group;
-//   3. one thread per chain item: start at P[k0] of the first deviation, add the
-//      remaining terms in order, taking the deviating term where the pattern
-//      says so (next set bit = next deviating observation);
+//      popcounts sizes the groups and lists the non-empty ones, and a second
+//      walk drops every (k, D) at offset[group] + rank of k in the bitmap --
+//      sorted by k without a sort;
+//   2. one warp per non-empty group: every lane reads its pattern over the
+//      group's entries (bit e = "deviates at the e-th deviating observation";
+//      straight-line code for up to four entries, no cross-lane work for one),
+//      match.any finds the distinct patterns and one chain item is taken from
+//      the warp's own item pool per distinct non-empty pattern (no atomics); a
+//      cell remembers its class within the group;
+//   3. the same warp evaluates its items (run_chains): 32 or 64 items walk k in
+//      lock step from the earliest first deviation among them -- a lane that has
+//      not deviated yet retraces P[] -- with the deviations of each 32-observation
+//      block gathered into a mask word up front, so a step is (shared load, bit
+//      test, select, add), and two chains per lane share every load;
 //   4. every cell looks up the value of its class and the row is written with
-//      coalesced 16-byte stores.
-// Two launches share the code: tier 1 (256 threads, 38 KB of shared memory, 5
-// CTAs per SM) takes rows with <= 256 observations, <= 1536 deviation entries
-// and <= 1024 chains (94 % of the config-2 rows); rows beyond that are queued
-// on the device and re-run by tier 2 (512 threads, 8192 entries, 4096 chains).
+//      coalesced 16-byte stores, four cells per thread.
+// The shared-memory layout is a compile-time constant (BuildSmem: group arrays
+// sized for 176 or 256 groups), so addresses are immediates.  Two launches share
+// the code: tier 1 (256 threads, 38 KB of shared memory, 5 CTAs per SM) takes rows
+// with <= 256 observations, <= 1536 deviation entries and <= 146 chains per warp
+// (93 % of the config-2 rows); rows beyond that are queued on the device and
+// re-run by tier 2 (512 threads, 8064 entries, 273 chains per warp).
 // What exceeds tier 2 as well (K > 512, or a group with more than 32 deviating
 // observations) walks the dense bitset table cell by cell: build_dense_row /
 // the per-group dense loop, the same arithmetic as build_matrix_dense_kernel,
-// the plain kernel that is also used when H is too large for the class
-// kernel's shared-memory layout (or MXB_BUILD_DENSE=1 is set).
+// the plain kernel that is also used when H > 8192 (or MXB_BUILD_DENSE=1 is set).
 #include <new>
 #include <string.h>
 #include <vector>
@@ -213,6 +220,29 @@ __device__ __forceinline__ void work_warps_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");
 }
 
+// mbarrier through which the prefix warp releases P[] to the warps that evaluate chains
+// (one arrival per row; the waiters track the phase parity).
+__device__ __forceinline__ uint32_t bar_addr(const uint64_t *bar) {
+    return (uint32_t)__cvta_generic_to_shared(bar);
+}
+__device__ __forceinline__ void bar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar_addr(bar)), "r"(parity)
+        : "memory");
+}
+
 // Dependent-add chains of up to 32 (64 with kDual) chain items starting at s_item[first]:
 // lane l evaluates item first + l (and first + 32 + l).  The warp walks k in lock step from
 // the 8-aligned block of the earliest first deviation among its items: a lane that has not
@@ -327,7 +357,7 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
     __shared__ int s_next[2];
     __shared__ int s_overflow;
     __shared__ int s_ndense;
-    __shared__ int s_prefix_ready;
+    __shared__ __align__(8) uint64_t s_prefix_bar;   // completes once per row: P[] is written
     __shared__ int s_nlist;
     using L = BuildSmem<Tier, kMaxGroups, kCounts>;
     constexpr int W = Tier::kObsWords;
@@ -361,6 +391,12 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
     const int n_hap = tb.n_hap;
     const int n_groups = tb.n_groups;
     const int64_t n_work = row_list ? (int64_t)*n_list : n_rows;
+    if (tid == 0) {
+        bar_init(&s_prefix_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t prefix_parity = 0;   // block-uniform: phase of s_prefix_bar the current row completes
+    __syncthreads();
 
     // Rows cost between 0.2x and 10x the average: after its first row a CTA takes rows from
     // a device-wide counter.  The next index is fetched while the current row is processed
@@ -390,7 +426,7 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
             s_pcnt[k + 1] = base_match ? 1 : 0;
         }
         for (int i = tid; i < n_groups * W; i += kClassThreads) s_gmap[i] = 0u;
-        if (tid == 0) { s_overflow = 0; s_ndense = 0; s_prefix_ready = 0; }
+        if (tid == 0) { s_overflow = 0; s_ndense = 0; }
         __syncthreads();
 
         if (warp == kWorkWarps) {
@@ -422,8 +458,7 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                 }
                 s_val[0] = acc;   // class 0: the baseline pattern
                 if (kCounts) s_icnt[0] = cnt;
-                __threadfence_block();
-                *reinterpret_cast<volatile int *>(&s_prefix_ready) = 1;
+                bar_arrive(&s_prefix_bar);
             }
         } else {
             // ---- 1. deviation entries of the row, grouped by 32-column group ------------------
@@ -558,10 +593,8 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
             }
 
             // ---- 3. one dependent-add chain per class, by the warp that found it (run_chains)
-            if (my_items > 0) {
-                while (*reinterpret_cast<volatile int *>(&s_prefix_ready) == 0) { }
-                __threadfence_block();
-            }
+            __syncwarp();   // the warp's items are visible to all of its lanes
+            bar_wait(&s_prefix_bar, prefix_parity);   // P[] is complete (every phase is waited on)
             // 64 items at a time (two independent chains per lane share every term load)
             // while the warp has more than 32 left, then one chain per lane
             int i0 = 0;
@@ -574,6 +607,7 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                                            s_icnt, s_ek, s_goff, s_term, s_prefix, s_pcnt);
         }
         __syncthreads();
+        prefix_parity ^= 1u;
         }  // !too_long
         if (too_long || s_overflow) {  // block-uniform: the row does not fit this tier's pools
             if (overflow_list) {
