@@ -445,6 +445,24 @@ def run_b200(opts):
         del host, read_mix
     dmat.free()
 
+    # ---- e2e of kernel 1: the drop-in build_em_matrix(signature strings) -> host ndarray ----
+    build_e2e = None
+    if not opts.no_e2e and world == 1 and opts.rows == 0:
+        _, _, smix = load_workload(opts.fragments, opts.seed, strings=True)
+        bargs = argparse.Namespace(verbose=False)
+        mixemt_b200.build_em_matrix(phylo.refseq, phylo, smix.signatures[:2000], haps, bargs)
+        barrier()
+        t0 = time.perf_counter()
+        mat = mixemt_b200.build_em_matrix(phylo.refseq, phylo, smix.signatures, haps, bargs)
+        barrier()
+        dt = time.perf_counter() - t0
+        build_e2e = {"seconds": dt, "cells_per_s": mat.size / dt, "d2h_bytes": mat.nbytes,
+                     "call": "mixemt_b200.build_em_matrix(refseq, phylo, %d signature strings, "
+                             "%d haplogroups, args) -> host ndarray: table packing, string "
+                             "parsing, kernel 1 and the %.2f GB device->host copy inside"
+                             % (len(smix.signatures), h, mat.nbytes / 1e9)}
+        del mat
+
     cpu = None
     if rank == 0 and world == 1 and not opts.no_cpu:
         try:
@@ -471,7 +489,8 @@ def run_b200(opts):
                 "gpu_launches": int(launches), "clocks": clocks.summary(),
                 "build": {"ms": build_best, "cells_per_s": float(n) * h / (build_best / 1e3),
                           "write_GBs": float(n) * h * 8 / (build_best / 1e3) / 1e9,
-                          "frac_of_hbm_peak": float(n) * h * 8 / (build_best / 1e3) / 1e9 / peak},
+                          "frac_of_hbm_peak": float(n) * h * 8 / (build_best / 1e3) / 1e9 / peak,
+                          "e2e": build_e2e},
                 "versions": {"numpy": np.__version__, "torch": torch.__version__}}
         print(json.dumps(line))
     if world > 1:

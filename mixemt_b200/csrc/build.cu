@@ -564,16 +564,28 @@ build_matrix_kernel(BuildTables tb, int64_t n_rows, const int32_t *__restrict__ 
                     continue;
                 }
                 uint32_t pattern;   // bit e: this lane's column deviates at the group's e-th entry
-                if (a <= 4) {       // nine groups in ten
+                if (a <= 5) {       // nineteen groups in twenty: patterns are numbers below 32
                     const uint32_t w0 = w[0], w1 = w[1];
                     pattern = ((w0 >> lane) & 1u) | (((w1 >> lane) & 1u) << 1);
                     if (a > 2) pattern |= ((w[2] >> lane) & 1u) << 2;
                     if (a > 3) pattern |= ((w[3] >> lane) & 1u) << 3;
-                } else {
-                    pattern = 0;
-#pragma unroll 4
-                    for (int e = a - 1; e >= 0; --e) pattern = (pattern << 1) | ((w[e] >> lane) & 1u);
+                    if (a > 4) pattern |= ((w[4] >> lane) & 1u) << 4;
+                    // the set of patterns present in the group, as a bitmap: classes are numbered
+                    // by pattern value, and lane p stores the item of pattern p
+                    const uint32_t present = __reduce_or_sync(0xffffffffu, 1u << pattern) & ~1u;
+                    const int n_lead = __popc(present);
+                    if (((present >> lane) & 1u) && my_items + n_lead <= kPool)
+                        s_item[base_idx + __popc(present & ((1u << lane) - 1u))] =
+                            make_uint2((uint32_t)lane, (uint32_t)g);
+                    my_items += n_lead;
+                    s_cell[g * 32 + lane] =
+                        (uint8_t)(pattern ? 1 + __popc(present & ((1u << pattern) - 1u)) : 0);
+                    if (lane == 0) s_gbase[g] = (uint16_t)base_idx;
+                    continue;
                 }
+                pattern = 0;
+#pragma unroll 4
+                for (int e = a - 1; e >= 0; --e) pattern = (pattern << 1) | ((w[e] >> lane) & 1u);
                 const uint32_t peers = __match_any_sync(0xffffffffu, pattern);
                 const int leader_lane = __ffs(peers) - 1;
                 const bool leader = (lane == leader_lane) && pattern != 0u;
