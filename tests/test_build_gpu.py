@@ -80,8 +80,10 @@ def test_build17_vs_oracle_counts_and_values(phylo17):
     assert ms > 0.0 and votes.sum() == mix.weights.sum()
 
 
+# 6000 haplotypes: the 256-group shared-memory layout of the class kernel; 8300: more than its
+# 8192 columns, i.e. the dense kernel
 @pytest.mark.parametrize("n_hap,n_pos", [(1, 5), (31, 40), (33, 64), (1024, 100), (1025, 333),
-                                         (2500, 700)])
+                                         (2500, 700), (6000, 900), (8300, 400)])
 def test_build_shapes_vs_oracle(n_hap, n_pos):
     phylo, refseq = synth.synthetic_phylo(n_hap=n_hap, n_pos=n_pos, ref_len=max(2 * n_pos, 600),
                                           markers_per_hap=min(6, n_pos), seed=n_hap)
@@ -173,6 +175,18 @@ def test_build_class_kernel_equals_dense_kernel(phylo17, monkeypatch):
     assert np.array_equal(mat, o_mat) and np.array_equal(cnt, o_cnt)
     assert np.array_equal(mat_nc, o_mat)
     assert np.array_equal(d_mat, o_mat) and np.array_equal(d_cnt, o_cnt)
+    # every row through the large-pool launch only
+    monkeypatch.setenv("MXB_BUILD_TIERS", "2")
+    t_mat, t_cnt, _, _ = build_matrix_from_csr(tables, csr, want_counts=True)
+    monkeypatch.delenv("MXB_BUILD_TIERS")
+    assert np.array_equal(t_mat, o_mat) and np.array_equal(t_cnt, o_cnt)
+    # deviation lists relative to the marker-free pattern instead of the majority pattern
+    # (read when the tables are packed on the device)
+    monkeypatch.setenv("MXB_BUILD_BASE_REF", "1")
+    tables_ref = HapVarBaseMatrix(phylo17.refseq, phylo17, haps).pack()
+    r_mat, r_cnt, _, _ = build_matrix_from_csr(tables_ref, csr, want_counts=True)
+    monkeypatch.delenv("MXB_BUILD_BASE_REF")
+    assert np.array_equal(r_mat, o_mat) and np.array_equal(r_cnt, o_cnt)
 
 
 def test_build_unsorted_and_repeated_positions(phylo17):
