@@ -323,6 +323,8 @@ def run_b200(opts):
     sess = ctypes.c_void_p()
     check(lib.mxb_em_create(ctx.handle, dmat.handle, ptr(weights), 1 if world > 1 else 0,
                             ctypes.byref(sess)))
+    hbm_bytes, n_dense_rows = ctypes.c_int64(), ctypes.c_int64()
+    check(lib.mxb_em_pass_bytes(sess, ctypes.byref(hbm_bytes), ctypes.byref(n_dense_rows)))
     lnp0 = np.log(np.random.RandomState(1).dirichlet([1.0] * h))
     check(lib.mxb_em_set_lnprops(sess, ptr(lnp0)))
     el, ps = ctypes.c_float(), ctypes.c_float()
@@ -346,17 +348,29 @@ def run_b200(opts):
     value = cells_total * opts.steps / dev_s
     lib.mxb_em_destroy(sess)
 
+    # The pass reads every row once per iteration.  Rows with at most 256 distinct values are
+    # stored as one byte per cell plus a 2 KB table (lossless, csrc/em.cu em_pack_kernel); the
+    # algorithmic bytes of the pass are what that layout holds, fp64_rows_bytes what the plain
+    # fp64 layout of SURVEY section 8(d) would hold (8 B per cell).
     ld = ((h + 15) // 16) * 16
-    pass_bytes = float(n) * ld * 8
+    fp64_bytes = float(n) * ld * 8
+    pass_bytes = float(hbm_bytes.value)
+    coded = n_dense_rows.value >= 0
     achieved = pass_bytes / pass_s / 1e9
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "em_pass_fast_kernel", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    key = "em_pass_coded_bytes_per_launch" if coded else "em_pass_fast_kernel_bytes_per_launch"
+    roofline = {"bound": "hbm",
+                "kernel": ("em_pass_fast_kernel<coded rows> (+ em_pass_fast_kernel<fp64 rows> for "
+                           "%d rows with more than 256 distinct values)" % n_dense_rows.value)
+                if coded else "em_pass_fast_kernel<fp64 rows>",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": pass_bytes,
                 "ms_per_launch": pass_s * 1e3,
+                "fp64_rows_bytes": fp64_bytes,
+                "fp64_rows_equivalent_GBs": fp64_bytes / pass_s / 1e9,
                 # the committed ncu capture is of the config-2 launch
-                "traffic": (traffic or {}).get("em_pass_fast_kernel_bytes_per_launch")
+                "traffic": (traffic or {}).get(key)
                 if opts.rows == 0 and opts.fragments == 1000000 else None}
 
     # ---- restart sweep (config 4): two restarts share every read of the matrix ----
@@ -481,7 +495,7 @@ def run_b200(opts):
                             % (world, "peer stores inside the EM tail kernel (CUDA IPC over NVLink)"
                                if lib.mxb_comm_p2p_enabled(ctx.handle) else "ncclAllReduce(fp64)"))
                            if world > 1 else "single GPU",
-                           "l2_policy": "input (%.2f GB) larger than L2, no flush needed"
+                           "l2_policy": "input (%.2f GB per pass) larger than L2, no flush needed"
                            % (pass_bytes / 1e9)},
                 "em_iters_per_s": opts.steps / dev_s,
                 "wall_ms_per_step": 1e3 * wall / opts.steps,

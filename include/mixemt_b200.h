@@ -189,6 +189,13 @@ int mxb_em_set_lnprops(mxb_em *em, const double *lnprops);
  * max_iter.  iters_out = iterations run; converged_out = 1/0. */
 int mxb_em_iterate(mxb_em *em, int64_t max_iter, double tol,
                    int64_t *iters_out, int32_t *converged_out);
+/* Bytes the pass kernel(s) of one EM iteration read from HBM, and how the rows are stored:
+ * *n_dense_rows = -1 when the session keeps L as fp64 rows (N x ld x 8 bytes per pass), else
+ * the number of rows kept as fp64 next to the dictionary-coded records of all rows
+ * (ld + 2048 bytes each; csrc/em.cu: em_pack_kernel).  Measurement aid of bench.py; no
+ * counterpart in the reference (em.py:57-91 re-reads the whole matrix several times). */
+int mxb_em_pass_bytes(const mxb_em *em, int64_t *bytes_per_pass, int64_t *n_dense_rows);
+
 /* Exactly n_iter iterations without convergence test or host sync (bench);
  * elapsed_ms (nullable) = device time between first and last launch,
  * pass_ms (nullable) = summed device time of the fused E/M pass kernel only

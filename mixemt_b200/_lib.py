@@ -95,6 +95,7 @@ _PROTOS = {
     "mxb_em_set_lnprops": (ctypes.c_int, [P, P]),
     "mxb_em_iterate": (ctypes.c_int, [P, c_i64, c_dbl, ctypes.POINTER(c_i64),
                                       ctypes.POINTER(c_i32)]),
+    "mxb_em_pass_bytes": (ctypes.c_int, [P, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "mxb_em_iterate_fixed": (ctypes.c_int, [P, c_i64, ctypes.POINTER(ctypes.c_float),
                                             ctypes.POINTER(ctypes.c_float)]),
     "mxb_em_get_lnprops": (ctypes.c_int, [P, ctypes.c_int, P]),

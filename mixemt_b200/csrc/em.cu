@@ -183,6 +183,115 @@ to_linear_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols, i
     }
 }
 
+// ---- dictionary-coded rows -----------------------------------------------------
+// A row of the matrix built by kernel 1 holds few distinct values (one per class of
+// haplotypes with the same match pattern: median 56, at most 256 for 93 % of the config-2
+// rows), and so does its row of L.  Such a row is stored losslessly as one byte per cell
+// plus a table of 256 doubles -- ld + 2048 bytes instead of 8 ld (5.8x fewer at H = 5408) --
+// and the pass kernel looks the values up in shared memory: the same numbers enter the same
+// sums in the same order, with a fraction of the HBM traffic.  Rows with more distinct
+// values ("dense rows") are gathered into a small fp64 matrix of their own and go through
+// the uncoded pass kernel.  Record of row r: [ld code bytes][256 doubles] at r * rec_bytes;
+// the record of a dense row has a zeroed table and weight 0, so it adds exactly nothing.
+constexpr int kDictSize = 256;
+constexpr int kDictSlots = 1024;      // hash slots of the coder (at most 512 ever taken)
+constexpr int kPackThreads = 256;
+constexpr unsigned long long kDictEmpty = 0xFFFFFFFFFFFFFFFFull;  // a NaN L never holds
+
+__global__ void __launch_bounds__(kPackThreads)
+em_pack_kernel(const double *__restrict__ lin, int64_t n_rows, int64_t ld,
+               const double *__restrict__ weights, unsigned char *__restrict__ rec,
+               int64_t rec_bytes, int *__restrict__ dense_flag, double *__restrict__ w_coded) {
+    __shared__ unsigned long long keys[kDictSlots];
+    __shared__ unsigned short ids[kDictSlots];
+    __shared__ int count;
+    extern __shared__ unsigned short cell_slot[];   // [ld] hash slot of every cell
+    const int tid = threadIdx.x;
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        for (int i = tid; i < kDictSlots; i += kPackThreads) keys[i] = kDictEmpty;
+        if (tid == 0) count = 0;
+        __syncthreads();
+        const double *src = lin + r * ld;
+        for (int64_t j = tid; j < ld; j += kPackThreads) {
+            if (*reinterpret_cast<volatile int *>(&count) > kDictSize) break;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(src[j]);
+            if (bits == kDictEmpty) { atomicAdd(&count, kDictSize + 1); break; }
+            unsigned h = (unsigned)((bits * 0x9E3779B97F4A7C15ull) >> 54);
+            while (true) {
+                const unsigned long long old = atomicCAS(&keys[h], kDictEmpty, bits);
+                if (old == kDictEmpty) {   // first sight of the value: next free code
+                    ids[h] = (unsigned short)atomicAdd(&count, 1);
+                    break;
+                }
+                if (old == bits) break;
+                h = (h + 1) & (kDictSlots - 1);
+            }
+            cell_slot[j] = (unsigned short)h;
+        }
+        __syncthreads();
+        const bool coded = count <= kDictSize;   // block-uniform
+        unsigned char *out = rec + r * rec_bytes;
+        double *tab = reinterpret_cast<double *>(out + ld);
+        for (int i = tid; i < kDictSize; i += kPackThreads) tab[i] = 0.0;
+        __syncthreads();
+        if (coded) {
+            for (int64_t j = tid; j < ld; j += kPackThreads) out[j] = (unsigned char)ids[cell_slot[j]];
+            for (int i = tid; i < kDictSlots; i += kPackThreads)
+                if (keys[i] != kDictEmpty) tab[ids[i]] = __longlong_as_double((long long)keys[i]);
+        } else {
+            for (int64_t j = tid; j < ld; j += kPackThreads) out[j] = 0;
+        }
+        if (tid == 0) {
+            dense_flag[r] = coded ? 0 : 1;
+            w_coded[r] = coded ? weights[r] : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
+// Positions of the dense rows, in row order (one block: deterministic, N / 1024 steps).
+__global__ void __launch_bounds__(1024)
+em_dense_list_kernel(const int *__restrict__ dense_flag, int64_t n_rows,
+                     int64_t *__restrict__ dense_rows, int64_t *__restrict__ n_dense) {
+    __shared__ int warp_tot[32];
+    __shared__ int64_t base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int64_t r0 = 0; r0 < n_rows; r0 += 1024) {
+        const int64_t r = r0 + tid;
+        const int f = (r < n_rows) ? dense_flag[r] : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, f != 0);
+        if (lane == 0) warp_tot[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int t = warp_tot[w];
+            if (w < warp) before += t;
+            total += t;
+        }
+        if (f) dense_rows[base + before + __popc(m & ((1u << lane) - 1u))] = r;
+        __syncthreads();
+        if (tid == 0) base += total;
+        __syncthreads();
+    }
+    if (tid == 0) *n_dense = base;
+}
+
+// dst[i] = lin[dense_rows[i]], w_dst[i] = weights[dense_rows[i]]
+__global__ void __launch_bounds__(256)
+em_gather_rows_kernel(const double *__restrict__ lin, int64_t ld, const double *__restrict__ weights,
+                      const int64_t *__restrict__ dense_rows, int64_t n_dense,
+                      double *__restrict__ dst, double *__restrict__ w_dst) {
+    for (int64_t i = blockIdx.x; i < n_dense; i += gridDim.x) {
+        const int64_t r = dense_rows[i];
+        const double2 *src = reinterpret_cast<const double2 *>(lin + r * ld);
+        double2 *d = reinterpret_cast<double2 *>(dst + i * ld);
+        for (int64_t j = threadIdx.x; j < ld / 2; j += 256) d[j] = src[j];
+        if (threadIdx.x == 0) w_dst[i] = weights[r];
+    }
+}
+
 // ---- fused E+M pass (fast path) ----------------------------------------------
 // Rows are handled two at a time between block barriers.  The two partial dot
 // products of a thread are reduced together: the first shuffle step hands row 0
@@ -195,18 +304,23 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int off) {
     return __shfl_xor_sync(0xffffffffu, v, off);
 }
 
-template <int NC>
+// kCoded: the rows are dictionary-coded records (see em_pack_kernel) of row_bytes each and a
+// cell is table[code]; otherwise fp64 rows of row_bytes = 8 ld.  accumulate != 0 adds the
+// column sums to what the launch before this one left in `partials` (dense rows first,
+// coded rows on top).
+template <int NC, bool kCoded>
 __global__ void __launch_bounds__(kPassThreads, 1)
-em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
-                    const double *__restrict__ weights, const double *__restrict__ pi0,
-                    const double *__restrict__ pi1, EmState *__restrict__ st,
-                    double *__restrict__ partials, int n_stages) {
+em_pass_fast_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
+                    int64_t n_rows, const double *__restrict__ weights,
+                    const double *__restrict__ pi0, const double *__restrict__ pi1,
+                    EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
+                    int accumulate) {
     static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
     pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t row_bytes = (uint32_t)(ld * sizeof(double));
-    double *scratch = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * row_bytes);
+    double *scratch = reinterpret_cast<double *>(
+        smem_raw + (((size_t)n_stages * row_bytes + 127) & ~(size_t)127));
     uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
 
     const int tid = threadIdx.x;
@@ -214,7 +328,7 @@ em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
     const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
     const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
     const int n_my = (int)(r_end - r_begin);
-    const unsigned char *my_rows = reinterpret_cast<const unsigned char *>(lin + r_begin * ld);
+    const unsigned char *my_rows = rows + (size_t)r_begin * row_bytes;
     const double *my_w = weights + r_begin;
     const uint32_t stages_u32 = smem_u32(smem_raw);
     const uint32_t full_u32 = smem_u32(full);
@@ -271,12 +385,30 @@ em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
             double dx = 0.0, dy = 0.0;
             if (q0 + g < n_my) {
                 mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
-                const double2 *srow = reinterpret_cast<const double2 *>(
-                    smem_raw + (size_t)s * row_bytes) + tid;
+                if (kCoded) {
+                    const unsigned char *srec = smem_raw + (size_t)s * row_bytes;
+                    const uint16_t *codes = reinterpret_cast<const uint16_t *>(srec) + tid;
+                    const double *tab = reinterpret_cast<const double *>(srec + ld);
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        if (k < NC - 1 || last_live) {
+                            const unsigned cc = codes[k * kPassThreads];   // cells 2c, 2c + 1
+                            lv[g][k] = make_double2(tab[cc & 0xFFu], tab[cc >> 8]);
+                        } else {
+                            lv[g][k] = make_double2(0.0, 0.0);
+                        }
+                    }
+                } else {
+                    const double2 *srow = reinterpret_cast<const double2 *>(
+                        smem_raw + (size_t)s * row_bytes) + tid;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        if (k < NC - 1 || last_live) lv[g][k] = srow[k * kPassThreads];
+                        else lv[g][k] = make_double2(0.0, 0.0);
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < NC; ++k) {
-                    if (k < NC - 1 || last_live) lv[g][k] = srow[k * kPassThreads];
-                    else lv[g][k] = make_double2(0.0, 0.0);
                     dx = fma(lv[g][k].x, pr[k].x, dx);
                     dy = fma(lv[g][k].y, pr[k].y, dy);
                 }
@@ -340,7 +472,14 @@ em_pass_fast_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
         const int c = tid + k * kPassThreads;
-        if (c < n_chunks) out[c] = tr[k];
+        if (c < n_chunks) {
+            if (accumulate) {
+                const double2 prev = out[c];
+                out[c] = make_double2(prev.x + tr[k].x, prev.y + tr[k].y);
+            } else {
+                out[c] = tr[k];
+            }
+        }
     }
     if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
 }
@@ -961,28 +1100,43 @@ struct mxb_em {
     // Restart slots: a batched session (run_em with n_multi > 1) iterates two restarts per
     // read of L.  Slot s lives at lnp[b] + s*ld, pi[b] + s*ld, partials + s*n_part*ld, state + s.
     int n_slots = 1;
+    // Dictionary-coded rows (em_pack_kernel): when `coded` the pass reads `rec` (all rows,
+    // dense rows as empty records) and `dense_lin` (the gathered dense rows) instead of `lin`.
+    bool coded = false;
+    unsigned char *rec = nullptr;     // [n_rows][rec_bytes]
+    size_t rec_bytes = 0;
+    double *w_coded = nullptr;        // [n_rows] weight, 0 for dense rows
+    double *dense_lin = nullptr;      // [n_dense][ld]
+    double *w_dense = nullptr;        // [n_dense]
+    int64_t n_dense = 0;
+    int coded_stages = 0;
+    size_t coded_smem = 0;
+    int grid_dense = 0;
     unsigned char *small = nullptr;  // one device block behind weights ... state (fewer driver calls)
     bool zero_iter = false;  // last iterate() ran no iteration
 };
 
 namespace mxb {
 
-typedef void (*pass_fn)(const double *, int64_t, int64_t, const double *, const double *,
-                        const double *, EmState *, double *, int);
+typedef void (*pass_fn)(const unsigned char *, uint32_t, int64_t, int64_t, const double *,
+                        const double *, const double *, EmState *, double *, int, int);
 
-static pass_fn pick_pass(int nc) {
+template <bool kCoded>
+static pass_fn pick_pass_t(int nc) {
     switch (nc) {
-        case 1: return em_pass_fast_kernel<1>;
-        case 2: return em_pass_fast_kernel<2>;
-        case 3: return em_pass_fast_kernel<3>;
-        case 4: return em_pass_fast_kernel<4>;
-        case 5: return em_pass_fast_kernel<5>;
-        case 6: return em_pass_fast_kernel<6>;
-        case 7: return em_pass_fast_kernel<7>;
-        case 8: return em_pass_fast_kernel<8>;
+        case 1: return em_pass_fast_kernel<1, kCoded>;
+        case 2: return em_pass_fast_kernel<2, kCoded>;
+        case 3: return em_pass_fast_kernel<3, kCoded>;
+        case 4: return em_pass_fast_kernel<4, kCoded>;
+        case 5: return em_pass_fast_kernel<5, kCoded>;
+        case 6: return em_pass_fast_kernel<6, kCoded>;
+        case 7: return em_pass_fast_kernel<7, kCoded>;
+        case 8: return em_pass_fast_kernel<8, kCoded>;
     }
     return nullptr;
 }
+static pass_fn pick_pass(int nc) { return pick_pass_t<false>(nc); }
+static pass_fn pick_pass_coded(int nc) { return pick_pass_t<true>(nc); }
 
 typedef void (*pair_fn)(const double *, int64_t, int64_t, const double *, const double *,
                         const double *, const double *, const double *, EmState *, double *,
@@ -1043,10 +1197,28 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
         ctx->launches += 1;
         return MXB_OK;
     }
-    if (em->fast) {
+    if (em->coded) {
+        // dense rows first (their own small matrix), then the coded records of all rows on top;
+        // both launches use the same grid, so partials[cta] is written, then added to
+        if (em->n_dense > 0) {
+            MXB_CUDA(launch_pdl(pick_pass(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
+                                em->smem_bytes, s, (const unsigned char *)em->dense_lin,
+                                (uint32_t)(em->ld * sizeof(double)), em->ld, em->n_dense,
+                                em->w_dense, em->pi[0], em->pi[1], em->state, em->partials,
+                                em->n_stages, 0));
+            ctx->launches += 1;
+        }
+        MXB_CUDA(launch_pdl(pick_pass_coded(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
+                            em->coded_smem, s, (const unsigned char *)em->rec,
+                            (uint32_t)em->rec_bytes, em->ld, em->n_rows, em->w_coded, em->pi[0],
+                            em->pi[1], em->state, em->partials, em->coded_stages,
+                            em->n_dense > 0 ? 1 : 0));
+        ctx->launches += 1;
+    } else if (em->fast) {
         MXB_CUDA(launch_pdl(pick_pass(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
-                            em->smem_bytes, s, em->lin, em->ld, em->n_rows, em->weights,
-                            em->pi[0], em->pi[1], em->state, em->partials, em->n_stages));
+                            em->smem_bytes, s, (const unsigned char *)em->lin,
+                            (uint32_t)(em->ld * sizeof(double)), em->ld, em->n_rows, em->weights,
+                            em->pi[0], em->pi[1], em->state, em->partials, em->n_stages, 0));
         ctx->launches += 1;
     } else {
         const int rd_blocks = (int)std::max<int64_t>(
@@ -1128,6 +1300,8 @@ int mxb_em_destroy(mxb_em *em) {
     cudaSetDevice(em->ctx->device);
     cudaStreamSynchronize(em->ctx->stream);
     dev_free(em->ctx, em->lin);
+    dev_free(em->ctx, em->rec);
+    dev_free(em->ctx, em->dense_lin);
     dev_free(em->ctx, em->small);
     for (int i = 0; i < 2; ++i)
         if (em->poll_ev[i]) cudaEventDestroy(em->poll_ev[i]);
@@ -1147,6 +1321,89 @@ __global__ void em_reset_state_kernel(EmState *st, long long max_iter, double to
     st->max_iter = max_iter;
     st->tol = tol;
     st->delta = 0.0;
+}
+
+// Dictionary-code the rows of em->lin (see em_pack_kernel).  On success with enough
+// codable rows the session switches to the coded pass and gives em->lin back; otherwise it
+// stays as it is.  MXB_EM_NO_PACK=1 keeps the fp64 rows (cross-check).
+static int em_pack_rows(mxb_em *em) {
+    mxb_ctx *ctx = em->ctx;
+    if (!em->fast || em->n_slots != 1 || em->n_rows == 0 || getenv("MXB_EM_NO_PACK")) return MXB_OK;
+    const size_t row_bytes = (size_t)em->ld * sizeof(double);
+    const size_t rec_bytes = (size_t)em->ld + kDictSize * sizeof(double);
+    const size_t fixed = 2 * kPassWarps * kPassGroup * sizeof(double) + 8 * sizeof(uint64_t) + 256;
+    if (ctx->smem_optin <= fixed) return MXB_OK;
+    const int stages = (int)std::min<size_t>(8, (ctx->smem_optin - fixed) / rec_bytes);
+    if (stages < kPassGroup + 1) return MXB_OK;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t n = (size_t)em->n_rows;
+    unsigned char *rec = nullptr, *tmp = nullptr;
+    cudaError_t e = dev_alloc(ctx, (void **)&rec, up(n * rec_bytes) + up(n * sizeof(double)));
+    if (e == cudaSuccess)
+        e = dev_alloc(ctx, (void **)&tmp, up(n * sizeof(int)) + up(n * sizeof(int64_t)) + 256);
+    if (e != cudaSuccess) {   // not enough memory for the coded copy: keep the fp64 rows
+        cudaGetLastError();
+        dev_free(ctx, rec);
+        dev_free(ctx, tmp);
+        return MXB_OK;
+    }
+    double *w_coded = reinterpret_cast<double *>(rec + up(n * rec_bytes));
+    int *flag = reinterpret_cast<int *>(tmp);
+    int64_t *list = reinterpret_cast<int64_t *>(tmp + up(n * sizeof(int)));
+    int64_t *d_count = reinterpret_cast<int64_t *>(tmp + up(n * sizeof(int)) + up(n * sizeof(int64_t)));
+    int64_t n_dense = 0;
+    double *dense = nullptr;
+    const int grid = (int)std::min<int64_t>(em->n_rows, (int64_t)ctx->num_sms * 8);
+    em_pack_kernel<<<grid, kPackThreads, (size_t)em->ld * sizeof(unsigned short), ctx->stream>>>(
+        em->lin, em->n_rows, em->ld, em->weights, rec, (int64_t)rec_bytes, flag, w_coded);
+    em_dense_list_kernel<<<1, 1024, 0, ctx->stream>>>(flag, em->n_rows, list, d_count);
+    ctx->launches += 2;
+    e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&n_dense, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    // worth it when the coded pass reads less than two thirds of the fp64 rows
+    const bool worth = e == cudaSuccess &&
+                       (double)n * rec_bytes + (double)n_dense * row_bytes < 0.66 * (double)n * row_bytes;
+    if (worth && n_dense > 0) {
+        e = dev_alloc(ctx, (void **)&dense, up((size_t)n_dense * row_bytes) + up((size_t)n_dense * sizeof(double)));
+        if (e == cudaSuccess) {
+            double *w_dense = reinterpret_cast<double *>((unsigned char *)dense + up((size_t)n_dense * row_bytes));
+            const int g = (int)std::min<int64_t>(n_dense, (int64_t)ctx->num_sms * 8);
+            em_gather_rows_kernel<<<g, 256, 0, ctx->stream>>>(em->lin, em->ld, em->weights, list,
+                                                               n_dense, dense, w_dense);
+            ctx->launches += 1;
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            em->w_dense = w_dense;
+        }
+    }
+    if (e == cudaSuccess && worth)
+        e = cudaFuncSetAttribute((const void *)pick_pass_coded(em->nc),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)stages * rec_bytes + fixed));
+    dev_free(ctx, tmp);
+    if (e != cudaSuccess || !worth) {
+        dev_free(ctx, rec);
+        dev_free(ctx, dense);
+        em->w_dense = nullptr;
+        if (e != cudaSuccess) {
+            set_error("em_pack_rows: %s", cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? MXB_ERR_NOMEM : MXB_ERR_CUDA;
+        }
+        return MXB_OK;
+    }
+    em->coded = true;
+    em->rec = rec;
+    em->rec_bytes = rec_bytes;
+    em->w_coded = w_coded;
+    em->dense_lin = dense;
+    em->n_dense = n_dense;
+    em->coded_stages = stages;
+    em->coded_smem = (size_t)stages * rec_bytes + fixed;
+    dev_free(ctx, em->lin);   // every pass reads the records and the dense rows from now on
+    em->lin = nullptr;
+    return MXB_OK;
 }
 
 static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int sharded,
@@ -1258,6 +1515,11 @@ static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weigh
         mxb_em_destroy(em);
         return e == cudaErrorMemoryAllocation ? MXB_ERR_NOMEM : MXB_ERR_CUDA;
     }
+    const int rc = em_pack_rows(em);
+    if (rc != MXB_OK) {
+        mxb_em_destroy(em);
+        return rc;
+    }
     *out = em;
     return MXB_OK;
 }
@@ -1269,6 +1531,16 @@ extern "C" {
 int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int sharded,
                   mxb_em **out) {
     return em_create_impl(ctx, m, weights, sharded, 1, out);
+}
+
+int mxb_em_pass_bytes(const mxb_em *em, int64_t *bytes_per_pass, int64_t *n_dense_rows) {
+    MXB_REQUIRE(em != nullptr, "NULL argument");
+    const int64_t row_bytes = em->ld * (int64_t)sizeof(double);
+    if (bytes_per_pass)
+        *bytes_per_pass = em->coded ? em->n_rows * (int64_t)em->rec_bytes + em->n_dense * row_bytes
+                                    : em->n_rows * row_bytes;
+    if (n_dense_rows) *n_dense_rows = em->coded ? em->n_dense : -1;
+    return MXB_OK;
 }
 
 int mxb_em_set_lnprops(mxb_em *em, const double *lnprops) {

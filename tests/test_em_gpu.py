@@ -329,3 +329,61 @@ def test_batched_restarts_equal_sequential(n_multi):
     assert list(o_it) == info_b["iterations"]
     assert np.abs(p_b - o_p).max() < 1e-10
     assert close_mix(m_b, o_m)
+
+
+@pytest.mark.parametrize("n_extra", [0, 37])
+def test_coded_rows_equal_fp64_rows(phylo17, n_extra):
+    """Rows with at most 256 distinct values are stored as one byte per cell plus a table
+    (em_pack_kernel) and looked up in shared memory by the pass kernel; rows with more go
+    through the fp64 pass.  Same numbers, same order of the sums: without dense rows the
+    result is bit-identical to the fp64 path (MXB_EM_NO_PACK=1), with them it differs only
+    by the order in which the two groups of rows are added."""
+    import ctypes
+    import os
+    from mixemt_b200._lib import lib, check, ptr
+    haps = sorted(phylo17.hap_var)
+    mix = synth.make_mixture(phylo17, phylo17.refseq, [("H1", 0.5), ("L3e", 0.3), ("U5a1", 0.2)],
+                             4000, seed=4)
+    tables = HapVarBaseMatrix(phylo17.refseq, phylo17, haps).pack()
+    mat, _, _, _ = build_matrix_from_csr(tables, mix.csr(tables))
+    wts = mix.weights.astype(np.float64)
+    distinct = np.array([len(np.unique(r)) for r in mat])
+    if n_extra == 0:
+        keep = distinct <= 256
+        mat, wts = np.ascontiguousarray(mat[keep]), wts[keep]
+    else:
+        rs = np.random.RandomState(3)
+        noise = mat[:n_extra] - rs.gamma(2.0, 1.0, size=(n_extra, mat.shape[1]))
+        mat = np.ascontiguousarray(np.vstack([mat[:1500], noise, mat[1500:]]))
+        wts = np.concatenate([wts[:1500], rs.randint(1, 9, size=n_extra).astype(np.float64),
+                              wts[1500:]])
+    n, h = mat.shape
+    ctx = get_context()
+    dev = DeviceMatrix.from_host(ctx, mat)
+    # the session reports what its pass reads
+    sess = ctypes.c_void_p()
+    check(lib.mxb_em_create(ctx.handle, dev.handle, ptr(wts), 0, ctypes.byref(sess)))
+    nbytes, n_dense = ctypes.c_int64(), ctypes.c_int64()
+    check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nbytes), ctypes.byref(n_dense)))
+    lib.mxb_em_destroy(sess)
+    expect_dense = int((np.array([len(np.unique(r)) for r in mat]) > 256).sum())
+    assert n_dense.value == expect_dense
+    assert nbytes.value == n * (h + 2048) + expect_dense * h * 8 < 0.5 * n * h * 8
+
+    inits = np.log(np.random.RandomState(1).dirichlet([1.0] * h, size=1))
+    a = make_args(max_iter=400, tolerance=1e-5)
+    p_c, m_c, info_c, _ = em.run_em_device(dev, wts, a, inits=inits)
+    os.environ["MXB_EM_NO_PACK"] = "1"
+    try:
+        p_f, m_f, info_f, _ = em.run_em_device(dev, wts, a, inits=inits)
+    finally:
+        del os.environ["MXB_EM_NO_PACK"]
+    assert info_c["iterations"] == info_f["iterations"] and info_c["iterations"][0] > 20
+    if n_extra == 0:
+        assert np.array_equal(p_c, p_f) and np.array_equal(m_c, m_f)
+    else:
+        assert np.abs(p_c - p_f).max() < 1e-13
+        assert close_mix(m_c, m_f, 1e-10)
+    o_p, o_m, o_it = oracle_c.run_em(mat, wts, inits, a.max_iter, a.tolerance)
+    assert list(o_it) == info_c["iterations"]
+    assert np.abs(p_c - o_p).max() < 1e-10
