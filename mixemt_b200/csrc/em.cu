@@ -304,11 +304,8 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int off) {
     return __shfl_xor_sync(0xffffffffu, v, off);
 }
 
-// kCoded: the rows are dictionary-coded records (see em_pack_kernel) of row_bytes each and a
-// cell is table[code]; otherwise fp64 rows of row_bytes = 8 ld.  accumulate != 0 adds the
-// column sums to what the launch before this one left in `partials` (dense rows first,
-// coded rows on top).
-template <int NC, bool kCoded>
+// accumulate != 0 adds the column sums to what the launch before this one left in `partials`.
+template <int NC>
 __global__ void __launch_bounds__(kPassThreads, 1)
 em_pass_fast_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
                     int64_t n_rows, const double *__restrict__ weights,
@@ -385,7 +382,176 @@ em_pass_fast_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, 
             double dx = 0.0, dy = 0.0;
             if (q0 + g < n_my) {
                 mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
-                if (kCoded) {
+                const double2 *srow = reinterpret_cast<const double2 *>(
+                    smem_raw + (size_t)s * row_bytes) + tid;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    if (k < NC - 1 || last_live) lv[g][k] = srow[k * kPassThreads];
+                    else lv[g][k] = make_double2(0.0, 0.0);
+                    dx = fma(lv[g][k].x, pr[k].x, dx);
+                    dy = fma(lv[g][k].y, pr[k].y, dy);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NC; ++k) lv[g][k] = make_double2(0.0, 0.0);
+            }
+            dot[g] = dx + dy;
+            if (++s == n_stages) { s = 0; ph ^= 1u; }
+        }
+        // both rows in one butterfly: lanes 0-15 end up with row 0, lanes 16-31 with row 1
+        double v = (upper ? dot[1] : dot[0]) + shfl_xor_f64(upper ? dot[0] : dot[1], 16);
+        v += shfl_xor_f64(v, 8);
+        v += shfl_xor_f64(v, 4);
+        v += shfl_xor_f64(v, 2);
+        v += shfl_xor_f64(v, 1);
+        double *sc = scratch + sbuf * (kPassWarps * kPassGroup);
+        if ((lane & 15) == 0) sc[(lane >> 4) * kPassWarps + warp] = v;
+        __syncthreads();  // all reads of this group's stages are done; warp totals visible
+        if (tid == 0) {
+#pragma unroll
+            for (int g = 0; g < kPassGroup; ++g) {
+                const int q = q0 + g + n_stages;
+                if (q < n_my) {
+                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_of[g];
+                    mbar_expect_tx_u32(bar, row_bytes);
+                    bulk_load_u32(stages_u32 + (uint32_t)s_of[g] * row_bytes,
+                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
+                }
+            }
+        }
+        // 16 warp totals per row sit in sc[0..15] / sc[16..31]: one value per lane
+        double t = sc[lane];
+        t += shfl_xor_f64(t, 8);
+        t += shfl_xor_f64(t, 4);
+        t += shfl_xor_f64(t, 2);
+        t += shfl_xor_f64(t, 1);
+        double coef_mine = 0.0;
+        if (w_mine != 0.0) {
+            coef_mine = w_mine / t;
+            bad |= (t == 0.0);
+        }
+        const double coef0 = __shfl_sync(0xffffffffu, coef_mine, 0);
+        const double coef1 = __shfl_sync(0xffffffffu, coef_mine, 16);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            tr[k].x = fma(coef0, lv[0][k].x, tr[k].x);
+            tr[k].y = fma(coef0, lv[0][k].y, tr[k].y);
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            tr[k].x = fma(coef1, lv[1][k].x, tr[k].x);
+            tr[k].y = fma(coef1, lv[1][k].y, tr[k].y);
+        }
+        stage = s;
+        phase = ph;
+        sbuf ^= 1;
+    }
+
+    double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int c = tid + k * kPassThreads;
+        if (c < n_chunks) {
+            if (accumulate) {
+                const double2 prev = out[c];
+                out[c] = make_double2(prev.x + tr[k].x, prev.y + tr[k].y);
+            } else {
+                out[c] = tr[k];
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
+}
+
+// ---- fused E+M pass over dictionary-coded rows ----------------------------------------
+// em_pass_fast_kernel over the records of em_pack_kernel ([ld code bytes][256 doubles], a
+// cell is table[code]): same ring, same column slices (chunk c = tid + k*512 covers cells
+// 2c, 2c+1, one 16-bit load brings both codes), same reduction; only the two values of a
+// chunk come from the row's table in shared memory instead of the stage itself.  A record
+// is 5.8x smaller than the fp64 row, so this kernel is bound by instruction issue (lookup
+// index arithmetic, butterflies, the division) and not by HBM: 0.55 ms for the 138 569
+// records of config 2 against 0.87 ms for the fp64 rows (more threads per CTA, eight rows
+// per barrier with the values looked up twice, and run-length aware lookups over
+// consecutive cells were all measured slower).  accumulate != 0 adds the column sums to what
+// the launch before this one (the fp64 pass over the dense rows) left in `partials`.
+template <int NC>
+__global__ void __launch_bounds__(kPassThreads, 1)
+em_pass_coded_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
+                    int64_t n_rows, const double *__restrict__ weights,
+                    const double *__restrict__ pi0, const double *__restrict__ pi1,
+                    EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
+                    int accumulate) {
+    static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
+    pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *scratch = reinterpret_cast<double *>(
+        smem_raw + (((size_t)n_stages * row_bytes + 127) & ~(size_t)127));
+    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int n_my = (int)(r_end - r_begin);
+    const unsigned char *my_rows = rows + (size_t)r_begin * row_bytes;
+    const double *my_w = weights + r_begin;
+    const uint32_t stages_u32 = smem_u32(smem_raw);
+    const uint32_t full_u32 = smem_u32(full);
+
+    // Prologue: L and the weights do not depend on the previous iteration's tail, so the
+    // ring is primed before waiting for it (the loads overlap the tail kernel).
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 0; q < n_my && q < n_stages; ++q) {
+            mbar_expect_tx(&full[q], row_bytes);
+            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
+                      &full[q]);
+        }
+    }
+    pdl_wait();  // proportions and control block of the previous iteration are final
+    if (st->done) {
+        // finished run: the primed loads must land before this CTA's shared memory is released
+        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
+        return;
+    }
+    const double *__restrict__ pi = st->cur ? pi1 : pi0;
+
+    // Thread-private column slice: chunk c = tid + k*512 covers doubles 2c, 2c+1.
+    const int n_chunks = (int)(ld >> 1);
+    double2 pr[NC], tr[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int c = tid + k * kPassThreads;
+        pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
+        tr[k] = make_double2(0.0, 0.0);
+    }
+    const bool last_live = tid + (NC - 1) * kPassThreads < n_chunks;  // only chunk NC-1 can be ragged
+
+    int stage = 0;          // ring slot of row q0
+    uint32_t phase = 0;     // its mbarrier parity
+    int sbuf = 0;
+    int bad = 0;
+    const bool upper = lane >= 16;
+    for (int q0 = 0; q0 < n_my; q0 += kPassGroup) {
+        double2 lv[kPassGroup][NC];
+        double dot[kPassGroup];
+        const int q_mine = q0 + (upper ? 1 : 0);
+        const double w_mine = (q_mine < n_my) ? my_w[q_mine] : 0.0;
+        int s_of[kPassGroup];
+        int s = stage;
+        uint32_t ph = phase;
+#pragma unroll
+        for (int g = 0; g < kPassGroup; ++g) {
+            s_of[g] = s;
+            double dx = 0.0, dy = 0.0;
+            if (q0 + g < n_my) {
+                mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
+                {
                     const unsigned char *srec = smem_raw + (size_t)s * row_bytes;
                     const uint16_t *codes = reinterpret_cast<const uint16_t *>(srec) + tid;
                     const double *tab = reinterpret_cast<const double *>(srec + ld);
@@ -397,14 +563,6 @@ em_pass_fast_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, 
                         } else {
                             lv[g][k] = make_double2(0.0, 0.0);
                         }
-                    }
-                } else {
-                    const double2 *srow = reinterpret_cast<const double2 *>(
-                        smem_raw + (size_t)s * row_bytes) + tid;
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        if (k < NC - 1 || last_live) lv[g][k] = srow[k * kPassThreads];
-                        else lv[g][k] = make_double2(0.0, 0.0);
                     }
                 }
 #pragma unroll
@@ -1121,22 +1279,32 @@ namespace mxb {
 typedef void (*pass_fn)(const unsigned char *, uint32_t, int64_t, int64_t, const double *,
                         const double *, const double *, EmState *, double *, int, int);
 
-template <bool kCoded>
-static pass_fn pick_pass_t(int nc) {
+static pass_fn pick_pass(int nc) {
     switch (nc) {
-        case 1: return em_pass_fast_kernel<1, kCoded>;
-        case 2: return em_pass_fast_kernel<2, kCoded>;
-        case 3: return em_pass_fast_kernel<3, kCoded>;
-        case 4: return em_pass_fast_kernel<4, kCoded>;
-        case 5: return em_pass_fast_kernel<5, kCoded>;
-        case 6: return em_pass_fast_kernel<6, kCoded>;
-        case 7: return em_pass_fast_kernel<7, kCoded>;
-        case 8: return em_pass_fast_kernel<8, kCoded>;
+        case 1: return em_pass_fast_kernel<1>;
+        case 2: return em_pass_fast_kernel<2>;
+        case 3: return em_pass_fast_kernel<3>;
+        case 4: return em_pass_fast_kernel<4>;
+        case 5: return em_pass_fast_kernel<5>;
+        case 6: return em_pass_fast_kernel<6>;
+        case 7: return em_pass_fast_kernel<7>;
+        case 8: return em_pass_fast_kernel<8>;
     }
     return nullptr;
 }
-static pass_fn pick_pass(int nc) { return pick_pass_t<false>(nc); }
-static pass_fn pick_pass_coded(int nc) { return pick_pass_t<true>(nc); }
+static pass_fn pick_pass_coded(int nc) {
+    switch (nc) {
+        case 1: return em_pass_coded_kernel<1>;
+        case 2: return em_pass_coded_kernel<2>;
+        case 3: return em_pass_coded_kernel<3>;
+        case 4: return em_pass_coded_kernel<4>;
+        case 5: return em_pass_coded_kernel<5>;
+        case 6: return em_pass_coded_kernel<6>;
+        case 7: return em_pass_coded_kernel<7>;
+        case 8: return em_pass_coded_kernel<8>;
+    }
+    return nullptr;
+}
 
 typedef void (*pair_fn)(const double *, int64_t, int64_t, const double *, const double *,
                         const double *, const double *, const double *, EmState *, double *,
@@ -1331,9 +1499,11 @@ static int em_pack_rows(mxb_em *em) {
     if (!em->fast || em->n_slots != 1 || em->n_rows == 0 || getenv("MXB_EM_NO_PACK")) return MXB_OK;
     const size_t row_bytes = (size_t)em->ld * sizeof(double);
     const size_t rec_bytes = (size_t)em->ld + kDictSize * sizeof(double);
-    const size_t fixed = 2 * kPassWarps * kPassGroup * sizeof(double) + 8 * sizeof(uint64_t) + 256;
+    constexpr int kMaxCodedStages = 16;
+    const size_t fixed = 2 * kPassWarps * kPassGroup * sizeof(double) +
+                         kMaxCodedStages * sizeof(uint64_t) + 256;
     if (ctx->smem_optin <= fixed) return MXB_OK;
-    const int stages = (int)std::min<size_t>(8, (ctx->smem_optin - fixed) / rec_bytes);
+    const int stages = (int)std::min<size_t>(kMaxCodedStages, (ctx->smem_optin - fixed) / rec_bytes);
     if (stages < kPassGroup + 1) return MXB_OK;
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t n = (size_t)em->n_rows;
