@@ -19,7 +19,9 @@ One JSON line is printed by rank 0:
             options: host->device copy of the matrix, all iterations, read-matrix
             materialisation and the device->host copy of the N x H result inside
             the timed region (after one short untimed call)
-  roofline  the fused E/M pass kernel against the measured HBM copy bandwidth
+  roofline  the fused E/M pass against the measured HBM copy bandwidth, on the bytes the
+            pass reads (dictionary-coded rows); fp64_rows_equivalent_GBs is
+            the same time against the 8 bytes per cell of the plain fp64 layout
   restart_sweep  4 restarts x 100 iterations per GPU (BASELINE.json config 4), two restarts
             per read of the matrix and one at a time; under torchrun the matrix is
             replicated and 4 N restarts are dealt over the N GPUs
@@ -360,9 +362,10 @@ def run_b200(opts):
     traffic = ncu_traffic()
     key = "em_pass_coded_bytes_per_launch" if coded else "em_pass_fast_kernel_bytes_per_launch"
     roofline = {"bound": "hbm",
-                "kernel": ("em_pass_fast_kernel<coded rows> (+ em_pass_fast_kernel<fp64 rows> for "
-                           "%d rows with more than 256 distinct values)" % n_dense_rows.value)
-                if coded else "em_pass_fast_kernel<fp64 rows>",
+                "kernel": ("em_pass_coded_kernel (dictionary-coded records of all rows) + "
+                           "em_pass_fast_kernel over the %d fp64 rows with more than 256 distinct "
+                           "values" % n_dense_rows.value)
+                if coded else "em_pass_fast_kernel (fp64 rows)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": pass_bytes,
