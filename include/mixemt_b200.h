@@ -179,7 +179,9 @@ int mxb_matrix_upload_rows(mxb_ctx *ctx, mxb_matrix *m, int64_t row0, int64_t n_
 
 /* ---- kernel 2: EM (replaces em_step / run_em, em.py:57-165) ---------------- */
 /* Session over one matrix shard.  weights[n_rows] (fp64).  sharded != 0 and a
- * comm on ctx: rows are a shard, column sums are all-reduced every iteration. */
+ * comm on ctx: rows are a shard, column sums are all-reduced every iteration.
+ * The session keeps L = exp(M - rowmax); rows with at most 256 distinct values are
+ * stored as one byte per cell plus a table (lossless, see mxb_em_pass_bytes). */
 int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
                   int sharded, mxb_em **out);
 int mxb_em_destroy(mxb_em *em);
