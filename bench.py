@@ -350,6 +350,34 @@ def run_b200(opts):
     value = cells_total * opts.steps / dev_s
     lib.mxb_em_destroy(sess)
 
+    # the same iterations over plain fp64 rows (MXB_EM_NO_PACK=1): the pass that sits at the HBM
+    # roofline, reported next to the coded pass that replaces it where rows compress
+    fp64_pass = None
+    if n_dense_rows.value >= 0:
+        os.environ["MXB_EM_NO_PACK"] = "1"
+        try:
+            sess2 = ctypes.c_void_p()
+            check(lib.mxb_em_create(ctx.handle, dmat.handle, ptr(weights), 1 if world > 1 else 0,
+                                    ctypes.byref(sess2)))
+            check(lib.mxb_em_set_lnprops(sess2, ptr(lnp0)))
+            el2, ps2 = ctypes.c_float(), ctypes.c_float()
+            k2 = min(opts.steps, 100)
+            check(lib.mxb_em_iterate_fixed(sess2, max(3, opts.warmup), ctypes.byref(el2), None))
+            barrier()
+            check(lib.mxb_em_iterate_fixed(sess2, k2, ctypes.byref(el2), ctypes.byref(ps2)))
+            lib.mxb_em_destroy(sess2)
+            ld2 = ((h + 15) // 16) * 16
+            gbs = float(n) * ld2 * 8 / (ps2.value / 1e3 / k2) / 1e9
+            fp64_pass = {"kernel": "em_pass_fast_kernel (fp64 rows, MXB_EM_NO_PACK=1)",
+                         "ms_per_launch": ps2.value / k2, "ms_per_step": el2.value / k2,
+                         "algorithmic_bytes_per_launch": float(n) * ld2 * 8,
+                         "achieved": gbs, "unit": "GB/s", "peak": peak, "frac": gbs / peak,
+                         "frac_of_nominal_8TBs": gbs / 8000.0,
+                         "traffic": (ncu_traffic() or {}).get("em_pass_fast_kernel_bytes_per_launch")
+                         if opts.rows == 0 and opts.fragments == 1000000 else None}
+        finally:
+            os.environ.pop("MXB_EM_NO_PACK", None)
+
     # The pass reads every row once per iteration.  Rows with at most 256 distinct values are
     # stored as one byte per cell plus a 2 KB table (lossless, csrc/em.cu em_pack_kernel); the
     # algorithmic bytes of the pass are what that layout holds, fp64_rows_bytes what the plain
@@ -374,7 +402,8 @@ def run_b200(opts):
                 "fp64_rows_equivalent_GBs": fp64_bytes / pass_s / 1e9,
                 # the committed ncu capture is of the config-2 launch
                 "traffic": (traffic or {}).get(key)
-                if opts.rows == 0 and opts.fragments == 1000000 else None}
+                if opts.rows == 0 and opts.fragments == 1000000 else None,
+                "fp64_pass": fp64_pass}
 
     # ---- restart sweep (config 4): two restarts share every read of the matrix ----
     # One GPU: 4 restarts, two per pass and one per pass.  N GPUs: the matrix of rank 0 is
