@@ -61,13 +61,19 @@ class HapVarBaseMatrix(object):
 
     def add_hap_markers(self, hap_var):
         refseq = self.refseq
+        # a variant string sits on every haplogroup below its branch (Build 17: 263 826
+        # entries, 10 k distinct strings): decode each string once
+        decoded = {}
         for hap, variants in hap_var.items():
             table = {}
             for var in variants:
-                pos = pos_from_var(var)
-                der = der_allele(var)
-                if der != refseq[pos]:
-                    table[pos] = der
+                hit = decoded.get(var)
+                if hit is None:
+                    pos = pos_from_var(var)
+                    der = der_allele(var)
+                    hit = decoded[var] = (pos, der if der != refseq[pos] else None)
+                if hit[1] is not None:
+                    table[hit[0]] = hit[1]
             self.markers[hap] = table
 
     # -- reference-compatible scalar probes (used by tests) -------------------
