@@ -647,7 +647,9 @@ em_pass_coded_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes,
 // Second version of the loop (same arithmetic in the same order): full row pairs without
 // "is there a second row" tests or zero fills, the odd last row peeled off, both records
 // waited for before the lookups of either start.  11 % fewer warp instructions per row pair
-// in SASS (274 against 307).  Selected by MXB_EM_CODED_V2=1 until it has been timed on the GPU.
+// in SASS (274 against 307): 0.568 ms per pass against 0.609 ms at config 2 (0.579 ms per
+// iteration against 0.621 ms).  This is the version that runs; MXB_EM_CODED_V1=1 selects the
+// first one.
 template <int NC>
 __global__ void __launch_bounds__(kPassThreads, 1)
 em_pass_coded_v2_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
@@ -1478,7 +1480,7 @@ static pass_fn pick_pass(int nc) {
     return nullptr;
 }
 static pass_fn pick_pass_coded(int nc) {
-    static const bool v2 = getenv("MXB_EM_CODED_V2") != nullptr;
+    static const bool v2 = getenv("MXB_EM_CODED_V1") == nullptr;
     if (v2) {
         switch (nc) {
             case 1: return em_pass_coded_v2_kernel<1>;
