@@ -650,14 +650,15 @@ em_pass_coded_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes,
 // in SASS (274 against 307): 0.568 ms per pass against 0.609 ms at config 2 (0.579 ms per
 // iteration against 0.621 ms).  This is the version that runs; MXB_EM_CODED_V1=1 selects the
 // first one.
-template <int NC>
-__global__ void __launch_bounds__(kPassThreads, 1)
+template <int NC, int THREADS = kPassThreads>
+__global__ void __launch_bounds__(THREADS, 1)
 em_pass_coded_v2_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
                     int64_t n_rows, const double *__restrict__ weights,
                     const double *__restrict__ pi0, const double *__restrict__ pi1,
                     EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
                     int accumulate) {
-    static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
+    static_assert(kPassGroup == 2 && THREADS % 32 == 0 && THREADS <= kPassThreads,
+                  "reduction layout below: at most 16 warp totals per row");
     pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -689,6 +690,9 @@ em_pass_coded_v2_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
                       &full[q]);
         }
     }
+    // totals slots of the warps a smaller CTA does not have (read by the 16-lane butterfly)
+    if (THREADS < kPassThreads && tid < 2 * kPassWarps * kPassGroup && (tid & 15) >= THREADS / 32)
+        scratch[tid] = 0.0;
     pdl_wait();  // proportions and control block of the previous iteration are final
     if (st->done) {
         // finished run: the primed loads must land before this CTA's shared memory is released
@@ -702,11 +706,11 @@ em_pass_coded_v2_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
     double2 pr[NC], tr[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * kPassThreads;
+        const int c = tid + k * THREADS;
         pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
         tr[k] = make_double2(0.0, 0.0);
     }
-    const bool last_live = tid + (NC - 1) * kPassThreads < n_chunks;  // only chunk NC-1 can be ragged
+    const bool last_live = tid + (NC - 1) * THREADS < n_chunks;  // only chunk NC-1 can be ragged
 
     int stage = 0;          // ring slot of row q0
     uint32_t phase = 0;     // its mbarrier parity
@@ -741,7 +745,7 @@ em_pass_coded_v2_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
 #pragma unroll
             for (int k = 0; k < NC; ++k) {
                 if (k < NC - 1 || last_live) {
-                    const unsigned cc = codes[k * kPassThreads];   // cells 2c, 2c + 1
+                    const unsigned cc = codes[k * THREADS];   // cells 2c, 2c + 1
                     lv[g][k] = make_double2(tab[cc & 0xFFu], tab[cc >> 8]);
                 } else {
                     lv[g][k] = make_double2(0.0, 0.0);
@@ -812,6 +816,195 @@ em_pass_coded_v2_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
     int q0 = 0;
     for (; q0 + 1 < n_my; q0 += kPassGroup) step(std::true_type{}, q0);
     if (q0 < n_my) step(std::false_type{}, q0);
+
+    double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int c = tid + k * THREADS;
+        if (c < n_chunks) {
+            if (accumulate) {
+                const double2 prev = out[c];
+                out[c] = make_double2(prev.x + tr[k].x, prev.y + tr[k].y);
+            } else {
+                out[c] = tr[k];
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
+}
+
+// Third version (experimental, MXB_EM_CODED_V3=1, not yet run on a GPU): the same sums in
+// the same order, one row at a time, software-pipelined and without a block barrier.
+//
+// The two-row loop above runs its 16 warps through the same phases in lock step: all of them
+// look values up (the LSU is saturated, ~960 of the ~2100 cycles a row pair takes), then all of
+// them sit in the butterfly / division chains (nothing to issue), then all of them add.  Here a
+// warp publishes its partial dot product of row r + 1 with an mbarrier *arrive* (non-blocking)
+// and only *waits* for the totals of row r, which every warp published one iteration earlier:
+// warps may drift a row apart, so the lookups of one overlap the reductions of another.
+//   iteration r of a warp:  lookups(r + 1) -> wait sum[r] -> [thread 0: refill the slot of row r]
+//                           -> totals(r), coefficient -> dot(r + 1), butterfly, publish(r + 1)
+//                           -> column sums += coefficient * values(r)
+// sum[b], b = r mod 4: mbarrier with one arrival per warp; totals buffer sc[b][16].  A warp
+// overwrites sc[(r + 1) mod 4] only after it saw sum[r] complete, i.e. after every warp has
+// published row r, which each does after reading the totals of row r - 1 >= r - 3.  "Every warp
+// has published row r" also means every warp has the values of row r in registers (the
+// published number depends on all of them), so its ring slot can be refilled.
+constexpr int kSumBufs = 4;
+
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kPassThreads, 1)
+em_pass_coded_v3_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
+                        int64_t n_rows, const double *__restrict__ weights,
+                        const double *__restrict__ pi0, const double *__restrict__ pi1,
+                        EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
+                        int accumulate) {
+    static_assert(kPassWarps == 16 && kSumBufs * kPassWarps <= 2 * kPassWarps * kPassGroup,
+                  "totals buffers live in the scratch area of the two-row kernels");
+    pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *scratch = reinterpret_cast<double *>(
+        smem_raw + (((size_t)n_stages * row_bytes + 127) & ~(size_t)127));
+    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
+    uint64_t *sum = full + 16;   // em_pack_rows: at most 16 stages, 256 spare bytes behind them
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int n_my = (int)(r_end - r_begin);
+    const unsigned char *my_rows = rows + (size_t)r_begin * row_bytes;
+    const double *my_w = weights + r_begin;
+    const uint32_t stages_u32 = smem_u32(smem_raw);
+    const uint32_t full_u32 = smem_u32(full);
+    const uint32_t sum_u32 = smem_u32(sum);
+
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        for (int b = 0; b < kSumBufs; ++b) mbar_init(&sum[b], kPassWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 0; q < n_my && q < n_stages; ++q) {
+            mbar_expect_tx(&full[q], row_bytes);
+            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
+                      &full[q]);
+        }
+    }
+    pdl_wait();  // proportions and control block of the previous iteration are final
+    if (st->done) {
+        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
+        return;
+    }
+    const double *__restrict__ pi = st->cur ? pi1 : pi0;
+
+    const int n_chunks = (int)(ld >> 1);
+    double2 pr[NC], tr[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int c = tid + k * kPassThreads;
+        pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
+        tr[k] = make_double2(0.0, 0.0);
+    }
+    const bool last_live = tid + (NC - 1) * kPassThreads < n_chunks;  // only chunk NC-1 can be ragged
+
+    int bad = 0;
+    // the values of a row: table lookups of this thread's 2 NC cells in ring slot s
+    auto lookups = [&](double2 (&lv)[NC], const int s) {
+        const unsigned char *srec = smem_raw + (size_t)s * row_bytes;
+        const uint16_t *codes = reinterpret_cast<const uint16_t *>(srec) + tid;
+        const double *tab = reinterpret_cast<const double *>(srec + ld);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            if (k < NC - 1 || last_live) {
+                const unsigned cc = codes[k * kPassThreads];   // cells 2c, 2c + 1
+                lv[k] = make_double2(tab[cc & 0xFFu], tab[cc >> 8]);
+            } else {
+                lv[k] = make_double2(0.0, 0.0);
+            }
+        }
+    };
+    // this warp's part of row r's dot product -> sc[r mod 4][warp], one arrival on sum[r mod 4]
+    auto publish = [&](const double2 (&lv)[NC], const int r) {
+        double dx = 0.0, dy = 0.0;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            dx = fma(lv[k].x, pr[k].x, dx);
+            dy = fma(lv[k].y, pr[k].y, dy);
+        }
+        double v = dx + dy;
+        v += shfl_xor_f64(v, 16);
+        v += shfl_xor_f64(v, 8);
+        v += shfl_xor_f64(v, 4);
+        v += shfl_xor_f64(v, 2);
+        v += shfl_xor_f64(v, 1);
+        if (lane == 0) {
+            const int b = r & (kSumBufs - 1);
+            scratch[b * kPassWarps + warp] = v;
+            mbar_arrive_u32(sum_u32 + 8u * (uint32_t)b);   // release: the store above is visible
+        }
+    };
+
+    if (n_my > 0) {
+        double2 lv0[NC], lv1[NC];
+        int s_next = 0;            // ring slot and parity of the row whose values are fetched next
+        uint32_t ph_next = 0;
+        mbar_wait_u32(full_u32, 0u);
+        lookups(lv0, 0);
+        if (++s_next == n_stages) { s_next = 0; ph_next ^= 1u; }
+        publish(lv0, 0);
+        // one row: `cur` holds the values of row r, `nxt` receives those of row r + 1
+        auto row_step = [&](double2 (&cur)[NC], double2 (&nxt)[NC], const int r) {
+            const double w_r = my_w[r];
+            const bool more = r + 1 < n_my;
+            const int s_cur = (s_next == 0 ? n_stages : s_next) - 1;   // slot of row r
+            if (more) {
+                mbar_wait_u32(full_u32 + 8u * (uint32_t)s_next, ph_next);
+                lookups(nxt, s_next);
+                if (++s_next == n_stages) { s_next = 0; ph_next ^= 1u; }
+            }
+            const int b = r & (kSumBufs - 1);
+            mbar_wait_u32(sum_u32 + 8u * (uint32_t)b, (uint32_t)(r >> 2) & 1u);
+            if (tid == 0) {
+                const int q = r + n_stages;
+                if (q < n_my) {
+                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_cur;
+                    mbar_expect_tx_u32(bar, row_bytes);
+                    bulk_load_u32(stages_u32 + (uint32_t)s_cur * row_bytes,
+                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
+                }
+            }
+            // 16 warp totals of row r: one per lane of each half-warp
+            double t = scratch[b * kPassWarps + (lane & 15)];
+            t += shfl_xor_f64(t, 8);
+            t += shfl_xor_f64(t, 4);
+            t += shfl_xor_f64(t, 2);
+            t += shfl_xor_f64(t, 1);
+            double coef = 0.0;
+            if (w_r != 0.0) {
+                coef = w_r / t;
+                bad |= (t == 0.0);
+            }
+            if (more) publish(nxt, r + 1);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                tr[k].x = fma(coef, cur[k].x, tr[k].x);
+                tr[k].y = fma(coef, cur[k].y, tr[k].y);
+            }
+        };
+        int r = 0;
+        for (; r + 1 < n_my; r += 2) {
+            row_step(lv0, lv1, r);
+            row_step(lv1, lv0, r + 1);
+        }
+        if (r < n_my) row_step(lv0, lv1, r);
+    }
 
     double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
 #pragma unroll
@@ -1479,32 +1672,64 @@ static pass_fn pick_pass(int nc) {
     }
     return nullptr;
 }
-static pass_fn pick_pass_coded(int nc) {
+// The coded pass and its CTA size.  Default: second loop version, 512 threads, chunk count
+// `nc`.  MXB_EM_CODED_V1=1: first loop version.  Experimental, not yet run on a GPU:
+// MXB_EM_CODED_V3=1 (pipelined rows, no block barrier) and MXB_EM_CODED_T384=1 (second loop
+// version with 384 threads: 16 instead of 12 cells per thread at H = 5408, so the per-row-pair
+// reduction, division and ring bookkeeping of a warp are spread over a third more cells).
+struct CodedPass {
+    pass_fn fn;
+    int threads;
+};
+static CodedPass pick_pass_coded(int nc, int64_t ld) {
+    static const bool v3 = getenv("MXB_EM_CODED_V3") != nullptr;
+    static const bool t384 = getenv("MXB_EM_CODED_T384") != nullptr;
     static const bool v2 = getenv("MXB_EM_CODED_V1") == nullptr;
+    if (v3) {
+        switch (nc) {
+            case 1: return {em_pass_coded_v3_kernel<1>, kPassThreads};
+            case 2: return {em_pass_coded_v3_kernel<2>, kPassThreads};
+            case 3: return {em_pass_coded_v3_kernel<3>, kPassThreads};
+            case 4: return {em_pass_coded_v3_kernel<4>, kPassThreads};
+            case 5: return {em_pass_coded_v3_kernel<5>, kPassThreads};
+            case 6: return {em_pass_coded_v3_kernel<6>, kPassThreads};
+            case 7: return {em_pass_coded_v3_kernel<7>, kPassThreads};
+            case 8: return {em_pass_coded_v3_kernel<8>, kPassThreads};
+        }
+        return {nullptr, 0};
+    }
+    if (t384) {
+        switch ((int)ceil_div(ld / 2, 384)) {
+            case 6: return {em_pass_coded_v2_kernel<6, 384>, 384};
+            case 7: return {em_pass_coded_v2_kernel<7, 384>, 384};
+            case 8: return {em_pass_coded_v2_kernel<8, 384>, 384};
+        }
+        // other widths keep the 512-thread kernel
+    }
     if (v2) {
         switch (nc) {
-            case 1: return em_pass_coded_v2_kernel<1>;
-            case 2: return em_pass_coded_v2_kernel<2>;
-            case 3: return em_pass_coded_v2_kernel<3>;
-            case 4: return em_pass_coded_v2_kernel<4>;
-            case 5: return em_pass_coded_v2_kernel<5>;
-            case 6: return em_pass_coded_v2_kernel<6>;
-            case 7: return em_pass_coded_v2_kernel<7>;
-            case 8: return em_pass_coded_v2_kernel<8>;
+            case 1: return {em_pass_coded_v2_kernel<1>, kPassThreads};
+            case 2: return {em_pass_coded_v2_kernel<2>, kPassThreads};
+            case 3: return {em_pass_coded_v2_kernel<3>, kPassThreads};
+            case 4: return {em_pass_coded_v2_kernel<4>, kPassThreads};
+            case 5: return {em_pass_coded_v2_kernel<5>, kPassThreads};
+            case 6: return {em_pass_coded_v2_kernel<6>, kPassThreads};
+            case 7: return {em_pass_coded_v2_kernel<7>, kPassThreads};
+            case 8: return {em_pass_coded_v2_kernel<8>, kPassThreads};
         }
-        return nullptr;
+        return {nullptr, 0};
     }
     switch (nc) {
-        case 1: return em_pass_coded_kernel<1>;
-        case 2: return em_pass_coded_kernel<2>;
-        case 3: return em_pass_coded_kernel<3>;
-        case 4: return em_pass_coded_kernel<4>;
-        case 5: return em_pass_coded_kernel<5>;
-        case 6: return em_pass_coded_kernel<6>;
-        case 7: return em_pass_coded_kernel<7>;
-        case 8: return em_pass_coded_kernel<8>;
+        case 1: return {em_pass_coded_kernel<1>, kPassThreads};
+        case 2: return {em_pass_coded_kernel<2>, kPassThreads};
+        case 3: return {em_pass_coded_kernel<3>, kPassThreads};
+        case 4: return {em_pass_coded_kernel<4>, kPassThreads};
+        case 5: return {em_pass_coded_kernel<5>, kPassThreads};
+        case 6: return {em_pass_coded_kernel<6>, kPassThreads};
+        case 7: return {em_pass_coded_kernel<7>, kPassThreads};
+        case 8: return {em_pass_coded_kernel<8>, kPassThreads};
     }
-    return nullptr;
+    return {nullptr, 0};
 }
 
 typedef void (*pair_fn)(const double *, int64_t, int64_t, const double *, const double *,
@@ -1577,7 +1802,8 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
                                 em->n_stages, 0));
             ctx->launches += 1;
         }
-        MXB_CUDA(launch_pdl(pick_pass_coded(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
+        const CodedPass cp = pick_pass_coded(em->nc, em->ld);
+        MXB_CUDA(launch_pdl(cp.fn, dim3(em->grid_fast), dim3(cp.threads),
                             em->coded_smem, s, (const unsigned char *)em->rec,
                             (uint32_t)em->rec_bytes, em->ld, em->n_rows, em->w_coded, em->pi[0],
                             em->pi[1], em->state, em->partials, em->coded_stages,
@@ -1750,7 +1976,7 @@ static int em_pack_rows(mxb_em *em) {
         }
     }
     if (e == cudaSuccess && worth)
-        e = cudaFuncSetAttribute((const void *)pick_pass_coded(em->nc),
+        e = cudaFuncSetAttribute((const void *)pick_pass_coded(em->nc, em->ld).fn,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)stages * rec_bytes + fixed));
     dev_free(ctx, tmp);
