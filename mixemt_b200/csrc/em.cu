@@ -251,6 +251,90 @@ em_pack_kernel(const double *__restrict__ lin, int64_t n_rows, int64_t ld,
     }
 }
 
+// Experimental (MXB_EM_CODED_PAIRS=1, not yet run on a GPU): the dictionary holds the values
+// of a *chunk* -- the two adjacent cells 2c, 2c + 1 one pass-kernel thread handles together --
+// instead of single cells.  91.6 % of the config-2 rows have at most 256 distinct chunks
+// (92.4 % have at most 256 distinct cells: scripts/analysis/pair_codes.py), so about the same
+// rows stay coded, and a chunk costs the pass one table lookup (LDS.128) instead of two
+// (LDS.64) and half the index arithmetic.  Record of row r, kPairRecBytes at r * kPairRecBytes:
+//   [kPassThreads x 8 code bytes: byte k of thread t = code of chunk t + k * kPassThreads]
+//   [256 x double2: the two values of a chunk]
+// so a thread fetches all its codes of a row with one 8-byte load.  The hash key of a chunk
+// is a 64-bit mix of its two values; every chunk is compared with the chunk that claimed its
+// slot afterwards, and a row with a key collision between different chunks simply stays dense.
+constexpr int kPairCodeBytes = kPassThreads * 8;
+constexpr int kPairRecBytes = kPairCodeBytes + kDictSize * 16;
+
+__device__ __forceinline__ unsigned long long pair_key(unsigned long long a, unsigned long long b) {
+    unsigned long long k = (a ^ (b << 29 | b >> 35)) * 0x9E3779B97F4A7C15ull;
+    k ^= b * 0xC2B2AE3D27D4EB4Full;
+    k ^= k >> 31;
+    return k == kDictEmpty ? 0x5851F42D4C957F2Dull : k;
+}
+
+__global__ void __launch_bounds__(kPackThreads)
+em_pack_pairs_kernel(const double *__restrict__ lin, int64_t n_rows, int64_t ld,
+                     const double *__restrict__ weights, unsigned char *__restrict__ rec,
+                     int *__restrict__ dense_flag, double *__restrict__ w_coded) {
+    __shared__ unsigned long long keys[kDictSlots];
+    __shared__ int rep[kDictSlots];            // the chunk that claimed the slot
+    __shared__ unsigned short ids[kDictSlots];
+    __shared__ int count;
+    __shared__ int clash;
+    extern __shared__ unsigned short chunk_slot[];   // [ld / 2] hash slot of every chunk
+    const int tid = threadIdx.x;
+    const int n_chunks = (int)(ld >> 1);
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        for (int i = tid; i < kDictSlots; i += kPackThreads) keys[i] = kDictEmpty;
+        if (tid == 0) { count = 0; clash = 0; }
+        __syncthreads();
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(lin + r * ld);
+        for (int c = tid; c < n_chunks; c += kPackThreads) {
+            if (*reinterpret_cast<volatile int *>(&count) > kDictSize) break;
+            const ulonglong2 ab = src[c];
+            const unsigned long long key = pair_key(ab.x, ab.y);
+            unsigned h = (unsigned)(key >> 54);
+            while (true) {
+                const unsigned long long old = atomicCAS(&keys[h], kDictEmpty, key);
+                if (old == kDictEmpty) {   // first sight of the key: next free code
+                    rep[h] = c;
+                    ids[h] = (unsigned short)atomicAdd(&count, 1);
+                    break;
+                }
+                if (old == key) break;
+                h = (h + 1) & (kDictSlots - 1);
+            }
+            chunk_slot[c] = (unsigned short)h;
+        }
+        __syncthreads();
+        bool coded = count <= kDictSize;   // block-uniform
+        if (coded) {
+            for (int c = tid; c < n_chunks; c += kPackThreads) {
+                const ulonglong2 ab = src[c], rp = src[rep[chunk_slot[c]]];
+                if (ab.x != rp.x || ab.y != rp.y) clash = 1;
+            }
+        }
+        __syncthreads();
+        coded = coded && clash == 0;
+        unsigned char *out = rec + r * (int64_t)kPairRecBytes;
+        for (int i = tid; i < kPairRecBytes / 8; i += kPackThreads)
+            reinterpret_cast<unsigned long long *>(out)[i] = 0ull;
+        __syncthreads();
+        if (coded) {
+            for (int c = tid; c < n_chunks; c += kPackThreads)
+                out[(c % kPassThreads) * 8 + c / kPassThreads] = (unsigned char)ids[chunk_slot[c]];
+            ulonglong2 *tab = reinterpret_cast<ulonglong2 *>(out + kPairCodeBytes);
+            for (int i = tid; i < kDictSlots; i += kPackThreads)
+                if (keys[i] != kDictEmpty) tab[ids[i]] = src[rep[i]];
+        }
+        if (tid == 0) {
+            dense_flag[r] = coded ? 0 : 1;
+            w_coded[r] = coded ? weights[r] : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
 // Positions of the dense rows, in row order (one block: deterministic, N / 1024 steps).
 __global__ void __launch_bounds__(1024)
 em_dense_list_kernel(const int *__restrict__ dense_flag, int64_t n_rows,
@@ -821,6 +905,188 @@ em_pass_coded_v2_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
         const int c = tid + k * THREADS;
+        if (c < n_chunks) {
+            if (accumulate) {
+                const double2 prev = out[c];
+                out[c] = make_double2(prev.x + tr[k].x, prev.y + tr[k].y);
+            } else {
+                out[c] = tr[k];
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
+}
+
+// The second loop version over chunk-coded records (em_pack_pairs_kernel): one 8-byte load
+// brings a thread's codes of a row, one 16-byte lookup the two values of a chunk.
+// Experimental, MXB_EM_CODED_PAIRS=1.
+template <int NC>
+__global__ void __launch_bounds__(kPassThreads, 1)
+em_pass_coded_pairs_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
+                    int64_t n_rows, const double *__restrict__ weights,
+                    const double *__restrict__ pi0, const double *__restrict__ pi1,
+                    EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
+                    int accumulate) {
+    static_assert(kPassGroup == 2 && kPassWarps == 16 && kMaxNC <= 8,
+                  "reduction layout below; a thread's codes of a row fit one 8-byte word");
+    pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *scratch = reinterpret_cast<double *>(
+        smem_raw + (((size_t)n_stages * row_bytes + 127) & ~(size_t)127));
+    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int n_my = (int)(r_end - r_begin);
+    const unsigned char *my_rows = rows + (size_t)r_begin * row_bytes;
+    const double *my_w = weights + r_begin;
+    const uint32_t stages_u32 = smem_u32(smem_raw);
+    const uint32_t full_u32 = smem_u32(full);
+
+    // Prologue: L and the weights do not depend on the previous iteration's tail, so the
+    // ring is primed before waiting for it (the loads overlap the tail kernel).
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 0; q < n_my && q < n_stages; ++q) {
+            mbar_expect_tx(&full[q], row_bytes);
+            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
+                      &full[q]);
+        }
+    }
+    pdl_wait();  // proportions and control block of the previous iteration are final
+    if (st->done) {
+        // finished run: the primed loads must land before this CTA's shared memory is released
+        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
+        return;
+    }
+    const double *__restrict__ pi = st->cur ? pi1 : pi0;
+
+    // Thread-private column slice: chunk c = tid + k*512 covers doubles 2c, 2c+1.
+    const int n_chunks = (int)(ld >> 1);
+    double2 pr[NC], tr[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int c = tid + k * kPassThreads;
+        pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
+        tr[k] = make_double2(0.0, 0.0);
+    }
+
+    int stage = 0;          // ring slot of row q0
+    uint32_t phase = 0;     // its mbarrier parity
+    int sbuf = 0;
+    int bad = 0;
+    const bool upper = lane >= 16;
+
+    // One group of rows between two block barriers: rows q0 and q0 + 1 (kBoth), or the last
+    // row alone when the CTA's row count is odd -- the loop over full pairs carries no
+    // "is there a second row" tests and no zero fills.  Both records are waited for before the
+    // lookups of either start, so the 4 NC table lookups of a thread are independent work.
+    auto step = [&](auto both_tag, const int q0) {
+        constexpr bool kBoth = decltype(both_tag)::value;
+        constexpr int G = kBoth ? 2 : 1;
+        double2 lv[G][NC];
+        double dot[G];
+        int s_of[G];
+        const double w_mine = (kBoth || !upper) ? my_w[q0 + (upper ? 1 : 0)] : 0.0;
+        int s = stage;
+        uint32_t ph = phase;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            s_of[g] = s;
+            mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
+            if (++s == n_stages) { s = 0; ph ^= 1u; }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const unsigned char *srec = smem_raw + (size_t)s_of[g] * row_bytes;
+            const uint2 cw = *reinterpret_cast<const uint2 *>(srec + tid * 8);   // this thread's codes
+            const unsigned char *tab = srec + kPairCodeBytes;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                // a chunk past the end of the row has code 0 and proportion 0: whatever the
+                // table holds there adds nothing to the dot product, and its column sum is
+                // never written
+                const unsigned word = (k < 4) ? cw.x : cw.y;
+                const unsigned off = ((word >> (8 * (k & 3))) & 0xFFu) << 4;
+                lv[g][k] = *reinterpret_cast<const double2 *>(tab + off);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            double dx = 0.0, dy = 0.0;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                dx = fma(lv[g][k].x, pr[k].x, dx);
+                dy = fma(lv[g][k].y, pr[k].y, dy);
+            }
+            dot[g] = dx + dy;
+        }
+        // both rows in one butterfly: lanes 0-15 end up with row 0, lanes 16-31 with row 1
+        const double dot1 = kBoth ? dot[G - 1] : 0.0;
+        double v = (upper ? dot1 : dot[0]) + shfl_xor_f64(upper ? dot[0] : dot1, 16);
+        v += shfl_xor_f64(v, 8);
+        v += shfl_xor_f64(v, 4);
+        v += shfl_xor_f64(v, 2);
+        v += shfl_xor_f64(v, 1);
+        double *sc = scratch + sbuf * (kPassWarps * kPassGroup);
+        if ((lane & 15) == 0) sc[(lane >> 4) * kPassWarps + warp] = v;
+        __syncthreads();  // all reads of this group's stages are done; warp totals visible
+        if (tid == 0) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int q = q0 + g + n_stages;
+                if (q < n_my) {
+                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_of[g];
+                    mbar_expect_tx_u32(bar, row_bytes);
+                    bulk_load_u32(stages_u32 + (uint32_t)s_of[g] * row_bytes,
+                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
+                }
+            }
+        }
+        // 16 warp totals per row sit in sc[0..15] / sc[16..31]: one value per lane
+        double t = sc[lane];
+        t += shfl_xor_f64(t, 8);
+        t += shfl_xor_f64(t, 4);
+        t += shfl_xor_f64(t, 2);
+        t += shfl_xor_f64(t, 1);
+        double coef_mine = 0.0;
+        if (w_mine != 0.0) {
+            coef_mine = w_mine / t;
+            bad |= (t == 0.0);
+        }
+        const double coef0 = __shfl_sync(0xffffffffu, coef_mine, 0);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            tr[k].x = fma(coef0, lv[0][k].x, tr[k].x);
+            tr[k].y = fma(coef0, lv[0][k].y, tr[k].y);
+        }
+        if (kBoth) {
+            const double coef1 = __shfl_sync(0xffffffffu, coef_mine, 16);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                tr[k].x = fma(coef1, lv[G - 1][k].x, tr[k].x);
+                tr[k].y = fma(coef1, lv[G - 1][k].y, tr[k].y);
+            }
+        }
+        stage = s;
+        phase = ph;
+        sbuf ^= 1;
+    };
+    int q0 = 0;
+    for (; q0 + 1 < n_my; q0 += kPassGroup) step(std::true_type{}, q0);
+    if (q0 < n_my) step(std::false_type{}, q0);
+
+    double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int c = tid + k * kPassThreads;
         if (c < n_chunks) {
             if (accumulate) {
                 const double2 prev = out[c];
@@ -1641,6 +1907,7 @@ struct mxb_em {
     // Dictionary-coded rows (em_pack_kernel): when `coded` the pass reads `rec` (all rows,
     // dense rows as empty records) and `dense_lin` (the gathered dense rows) instead of `lin`.
     bool coded = false;
+    bool coded_pairs = false;         // records hold chunk dictionaries (em_pack_pairs_kernel)
     unsigned char *rec = nullptr;     // [n_rows][rec_bytes]
     size_t rec_bytes = 0;
     double *w_coded = nullptr;        // [n_rows] weight, 0 for dense rows
@@ -1681,7 +1948,20 @@ struct CodedPass {
     pass_fn fn;
     int threads;
 };
-static CodedPass pick_pass_coded(int nc, int64_t ld) {
+static CodedPass pick_pass_coded(int nc, int64_t ld, bool pairs) {
+    if (pairs) {
+        switch (nc) {
+            case 1: return {em_pass_coded_pairs_kernel<1>, kPassThreads};
+            case 2: return {em_pass_coded_pairs_kernel<2>, kPassThreads};
+            case 3: return {em_pass_coded_pairs_kernel<3>, kPassThreads};
+            case 4: return {em_pass_coded_pairs_kernel<4>, kPassThreads};
+            case 5: return {em_pass_coded_pairs_kernel<5>, kPassThreads};
+            case 6: return {em_pass_coded_pairs_kernel<6>, kPassThreads};
+            case 7: return {em_pass_coded_pairs_kernel<7>, kPassThreads};
+            case 8: return {em_pass_coded_pairs_kernel<8>, kPassThreads};
+        }
+        return {nullptr, 0};
+    }
     static const bool v3 = getenv("MXB_EM_CODED_V3") != nullptr;
     static const bool t384 = getenv("MXB_EM_CODED_T384") != nullptr;
     static const bool v2 = getenv("MXB_EM_CODED_V1") == nullptr;
@@ -1802,7 +2082,7 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
                                 em->n_stages, 0));
             ctx->launches += 1;
         }
-        const CodedPass cp = pick_pass_coded(em->nc, em->ld);
+        const CodedPass cp = pick_pass_coded(em->nc, em->ld, em->coded_pairs);
         MXB_CUDA(launch_pdl(cp.fn, dim3(em->grid_fast), dim3(cp.threads),
                             em->coded_smem, s, (const unsigned char *)em->rec,
                             (uint32_t)em->rec_bytes, em->ld, em->n_rows, em->w_coded, em->pi[0],
@@ -1925,7 +2205,10 @@ static int em_pack_rows(mxb_em *em) {
     mxb_ctx *ctx = em->ctx;
     if (!em->fast || em->n_slots != 1 || em->n_rows == 0 || getenv("MXB_EM_NO_PACK")) return MXB_OK;
     const size_t row_bytes = (size_t)em->ld * sizeof(double);
-    const size_t rec_bytes = (size_t)em->ld + kDictSize * sizeof(double);
+    // MXB_EM_CODED_PAIRS=1 (experimental): dictionaries of cell pairs, see em_pack_pairs_kernel
+    const bool pairs = getenv("MXB_EM_CODED_PAIRS") != nullptr && em->nc <= 8;
+    const size_t rec_bytes = pairs ? (size_t)kPairRecBytes
+                                   : (size_t)em->ld + kDictSize * sizeof(double);
     constexpr int kMaxCodedStages = 16;
     const size_t fixed = 2 * kPassWarps * kPassGroup * sizeof(double) +
                          kMaxCodedStages * sizeof(uint64_t) + 256;
@@ -1951,8 +2234,13 @@ static int em_pack_rows(mxb_em *em) {
     int64_t n_dense = 0;
     double *dense = nullptr;
     const int grid = (int)std::min<int64_t>(em->n_rows, (int64_t)ctx->num_sms * 8);
-    em_pack_kernel<<<grid, kPackThreads, (size_t)em->ld * sizeof(unsigned short), ctx->stream>>>(
-        em->lin, em->n_rows, em->ld, em->weights, rec, (int64_t)rec_bytes, flag, w_coded);
+    if (pairs)
+        em_pack_pairs_kernel<<<grid, kPackThreads, (size_t)(em->ld / 2) * sizeof(unsigned short),
+                               ctx->stream>>>(em->lin, em->n_rows, em->ld, em->weights, rec, flag,
+                                              w_coded);
+    else
+        em_pack_kernel<<<grid, kPackThreads, (size_t)em->ld * sizeof(unsigned short), ctx->stream>>>(
+            em->lin, em->n_rows, em->ld, em->weights, rec, (int64_t)rec_bytes, flag, w_coded);
     em_dense_list_kernel<<<1, 1024, 0, ctx->stream>>>(flag, em->n_rows, list, d_count);
     ctx->launches += 2;
     e = cudaGetLastError();
@@ -1976,7 +2264,7 @@ static int em_pack_rows(mxb_em *em) {
         }
     }
     if (e == cudaSuccess && worth)
-        e = cudaFuncSetAttribute((const void *)pick_pass_coded(em->nc, em->ld).fn,
+        e = cudaFuncSetAttribute((const void *)pick_pass_coded(em->nc, em->ld, pairs).fn,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)stages * rec_bytes + fixed));
     dev_free(ctx, tmp);
@@ -1991,6 +2279,7 @@ static int em_pack_rows(mxb_em *em) {
         return MXB_OK;
     }
     em->coded = true;
+    em->coded_pairs = pairs;
     em->rec = rec;
     em->rec_bytes = rec_bytes;
     em->w_coded = w_coded;

@@ -7,8 +7,8 @@ Variants are selected by environment flags that csrc/em.cu reads once per proces
 variant synchronises through mbarriers and has not run on a GPU yet; a deadlock must not
 take the box down.  Prints ms per iteration, ms per pass and the largest difference of the
 log-proportions after the iterations against the default variant (v1, v2 and v3 add the
-same numbers in the same order: expected 0; t384 maps columns to threads differently:
-expected ~1e-15).
+same numbers in the same order: expected 0; t384 maps columns to threads differently and
+`pairs` codes a slightly different set of rows: expected ~1e-15).
 """
 import ctypes
 import json
@@ -25,6 +25,7 @@ VARIANTS = [("v2 (default)", {}),
             ("v1", {"MXB_EM_CODED_V1": "1"}),
             ("v3 pipelined", {"MXB_EM_CODED_V3": "1"}),
             ("v2 384 threads", {"MXB_EM_CODED_T384": "1"}),
+            ("pairs (chunk dictionary)", {"MXB_EM_CODED_PAIRS": "1"}),
             ("fp64 rows", {"MXB_EM_NO_PACK": "1"})]
 
 
@@ -66,21 +67,22 @@ def main():
     for name, env in VARIANTS:
         out = os.path.join(ROOT, "gpurun_out", "variant_%s.npy" % name.split()[0])
         e = dict(os.environ)
-        for k in ("MXB_EM_CODED_V1", "MXB_EM_CODED_V3", "MXB_EM_CODED_T384", "MXB_EM_NO_PACK"):
+        for k in ("MXB_EM_CODED_V1", "MXB_EM_CODED_V3", "MXB_EM_CODED_T384", "MXB_EM_CODED_PAIRS",
+                  "MXB_EM_NO_PACK"):
             e.pop(k, None)
         e.update(env)
         cmd = ["timeout", "120", sys.executable, os.path.abspath(__file__), "--child", frags, iters,
                out]
         r = subprocess.run(cmd, env=e, capture_output=True, text=True)
         if r.returncode != 0:
-            print("%-16s FAILED rc=%d %s" % (name, r.returncode, r.stderr.strip()[-300:]))
+            print("%-26s FAILED rc=%d %s" % (name, r.returncode, r.stderr.strip()[-300:]))
             continue
         info = json.loads(r.stdout.strip().splitlines()[-1])
         lnp = np.load(out)
         if ref is None:
             ref = lnp
         live = np.isfinite(ref) & np.isfinite(lnp)
-        print("%-16s %.4f ms per iteration, %.4f ms per pass, max |d ln pi| vs default %.3g"
+        print("%-26s %.4f ms per iteration, %.4f ms per pass, max |d ln pi| vs default %.3g"
               % (name, info["ms_per_iteration"], info["ms_per_pass"],
                  float(np.abs(lnp[live] - ref[live]).max())))
 
