@@ -256,14 +256,17 @@ em_pack_kernel(const double *__restrict__ lin, int64_t n_rows, int64_t ld,
 // instead of single cells.  91.6 % of the config-2 rows have at most 256 distinct chunks
 // (92.4 % have at most 256 distinct cells: scripts/analysis/pair_codes.py), so about the same
 // rows stay coded, and a chunk costs the pass one table lookup (LDS.128) instead of two
-// (LDS.64) and half the index arithmetic.  Record of row r, kPairRecBytes at r * kPairRecBytes:
-//   [kPassThreads x 8 code bytes: byte k of thread t = code of chunk t + k * kPassThreads]
+// (LDS.64) and half the index arithmetic.  Record of row r, pair_rec_bytes(T) bytes:
+//   [T x 8 code bytes: byte k of thread t = code of chunk t + k * T]   (T = threads of the pass)
 //   [256 x double2: the two values of a chunk]
 // so a thread fetches all its codes of a row with one 8-byte load.  The hash key of a chunk
 // is a 64-bit mix of its two values; every chunk is compared with the chunk that claimed its
 // slot afterwards, and a row with a key collision between different chunks simply stays dense.
-constexpr int kPairCodeBytes = kPassThreads * 8;
-constexpr int kPairRecBytes = kPairCodeBytes + kDictSize * 16;
+constexpr int kPairTableBytes = kDictSize * 16;
+// record bytes for a pass kernel of `pass_threads` threads: 8 code bytes per thread + the table
+__host__ __device__ constexpr int pair_rec_bytes(int pass_threads) {
+    return pass_threads * 8 + kPairTableBytes;
+}
 
 __device__ __forceinline__ unsigned long long pair_key(unsigned long long a, unsigned long long b) {
     unsigned long long k = (a ^ (b << 29 | b >> 35)) * 0x9E3779B97F4A7C15ull;
@@ -275,7 +278,8 @@ __device__ __forceinline__ unsigned long long pair_key(unsigned long long a, uns
 __global__ void __launch_bounds__(kPackThreads)
 em_pack_pairs_kernel(const double *__restrict__ lin, int64_t n_rows, int64_t ld,
                      const double *__restrict__ weights, unsigned char *__restrict__ rec,
-                     int *__restrict__ dense_flag, double *__restrict__ w_coded) {
+                     int pass_threads, int *__restrict__ dense_flag, double *__restrict__ w_coded) {
+    const int rec_bytes = pair_rec_bytes(pass_threads);
     __shared__ unsigned long long keys[kDictSlots];
     __shared__ int rep[kDictSlots];            // the chunk that claimed the slot
     __shared__ unsigned short ids[kDictSlots];
@@ -316,14 +320,14 @@ em_pack_pairs_kernel(const double *__restrict__ lin, int64_t n_rows, int64_t ld,
         }
         __syncthreads();
         coded = coded && clash == 0;
-        unsigned char *out = rec + r * (int64_t)kPairRecBytes;
-        for (int i = tid; i < kPairRecBytes / 8; i += kPackThreads)
+        unsigned char *out = rec + r * (int64_t)rec_bytes;
+        for (int i = tid; i < rec_bytes / 8; i += kPackThreads)
             reinterpret_cast<unsigned long long *>(out)[i] = 0ull;
         __syncthreads();
         if (coded) {
             for (int c = tid; c < n_chunks; c += kPackThreads)
-                out[(c % kPassThreads) * 8 + c / kPassThreads] = (unsigned char)ids[chunk_slot[c]];
-            ulonglong2 *tab = reinterpret_cast<ulonglong2 *>(out + kPairCodeBytes);
+                out[(c % pass_threads) * 8 + c / pass_threads] = (unsigned char)ids[chunk_slot[c]];
+            ulonglong2 *tab = reinterpret_cast<ulonglong2 *>(out + pass_threads * 8);
             for (int i = tid; i < kDictSlots; i += kPackThreads)
                 if (keys[i] != kDictEmpty) tab[ids[i]] = src[rep[i]];
         }
@@ -920,15 +924,15 @@ em_pass_coded_v2_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
 // The second loop version over chunk-coded records (em_pack_pairs_kernel): one 8-byte load
 // brings a thread's codes of a row, one 16-byte lookup the two values of a chunk.
 // Experimental, MXB_EM_CODED_PAIRS=1.
-template <int NC>
-__global__ void __launch_bounds__(kPassThreads, 1)
+template <int NC, int THREADS = kPassThreads>
+__global__ void __launch_bounds__(THREADS, 1)
 em_pass_coded_pairs_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
                     int64_t n_rows, const double *__restrict__ weights,
                     const double *__restrict__ pi0, const double *__restrict__ pi1,
                     EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
                     int accumulate) {
-    static_assert(kPassGroup == 2 && kPassWarps == 16 && kMaxNC <= 8,
-                  "reduction layout below; a thread's codes of a row fit one 8-byte word");
+    static_assert(kPassGroup == 2 && THREADS % 32 == 0 && THREADS <= kPassThreads && NC <= 8,
+                  "at most 16 warp totals per row; a thread's codes of a row fit one 8-byte word");
     pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -960,6 +964,9 @@ em_pass_coded_pairs_kernel(const unsigned char *__restrict__ rows, uint32_t row_
                       &full[q]);
         }
     }
+    // totals slots of the warps a smaller CTA does not have (read by the 16-lane butterfly)
+    if (THREADS < kPassThreads && tid < 2 * kPassWarps * kPassGroup && (tid & 15) >= THREADS / 32)
+        scratch[tid] = 0.0;
     pdl_wait();  // proportions and control block of the previous iteration are final
     if (st->done) {
         // finished run: the primed loads must land before this CTA's shared memory is released
@@ -973,7 +980,7 @@ em_pass_coded_pairs_kernel(const unsigned char *__restrict__ rows, uint32_t row_
     double2 pr[NC], tr[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * kPassThreads;
+        const int c = tid + k * THREADS;
         pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
         tr[k] = make_double2(0.0, 0.0);
     }
@@ -1005,9 +1012,12 @@ em_pass_coded_pairs_kernel(const unsigned char *__restrict__ rows, uint32_t row_
         }
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const unsigned char *srec = smem_raw + (size_t)s_of[g] * row_bytes;
-            const uint2 cw = *reinterpret_cast<const uint2 *>(srec + tid * 8);   // this thread's codes
-            const unsigned char *tab = srec + kPairCodeBytes;
+            // 32-bit shared-window addresses: record base (warp-uniform) + per-thread offset
+            const uint32_t rec_u32 = stages_u32 + (uint32_t)s_of[g] * row_bytes;
+            uint2 cw;   // this thread's codes of the row
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(cw.x), "=r"(cw.y) : "r"(rec_u32 + (uint32_t)tid * 8u) : "memory");
+            const uint32_t tab_u32 = rec_u32 + (uint32_t)(THREADS * 8);
 #pragma unroll
             for (int k = 0; k < NC; ++k) {
                 // a chunk past the end of the row has code 0 and proportion 0: whatever the
@@ -1015,7 +1025,8 @@ em_pass_coded_pairs_kernel(const unsigned char *__restrict__ rows, uint32_t row_
                 // never written
                 const unsigned word = (k < 4) ? cw.x : cw.y;
                 const unsigned off = ((word >> (8 * (k & 3))) & 0xFFu) << 4;
-                lv[g][k] = *reinterpret_cast<const double2 *>(tab + off);
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                             : "=d"(lv[g][k].x), "=d"(lv[g][k].y) : "r"(tab_u32 + off) : "memory");
             }
         }
 #pragma unroll
@@ -1086,7 +1097,7 @@ em_pass_coded_pairs_kernel(const unsigned char *__restrict__ rows, uint32_t row_
     double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * kPassThreads;
+        const int c = tid + k * THREADS;
         if (c < n_chunks) {
             if (accumulate) {
                 const double2 prev = out[c];
@@ -1907,7 +1918,8 @@ struct mxb_em {
     // Dictionary-coded rows (em_pack_kernel): when `coded` the pass reads `rec` (all rows,
     // dense rows as empty records) and `dense_lin` (the gathered dense rows) instead of `lin`.
     bool coded = false;
-    bool coded_pairs = false;         // records hold chunk dictionaries (em_pack_pairs_kernel)
+    int pair_threads = 0;             // != 0: records hold chunk dictionaries laid out for a pass
+                                      // kernel of that many threads (em_pack_pairs_kernel)
     unsigned char *rec = nullptr;     // [n_rows][rec_bytes]
     size_t rec_bytes = 0;
     double *w_coded = nullptr;        // [n_rows] weight, 0 for dense rows
@@ -1948,8 +1960,21 @@ struct CodedPass {
     pass_fn fn;
     int threads;
 };
-static CodedPass pick_pass_coded(int nc, int64_t ld, bool pairs) {
-    if (pairs) {
+static CodedPass pick_pass_coded(int nc, int64_t ld, int pair_threads) {
+    if (pair_threads == 384) {
+        switch ((int)ceil_div(ld / 2, 384)) {
+            case 1: return {em_pass_coded_pairs_kernel<1, 384>, 384};
+            case 2: return {em_pass_coded_pairs_kernel<2, 384>, 384};
+            case 3: return {em_pass_coded_pairs_kernel<3, 384>, 384};
+            case 4: return {em_pass_coded_pairs_kernel<4, 384>, 384};
+            case 5: return {em_pass_coded_pairs_kernel<5, 384>, 384};
+            case 6: return {em_pass_coded_pairs_kernel<6, 384>, 384};
+            case 7: return {em_pass_coded_pairs_kernel<7, 384>, 384};
+            case 8: return {em_pass_coded_pairs_kernel<8, 384>, 384};
+        }
+        return {nullptr, 0};
+    }
+    if (pair_threads != 0) {
         switch (nc) {
             case 1: return {em_pass_coded_pairs_kernel<1>, kPassThreads};
             case 2: return {em_pass_coded_pairs_kernel<2>, kPassThreads};
@@ -2082,7 +2107,7 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
                                 em->n_stages, 0));
             ctx->launches += 1;
         }
-        const CodedPass cp = pick_pass_coded(em->nc, em->ld, em->coded_pairs);
+        const CodedPass cp = pick_pass_coded(em->nc, em->ld, em->pair_threads);
         MXB_CUDA(launch_pdl(cp.fn, dim3(em->grid_fast), dim3(cp.threads),
                             em->coded_smem, s, (const unsigned char *)em->rec,
                             (uint32_t)em->rec_bytes, em->ld, em->n_rows, em->w_coded, em->pi[0],
@@ -2206,8 +2231,13 @@ static int em_pack_rows(mxb_em *em) {
     if (!em->fast || em->n_slots != 1 || em->n_rows == 0 || getenv("MXB_EM_NO_PACK")) return MXB_OK;
     const size_t row_bytes = (size_t)em->ld * sizeof(double);
     // MXB_EM_CODED_PAIRS=1 (experimental): dictionaries of cell pairs, see em_pack_pairs_kernel
-    const bool pairs = getenv("MXB_EM_CODED_PAIRS") != nullptr && em->nc <= 8;
-    const size_t rec_bytes = pairs ? (size_t)kPairRecBytes
+    // (with MXB_EM_CODED_T384=1 laid out for the 384-thread pass kernel where the row fits it)
+    int pair_threads = 0;
+    if (getenv("MXB_EM_CODED_PAIRS") != nullptr && em->nc <= 8)
+        pair_threads = (getenv("MXB_EM_CODED_T384") != nullptr && ceil_div(em->ld / 2, 384) <= 8)
+                           ? 384 : kPassThreads;
+    const bool pairs = pair_threads != 0;
+    const size_t rec_bytes = pairs ? (size_t)pair_rec_bytes(pair_threads)
                                    : (size_t)em->ld + kDictSize * sizeof(double);
     constexpr int kMaxCodedStages = 16;
     const size_t fixed = 2 * kPassWarps * kPassGroup * sizeof(double) +
@@ -2236,8 +2266,8 @@ static int em_pack_rows(mxb_em *em) {
     const int grid = (int)std::min<int64_t>(em->n_rows, (int64_t)ctx->num_sms * 8);
     if (pairs)
         em_pack_pairs_kernel<<<grid, kPackThreads, (size_t)(em->ld / 2) * sizeof(unsigned short),
-                               ctx->stream>>>(em->lin, em->n_rows, em->ld, em->weights, rec, flag,
-                                              w_coded);
+                               ctx->stream>>>(em->lin, em->n_rows, em->ld, em->weights, rec,
+                                              pair_threads, flag, w_coded);
     else
         em_pack_kernel<<<grid, kPackThreads, (size_t)em->ld * sizeof(unsigned short), ctx->stream>>>(
             em->lin, em->n_rows, em->ld, em->weights, rec, (int64_t)rec_bytes, flag, w_coded);
@@ -2264,7 +2294,7 @@ static int em_pack_rows(mxb_em *em) {
         }
     }
     if (e == cudaSuccess && worth)
-        e = cudaFuncSetAttribute((const void *)pick_pass_coded(em->nc, em->ld, pairs).fn,
+        e = cudaFuncSetAttribute((const void *)pick_pass_coded(em->nc, em->ld, pair_threads).fn,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)stages * rec_bytes + fixed));
     dev_free(ctx, tmp);
@@ -2279,7 +2309,7 @@ static int em_pack_rows(mxb_em *em) {
         return MXB_OK;
     }
     em->coded = true;
-    em->coded_pairs = pairs;
+    em->pair_threads = pair_threads;
     em->rec = rec;
     em->rec_bytes = rec_bytes;
     em->w_coded = w_coded;

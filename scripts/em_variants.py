@@ -26,6 +26,7 @@ VARIANTS = [("v2 (default)", {}),
             ("v3 pipelined", {"MXB_EM_CODED_V3": "1"}),
             ("v2 384 threads", {"MXB_EM_CODED_T384": "1"}),
             ("pairs (chunk dictionary)", {"MXB_EM_CODED_PAIRS": "1"}),
+            ("pairs, 384 threads", {"MXB_EM_CODED_PAIRS": "1", "MXB_EM_CODED_T384": "1"}),
             ("fp64 rows", {"MXB_EM_NO_PACK": "1"})]
 
 
@@ -65,7 +66,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     ref = None
     for name, env in VARIANTS:
-        out = os.path.join(ROOT, "gpurun_out", "variant_%s.npy" % name.split()[0])
+        out = os.path.join(ROOT, "gpurun_out", "variant_%d.npy" % VARIANTS.index((name, env)))
         e = dict(os.environ)
         for k in ("MXB_EM_CODED_V1", "MXB_EM_CODED_V3", "MXB_EM_CODED_T384", "MXB_EM_CODED_PAIRS",
                   "MXB_EM_NO_PACK"):
