@@ -1307,7 +1307,7 @@ em_pass_coded_v3_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
 // from shared memory twice -- once for the two dot products, once for the two
 // column-sum updates -- and a second block barrier per row pair releases the stages.
 // The four (row, restart) dot products of a row pair ride one butterfly.
-template <int NC>
+template <int NC, bool kAccumulate = false>
 __global__ void __launch_bounds__(kPassThreads, 1)
 em_pass_pair_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
                     const double *__restrict__ weights, const double *__restrict__ pi_a0,
@@ -1444,6 +1444,196 @@ em_pass_pair_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
                         tb[k].x = fma(cb, l.x, tb[k].x);
                         tb[k].y = fma(cb, l.y, tb[k].y);
                     }
+                }
+            }
+        }
+        __syncthreads();  // both staged rows have been read twice: release them
+        if (tid == 0) {
+#pragma unroll
+            for (int g = 0; g < kPassGroup; ++g) {
+                const int q = q0 + g + n_stages;
+                if (q < n_my) {
+                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_of[g];
+                    mbar_expect_tx_u32(bar, row_bytes);
+                    bulk_load_u32(stages_u32 + (uint32_t)s_of[g] * row_bytes,
+                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
+                }
+            }
+        }
+        stage = s;
+        phase = ph;
+    }
+
+    double2 *out_a = reinterpret_cast<double2 *>(partials_a + (size_t)blockIdx.x * ld);
+    double2 *out_b = reinterpret_cast<double2 *>(partials_b + (size_t)blockIdx.x * ld);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int c = tid + k * kPassThreads;
+        if (c < n_chunks) {
+            if (kAccumulate) {   // on top of what the launch before this one left (coded sessions)
+                const double2 qa = out_a[c], qb = out_b[c];
+                out_a[c] = make_double2(qa.x + ta[k].x, qa.y + ta[k].y);
+                out_b[c] = make_double2(qb.x + tb[k].x, qb.y + tb[k].y);
+            } else {
+                out_a[c] = ta[k];
+                out_b[c] = tb[k];
+            }
+        }
+    }
+    if (bad) atomicOr(&st[(q4 & 1)].bad, 1);
+}
+
+// Two restarts per read of the chunk-coded records (em_pack_pairs_kernel, 512-thread layout):
+// em_pass_pair_kernel with the two values of a chunk looked up in the row's table, in both
+// sweeps over a staged row.  Writes the column sums; the fp64 pair pass over the dense rows
+// (em_pass_pair_kernel<NC, true>) adds its own afterwards.  Experimental, MXB_EM_CODED_PAIRS=1.
+template <int NC>
+__global__ void __launch_bounds__(kPassThreads, 1)
+em_pass_pair_coded_kernel(const unsigned char *__restrict__ rec, int64_t ld, int64_t n_rows,
+                    const double *__restrict__ weights, const double *__restrict__ pi_a0,
+                    const double *__restrict__ pi_a1, const double *__restrict__ pi_b0,
+                    const double *__restrict__ pi_b1, EmState *__restrict__ st,
+                    double *__restrict__ partials_a, double *__restrict__ partials_b,
+                    int n_stages) {
+    static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
+    pdl_launch_dependents();
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr uint32_t row_bytes = (uint32_t)pair_rec_bytes(kPassThreads);
+    double *scratch = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * row_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int n_my = (int)(r_end - r_begin);
+    const unsigned char *my_rows = rec + (size_t)r_begin * row_bytes;
+    const double *my_w = weights + r_begin;
+    const uint32_t stages_u32 = smem_u32(smem_raw);
+    const uint32_t full_u32 = smem_u32(full);
+
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 0; q < n_my && q < n_stages; ++q) {
+            mbar_expect_tx(&full[q], row_bytes);
+            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
+                      &full[q]);
+        }
+    }
+
+    pdl_wait();
+    const int done_a = st[0].done, done_b = st[1].done;
+    if (done_a && done_b) {
+        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
+        return;
+    }
+    const double *__restrict__ pia = st[0].cur ? pi_a1 : pi_a0;
+    const double *__restrict__ pib = st[1].cur ? pi_b1 : pi_b0;
+
+    const int n_chunks = (int)(ld >> 1);
+    double2 pa[NC], pb[NC], ta[NC], tb[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int c = tid + k * kPassThreads;
+        const bool in = c < n_chunks;
+        pa[k] = in ? reinterpret_cast<const double2 *>(pia)[c] : make_double2(0.0, 0.0);
+        pb[k] = in ? reinterpret_cast<const double2 *>(pib)[c] : make_double2(0.0, 0.0);
+        ta[k] = make_double2(0.0, 0.0);
+        tb[k] = make_double2(0.0, 0.0);
+    }
+
+    int stage = 0;
+    uint32_t phase = 0;
+    int bad = 0;
+    // quarter q4 = lane >> 3 owns pair (row g = q4 >> 1, restart = q4 & 1) after the butterfly
+    const int q4 = lane >> 3;
+    const bool mine_done = (q4 & 1) ? done_b != 0 : done_a != 0;
+    for (int q0 = 0; q0 < n_my; q0 += kPassGroup) {
+        const int q_mine = q0 + (q4 >> 1);
+        const double w_mine = (q_mine < n_my) ? my_w[q_mine] : 0.0;
+        int s_of[kPassGroup];
+        double d[4];  // [row][restart]
+        int s = stage;
+        uint32_t ph = phase;
+#pragma unroll
+        for (int g = 0; g < kPassGroup; ++g) {
+            s_of[g] = s;
+            double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+            if (q0 + g < n_my) {
+                mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
+                const uint32_t rec_u32 = stages_u32 + (uint32_t)s * row_bytes;
+                uint2 cw;   // this thread's chunk codes of the row
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(cw.x), "=r"(cw.y) : "r"(rec_u32 + (uint32_t)tid * 8u) : "memory");
+                const uint32_t tab_u32 = rec_u32 + (uint32_t)(kPassThreads * 8);
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    // a chunk past the end of the row has code 0 and proportions 0
+                    const unsigned word = (k < 4) ? cw.x : cw.y;
+                    const unsigned off = ((word >> (8 * (k & 3))) & 0xFFu) << 4;
+                    double2 l;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                                 : "=d"(l.x), "=d"(l.y) : "r"(tab_u32 + off) : "memory");
+                    ax = fma(l.x, pa[k].x, ax);
+                    ay = fma(l.y, pa[k].y, ay);
+                    bx = fma(l.x, pb[k].x, bx);
+                    by = fma(l.y, pb[k].y, by);
+                }
+            }
+            d[2 * g] = ax + ay;
+            d[2 * g + 1] = bx + by;
+            if (++s == n_stages) { s = 0; ph ^= 1u; }
+        }
+        // four sums in one butterfly: halves keep a row, quarters keep a restart
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        double e0 = (up16 ? d[2] : d[0]) + shfl_xor_f64(up16 ? d[0] : d[2], 16);
+        double e1 = (up16 ? d[3] : d[1]) + shfl_xor_f64(up16 ? d[1] : d[3], 16);
+        double v = (up8 ? e1 : e0) + shfl_xor_f64(up8 ? e0 : e1, 8);
+        v += shfl_xor_f64(v, 4);
+        v += shfl_xor_f64(v, 2);
+        v += shfl_xor_f64(v, 1);
+        // scratch[pair q4][warp]; the loop's second barrier separates consecutive groups
+        if ((lane & 7) == 0) scratch[q4 * kPassWarps + warp] = v;
+        __syncthreads();
+        // 16 warp totals per pair: lane reads two of them, 3-step butterfly inside its quarter
+        double t = scratch[q4 * kPassWarps + (lane & 7)] + scratch[q4 * kPassWarps + 8 + (lane & 7)];
+        t += shfl_xor_f64(t, 4);
+        t += shfl_xor_f64(t, 2);
+        t += shfl_xor_f64(t, 1);
+        double coef_mine = 0.0;
+        if (w_mine != 0.0) {
+            coef_mine = w_mine / t;
+            bad |= (t == 0.0 && !mine_done);
+        }
+        const double c0a = __shfl_sync(0xffffffffu, coef_mine, 0);
+        const double c0b = __shfl_sync(0xffffffffu, coef_mine, 8);
+        const double c1a = __shfl_sync(0xffffffffu, coef_mine, 16);
+        const double c1b = __shfl_sync(0xffffffffu, coef_mine, 24);
+#pragma unroll
+        for (int g = 0; g < kPassGroup; ++g) {
+            if (q0 + g < n_my) {
+                const double ca = g ? c1a : c0a, cb = g ? c1b : c0b;
+                const uint32_t rec_u32 = stages_u32 + (uint32_t)s_of[g] * row_bytes;
+                uint2 cw;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(cw.x), "=r"(cw.y) : "r"(rec_u32 + (uint32_t)tid * 8u) : "memory");
+                const uint32_t tab_u32 = rec_u32 + (uint32_t)(kPassThreads * 8);
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    const unsigned word = (k < 4) ? cw.x : cw.y;
+                    const unsigned off = ((word >> (8 * (k & 3))) & 0xFFu) << 4;
+                    double2 l;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                                 : "=d"(l.x), "=d"(l.y) : "r"(tab_u32 + off) : "memory");
+                    ta[k].x = fma(ca, l.x, ta[k].x);
+                    ta[k].y = fma(ca, l.y, ta[k].y);
+                    tb[k].x = fma(cb, l.x, tb[k].x);
+                    tb[k].y = fma(cb, l.y, tb[k].y);
                 }
             }
         }
@@ -2051,6 +2241,32 @@ static pair_fn pick_pair(int nc) {
     }
     return nullptr;
 }
+// the fp64 pair pass adding its column sums to what the coded pair pass left (dense rows)
+static pair_fn pick_pair_accumulate(int nc) {
+    switch (nc) {
+        case 1: return em_pass_pair_kernel<1, true>;
+        case 2: return em_pass_pair_kernel<2, true>;
+        case 3: return em_pass_pair_kernel<3, true>;
+        case 4: return em_pass_pair_kernel<4, true>;
+        case 5: return em_pass_pair_kernel<5, true>;
+        case 6: return em_pass_pair_kernel<6, true>;
+    }
+    return nullptr;
+}
+typedef void (*pair_coded_fn)(const unsigned char *, int64_t, int64_t, const double *,
+                              const double *, const double *, const double *, const double *,
+                              EmState *, double *, double *, int);
+static pair_coded_fn pick_pair_coded(int nc) {
+    switch (nc) {
+        case 1: return em_pass_pair_coded_kernel<1>;
+        case 2: return em_pass_pair_coded_kernel<2>;
+        case 3: return em_pass_pair_coded_kernel<3>;
+        case 4: return em_pass_pair_coded_kernel<4>;
+        case 5: return em_pass_pair_coded_kernel<5>;
+        case 6: return em_pass_pair_coded_kernel<6>;
+    }
+    return nullptr;
+}
 constexpr int kMaxPairNC = 6;   // 2 restarts x (pi + T) x NC double2 must fit 128 registers
 constexpr int kMaxSlots = 2;
 
@@ -2082,11 +2298,29 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
     if (pass_begin) MXB_CUDA(cudaEventRecord(pass_begin, s));
     if (em->n_slots == 2) {
         const size_t ps = (size_t)em->n_part * em->ld;
-        MXB_CUDA(launch_pdl(pick_pair(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
-                            em->smem_bytes, s, em->lin, em->ld, em->n_rows, em->weights,
-                            em->pi[0], em->pi[1], em->pi[0] + em->ld, em->pi[1] + em->ld,
-                            em->state, em->partials, em->partials + ps, em->n_stages));
-        ctx->launches += 1;
+        if (em->coded) {
+            // chunk-coded records of all rows, then the fp64 rows of the dense ones on top
+            MXB_CUDA(launch_pdl(pick_pair_coded(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
+                                em->coded_smem, s, (const unsigned char *)em->rec, em->ld,
+                                em->n_rows, em->w_coded, em->pi[0], em->pi[1], em->pi[0] + em->ld,
+                                em->pi[1] + em->ld, em->state, em->partials, em->partials + ps,
+                                em->coded_stages));
+            ctx->launches += 1;
+            if (em->n_dense > 0) {
+                MXB_CUDA(launch_pdl(pick_pair_accumulate(em->nc), dim3(em->grid_fast),
+                                    dim3(kPassThreads), em->smem_bytes, s, em->dense_lin, em->ld,
+                                    em->n_dense, em->w_dense, em->pi[0], em->pi[1],
+                                    em->pi[0] + em->ld, em->pi[1] + em->ld, em->state,
+                                    em->partials, em->partials + ps, em->n_stages));
+                ctx->launches += 1;
+            }
+        } else {
+            MXB_CUDA(launch_pdl(pick_pair(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
+                                em->smem_bytes, s, em->lin, em->ld, em->n_rows, em->weights,
+                                em->pi[0], em->pi[1], em->pi[0] + em->ld, em->pi[1] + em->ld,
+                                em->state, em->partials, em->partials + ps, em->n_stages));
+            ctx->launches += 1;
+        }
         if (pass_end) MXB_CUDA(cudaEventRecord(pass_end, s));
         P2PArgs pa;
         memset(&pa, 0, sizeof(pa));
@@ -2228,14 +2462,19 @@ __global__ void em_reset_state_kernel(EmState *st, long long max_iter, double to
 // stays as it is.  MXB_EM_NO_PACK=1 keeps the fp64 rows (cross-check).
 static int em_pack_rows(mxb_em *em) {
     mxb_ctx *ctx = em->ctx;
-    if (!em->fast || em->n_slots != 1 || em->n_rows == 0 || getenv("MXB_EM_NO_PACK")) return MXB_OK;
+    if (!em->fast || em->n_rows == 0 || getenv("MXB_EM_NO_PACK")) return MXB_OK;
+    // restart pairs read fp64 rows unless the chunk dictionary is asked for (experimental)
+    const bool two_slots = em->n_slots == 2;
+    if (two_slots && getenv("MXB_EM_CODED_PAIRS") == nullptr) return MXB_OK;
+    if (em->n_slots > 2) return MXB_OK;
     const size_t row_bytes = (size_t)em->ld * sizeof(double);
     // MXB_EM_CODED_PAIRS=1 (experimental): dictionaries of cell pairs, see em_pack_pairs_kernel
     // (with MXB_EM_CODED_T384=1 laid out for the 384-thread pass kernel where the row fits it)
     int pair_threads = 0;
     if (getenv("MXB_EM_CODED_PAIRS") != nullptr && em->nc <= 8)
-        pair_threads = (getenv("MXB_EM_CODED_T384") != nullptr && ceil_div(em->ld / 2, 384) <= 8)
-                           ? 384 : kPassThreads;
+        pair_threads = (!two_slots && getenv("MXB_EM_CODED_T384") != nullptr &&
+                        ceil_div(em->ld / 2, 384) <= 8) ? 384 : kPassThreads;
+    if (two_slots && pair_threads == 0) return MXB_OK;
     const bool pairs = pair_threads != 0;
     const size_t rec_bytes = pairs ? (size_t)pair_rec_bytes(pair_threads)
                                    : (size_t)em->ld + kDictSize * sizeof(double);
@@ -2294,9 +2533,13 @@ static int em_pack_rows(mxb_em *em) {
         }
     }
     if (e == cudaSuccess && worth)
-        e = cudaFuncSetAttribute((const void *)pick_pass_coded(em->nc, em->ld, pair_threads).fn,
+        e = cudaFuncSetAttribute(two_slots ? (const void *)pick_pair_coded(em->nc)
+                                           : (const void *)pick_pass_coded(em->nc, em->ld, pair_threads).fn,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)stages * rec_bytes + fixed));
+    if (e == cudaSuccess && worth && two_slots && n_dense > 0)
+        e = cudaFuncSetAttribute((const void *)pick_pair_accumulate(em->nc),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em->smem_bytes);
     dev_free(ctx, tmp);
     if (e != cudaSuccess || !worth) {
         dev_free(ctx, rec);
