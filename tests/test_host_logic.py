@@ -139,3 +139,32 @@ def test_synth_is_deterministic_and_well_formed(phylo17):
     assert np.array_equal(csr.base_code, direct.base_code)
     k = np.diff(csr.row_ptr)
     assert 10 <= k.min() and k.max() <= 200 and 60 < k.mean() < 100
+
+
+def test_parse_fuzz_against_python():
+    """Random short strings over the characters that matter to ``int()`` and to the two
+    splits: the C parser accepts, rejects (ValueError) and reports unknown positions (KeyError)
+    exactly where ``pos_obs_from_sig`` + the table lookup would (preprocess.py:151-160, :79-84)."""
+    import random
+    from mixemt_b200.phylo_tables import PhyloTables
+    variants = {p: collections.Counter("A") for p in range(40)}
+    phylo = PhyloTables(variants, {"X": ["A1G"]}, "A" * 64)
+    t = HapVarBaseMatrix("A" * 64, phylo, ["X"]).pack()
+    rnd = random.Random(7)
+    alphabet = "0123456789:,_+- \tACGTx\n"
+    for _ in range(20000):
+        sig = "".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 12)))
+        try:
+            want = py_pos_obs(sig)
+        except ValueError:
+            want = None
+        csr, err = parse_signatures([sig], t)
+        if want is None:
+            assert err is not None and err[1] == "value", sig
+            continue
+        outside = [p for p, _ in want if not 0 <= p < 40]
+        if outside:
+            assert err == (0, "key", outside[0]), sig
+        else:
+            assert err is None, sig
+            assert [int(t.positions[i]) for i in csr.pos_idx] == [p for p, _ in want], sig

@@ -88,3 +88,30 @@ def test_reduce_reads_live_reference():
     ref = ref_pre.reduce_reads(read_obs)
     got = pre.reduce_reads(read_obs)
     assert list(ref) == list(got) and all(ref[s] == got[s] for s in ref)
+
+
+def test_fuzz_against_python_restatement():
+    """Random small fragment sets (shared positions, empty fragments, multi-digit positions that
+    sort differently as strings): the drop-in dict and the array form agree with the reference's
+    loop (preprocess.py:163-174) and its sorted() order (:219-220)."""
+    import random
+    from mixemt_b200.preprocess import flatten_read_obs, reduce_reads, reduce_reads_arrays
+    rnd = random.Random(3)
+    for _ in range(400):
+        pool = [rnd.randint(0, 16568) for _ in range(rnd.randint(1, 8))]
+        read_obs = {}
+        for f in range(rnd.randint(0, 60)):
+            obs = {}
+            for _ in range(rnd.randint(0, 6)):
+                obs[rnd.choice(pool)] = rnd.choice("ACGTN")
+            read_obs["r%d" % f] = obs
+        want = {}
+        for rid, obs in read_obs.items():
+            sig = ','.join("%d:%s" % (p, obs[p]) for p in sorted(obs))
+            want.setdefault(sig, []).append(rid)
+        assert list(reduce_reads(read_obs).items()) == list(want.items())
+        ids, frag_ptr, pos, base = flatten_read_obs(read_obs)
+        red = reduce_reads_arrays(frag_ptr, pos, base)
+        order = sorted(want)
+        assert red.signatures == order
+        assert red.weights.tolist() == [len(want[s]) for s in order]
