@@ -382,6 +382,26 @@ em_gather_rows_kernel(const double *__restrict__ lin, int64_t ld, const double *
     }
 }
 
+// MXB_EM_CODED_COMPACT=1 (experimental): the coded pass skips the dense rows instead of
+// running over their empty records -- records and weights of the coded rows only, in row order.
+__global__ void em_flag_invert_kernel(int *__restrict__ flag, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        flag[i] = flag[i] ? 0 : 1;
+}
+__global__ void __launch_bounds__(256)
+em_gather_records_kernel(const unsigned char *__restrict__ rec, int64_t rec_bytes,
+                         const double *__restrict__ w_src, const int64_t *__restrict__ rows,
+                         int64_t n_out, unsigned char *__restrict__ dst, double *__restrict__ w_dst) {
+    for (int64_t i = blockIdx.x; i < n_out; i += gridDim.x) {
+        const int64_t r = rows[i];
+        const uint4 *src = reinterpret_cast<const uint4 *>(rec + r * rec_bytes);
+        uint4 *d = reinterpret_cast<uint4 *>(dst + i * rec_bytes);
+        for (int64_t j = threadIdx.x; j < rec_bytes / 16; j += 256) d[j] = src[j];
+        if (threadIdx.x == 0) w_dst[i] = w_src[r];
+    }
+}
+
 // ---- fused E+M pass (fast path) ----------------------------------------------
 // Rows are handled two at a time between block barriers.  The two partial dot
 // products of a thread are reduced together: the first shuffle step hands row 0
@@ -2110,7 +2130,8 @@ struct mxb_em {
     bool coded = false;
     int pair_threads = 0;             // != 0: records hold chunk dictionaries laid out for a pass
                                       // kernel of that many threads (em_pack_pairs_kernel)
-    unsigned char *rec = nullptr;     // [n_rows][rec_bytes]
+    unsigned char *rec = nullptr;     // [n_coded][rec_bytes]
+    int64_t n_coded = 0;              // rows of `rec`: all rows, or the coded ones only (compact)
     size_t rec_bytes = 0;
     double *w_coded = nullptr;        // [n_rows] weight, 0 for dense rows
     double *dense_lin = nullptr;      // [n_dense][ld]
@@ -2302,7 +2323,7 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
             // chunk-coded records of all rows, then the fp64 rows of the dense ones on top
             MXB_CUDA(launch_pdl(pick_pair_coded(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
                                 em->coded_smem, s, (const unsigned char *)em->rec, em->ld,
-                                em->n_rows, em->w_coded, em->pi[0], em->pi[1], em->pi[0] + em->ld,
+                                em->n_coded, em->w_coded, em->pi[0], em->pi[1], em->pi[0] + em->ld,
                                 em->pi[1] + em->ld, em->state, em->partials, em->partials + ps,
                                 em->coded_stages));
             ctx->launches += 1;
@@ -2344,7 +2365,7 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
         const CodedPass cp = pick_pass_coded(em->nc, em->ld, em->pair_threads);
         MXB_CUDA(launch_pdl(cp.fn, dim3(em->grid_fast), dim3(cp.threads),
                             em->coded_smem, s, (const unsigned char *)em->rec,
-                            (uint32_t)em->rec_bytes, em->ld, em->n_rows, em->w_coded, em->pi[0],
+                            (uint32_t)em->rec_bytes, em->ld, em->n_coded, em->w_coded, em->pi[0],
                             em->pi[1], em->state, em->partials, em->coded_stages,
                             em->n_dense > 0 ? 1 : 0));
         ctx->launches += 1;
@@ -2532,6 +2553,35 @@ static int em_pack_rows(mxb_em *em) {
             em->w_dense = w_dense;
         }
     }
+    int64_t n_coded = em->n_rows;
+    if (e == cudaSuccess && worth && n_dense > 0 && getenv("MXB_EM_CODED_COMPACT") != nullptr) {
+        // records of the coded rows only (the flags and the list buffer are reused)
+        const int64_t n_keep = em->n_rows - n_dense;
+        unsigned char *rec2 = nullptr;
+        e = dev_alloc(ctx, (void **)&rec2, up((size_t)n_keep * rec_bytes) + up((size_t)n_keep * sizeof(double)) + 256);
+        if (e == cudaSuccess) {
+            double *w2 = reinterpret_cast<double *>(rec2 + up((size_t)n_keep * rec_bytes));
+            em_flag_invert_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(flag, em->n_rows);
+            em_dense_list_kernel<<<1, 1024, 0, ctx->stream>>>(flag, em->n_rows, list, d_count);
+            const int g = (int)std::max<int64_t>(1, std::min<int64_t>(n_keep, (int64_t)ctx->num_sms * 8));
+            em_gather_records_kernel<<<g, 256, 0, ctx->stream>>>(rec, (int64_t)rec_bytes, w_coded, list,
+                                                                  n_keep, rec2, w2);
+            ctx->launches += 3;
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e == cudaSuccess) {
+                dev_free(ctx, rec);
+                rec = rec2;
+                w_coded = w2;
+                n_coded = n_keep;
+            } else {
+                dev_free(ctx, rec2);
+            }
+        } else {       // no room for the compact copy: keep the records of all rows
+            cudaGetLastError();
+            e = cudaSuccess;
+        }
+    }
     if (e == cudaSuccess && worth)
         e = cudaFuncSetAttribute(two_slots ? (const void *)pick_pair_coded(em->nc)
                                            : (const void *)pick_pass_coded(em->nc, em->ld, pair_threads).fn,
@@ -2554,6 +2604,7 @@ static int em_pack_rows(mxb_em *em) {
     em->coded = true;
     em->pair_threads = pair_threads;
     em->rec = rec;
+    em->n_coded = n_coded;
     em->rec_bytes = rec_bytes;
     em->w_coded = w_coded;
     em->dense_lin = dense;
@@ -2696,7 +2747,7 @@ int mxb_em_pass_bytes(const mxb_em *em, int64_t *bytes_per_pass, int64_t *n_dens
     MXB_REQUIRE(em != nullptr, "NULL argument");
     const int64_t row_bytes = em->ld * (int64_t)sizeof(double);
     if (bytes_per_pass)
-        *bytes_per_pass = em->coded ? em->n_rows * (int64_t)em->rec_bytes + em->n_dense * row_bytes
+        *bytes_per_pass = em->coded ? em->n_coded * (int64_t)em->rec_bytes + em->n_dense * row_bytes
                                     : em->n_rows * row_bytes;
     if (n_dense_rows) *n_dense_rows = em->coded ? em->n_dense : -1;
     return MXB_OK;

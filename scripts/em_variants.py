@@ -27,6 +27,9 @@ VARIANTS = [("v2 (default)", {}),
             ("v2 384 threads", {"MXB_EM_CODED_T384": "1"}),
             ("pairs (chunk dictionary)", {"MXB_EM_CODED_PAIRS": "1"}),
             ("pairs, 384 threads", {"MXB_EM_CODED_PAIRS": "1", "MXB_EM_CODED_T384": "1"}),
+            ("v2, coded rows only", {"MXB_EM_CODED_COMPACT": "1"}),
+            ("pairs, 384, coded only", {"MXB_EM_CODED_PAIRS": "1", "MXB_EM_CODED_T384": "1",
+                                        "MXB_EM_CODED_COMPACT": "1"}),
             ("fp64 rows", {"MXB_EM_NO_PACK": "1"})]
 
 
@@ -69,7 +72,7 @@ def main():
         out = os.path.join(ROOT, "gpurun_out", "variant_%d.npy" % VARIANTS.index((name, env)))
         e = dict(os.environ)
         for k in ("MXB_EM_CODED_V1", "MXB_EM_CODED_V3", "MXB_EM_CODED_T384", "MXB_EM_CODED_PAIRS",
-                  "MXB_EM_NO_PACK"):
+                  "MXB_EM_CODED_COMPACT", "MXB_EM_NO_PACK"):
             e.pop(k, None)
         e.update(env)
         cmd = ["timeout", "120", sys.executable, os.path.abspath(__file__), "--child", frags, iters,

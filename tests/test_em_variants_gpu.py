@@ -60,13 +60,15 @@ VARIANTS = {
     "t384": {"MXB_EM_CODED_T384": "1"},
     "pairs": {"MXB_EM_CODED_PAIRS": "1"},
     "pairs_t384": {"MXB_EM_CODED_PAIRS": "1", "MXB_EM_CODED_T384": "1"},
+    "compact": {"MXB_EM_CODED_COMPACT": "1"},
+    "pairs_compact": {"MXB_EM_CODED_PAIRS": "1", "MXB_EM_CODED_COMPACT": "1"},
 }
 
 
 def run_child(env_extra, fragments, n_multi):
     env = dict(os.environ)
     for key in ("MXB_EM_CODED_V1", "MXB_EM_CODED_V3", "MXB_EM_CODED_T384", "MXB_EM_CODED_PAIRS",
-                "MXB_EM_NO_PACK"):
+                "MXB_EM_CODED_COMPACT", "MXB_EM_NO_PACK"):
         env.pop(key, None)
     env.update(env_extra)
     code = CHILD % {"root": ROOT, "fragments": fragments, "n_multi": n_multi}
