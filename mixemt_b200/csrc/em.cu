@@ -575,192 +575,23 @@ em_pass_fast_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, 
 
 // ---- fused E+M pass over dictionary-coded rows ----------------------------------------
 // em_pass_fast_kernel over the records of em_pack_kernel ([ld code bytes][256 doubles], a
-// cell is table[code]): same ring, same column slices (chunk c = tid + k*512 covers cells
+// cell is table[code]): same ring, same column slices (chunk c = tid + k*THREADS covers cells
 // 2c, 2c+1, one 16-bit load brings both codes), same reduction; only the two values of a
 // chunk come from the row's table in shared memory instead of the stage itself.  A record
 // is 5.8x smaller than the fp64 row, so this kernel is bound by instruction issue (lookup
-// index arithmetic, butterflies, the division) and not by HBM: 0.55 ms for the 138 569
+// index arithmetic, butterflies, the division) and not by HBM: 0.50 ms for the 138 569
 // records of config 2 against 0.87 ms for the fp64 rows (more threads per CTA, eight rows
 // per barrier with the values looked up twice, and run-length aware lookups over
-// consecutive cells were all measured slower).  accumulate != 0 adds the column sums to what
-// the launch before this one (the fp64 pass over the dense rows) left in `partials`.
-template <int NC>
-__global__ void __launch_bounds__(kPassThreads, 1)
-em_pass_coded_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
-                    int64_t n_rows, const double *__restrict__ weights,
-                    const double *__restrict__ pi0, const double *__restrict__ pi1,
-                    EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
-                    int accumulate) {
-    static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
-    pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *scratch = reinterpret_cast<double *>(
-        smem_raw + (((size_t)n_stages * row_bytes + 127) & ~(size_t)127));
-    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
-    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
-    const int n_my = (int)(r_end - r_begin);
-    const unsigned char *my_rows = rows + (size_t)r_begin * row_bytes;
-    const double *my_w = weights + r_begin;
-    const uint32_t stages_u32 = smem_u32(smem_raw);
-    const uint32_t full_u32 = smem_u32(full);
-
-    // Prologue: L and the weights do not depend on the previous iteration's tail, so the
-    // ring is primed before waiting for it (the loads overlap the tail kernel).
-    if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int q = 0; q < n_my && q < n_stages; ++q) {
-            mbar_expect_tx(&full[q], row_bytes);
-            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
-                      &full[q]);
-        }
-    }
-    pdl_wait();  // proportions and control block of the previous iteration are final
-    if (st->done) {
-        // finished run: the primed loads must land before this CTA's shared memory is released
-        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
-        return;
-    }
-    const double *__restrict__ pi = st->cur ? pi1 : pi0;
-
-    // Thread-private column slice: chunk c = tid + k*512 covers doubles 2c, 2c+1.
-    const int n_chunks = (int)(ld >> 1);
-    double2 pr[NC], tr[NC];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * kPassThreads;
-        pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
-        tr[k] = make_double2(0.0, 0.0);
-    }
-    const bool last_live = tid + (NC - 1) * kPassThreads < n_chunks;  // only chunk NC-1 can be ragged
-
-    int stage = 0;          // ring slot of row q0
-    uint32_t phase = 0;     // its mbarrier parity
-    int sbuf = 0;
-    int bad = 0;
-    const bool upper = lane >= 16;
-    for (int q0 = 0; q0 < n_my; q0 += kPassGroup) {
-        double2 lv[kPassGroup][NC];
-        double dot[kPassGroup];
-        const int q_mine = q0 + (upper ? 1 : 0);
-        const double w_mine = (q_mine < n_my) ? my_w[q_mine] : 0.0;
-        int s_of[kPassGroup];
-        int s = stage;
-        uint32_t ph = phase;
-#pragma unroll
-        for (int g = 0; g < kPassGroup; ++g) {
-            s_of[g] = s;
-            double dx = 0.0, dy = 0.0;
-            if (q0 + g < n_my) {
-                mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
-                {
-                    const unsigned char *srec = smem_raw + (size_t)s * row_bytes;
-                    const uint16_t *codes = reinterpret_cast<const uint16_t *>(srec) + tid;
-                    const double *tab = reinterpret_cast<const double *>(srec + ld);
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) {
-                        if (k < NC - 1 || last_live) {
-                            const unsigned cc = codes[k * kPassThreads];   // cells 2c, 2c + 1
-                            lv[g][k] = make_double2(tab[cc & 0xFFu], tab[cc >> 8]);
-                        } else {
-                            lv[g][k] = make_double2(0.0, 0.0);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < NC; ++k) {
-                    dx = fma(lv[g][k].x, pr[k].x, dx);
-                    dy = fma(lv[g][k].y, pr[k].y, dy);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < NC; ++k) lv[g][k] = make_double2(0.0, 0.0);
-            }
-            dot[g] = dx + dy;
-            if (++s == n_stages) { s = 0; ph ^= 1u; }
-        }
-        // both rows in one butterfly: lanes 0-15 end up with row 0, lanes 16-31 with row 1
-        double v = (upper ? dot[1] : dot[0]) + shfl_xor_f64(upper ? dot[0] : dot[1], 16);
-        v += shfl_xor_f64(v, 8);
-        v += shfl_xor_f64(v, 4);
-        v += shfl_xor_f64(v, 2);
-        v += shfl_xor_f64(v, 1);
-        double *sc = scratch + sbuf * (kPassWarps * kPassGroup);
-        if ((lane & 15) == 0) sc[(lane >> 4) * kPassWarps + warp] = v;
-        __syncthreads();  // all reads of this group's stages are done; warp totals visible
-        if (tid == 0) {
-#pragma unroll
-            for (int g = 0; g < kPassGroup; ++g) {
-                const int q = q0 + g + n_stages;
-                if (q < n_my) {
-                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_of[g];
-                    mbar_expect_tx_u32(bar, row_bytes);
-                    bulk_load_u32(stages_u32 + (uint32_t)s_of[g] * row_bytes,
-                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
-                }
-            }
-        }
-        // 16 warp totals per row sit in sc[0..15] / sc[16..31]: one value per lane
-        double t = sc[lane];
-        t += shfl_xor_f64(t, 8);
-        t += shfl_xor_f64(t, 4);
-        t += shfl_xor_f64(t, 2);
-        t += shfl_xor_f64(t, 1);
-        double coef_mine = 0.0;
-        if (w_mine != 0.0) {
-            coef_mine = w_mine / t;
-            bad |= (t == 0.0);
-        }
-        const double coef0 = __shfl_sync(0xffffffffu, coef_mine, 0);
-        const double coef1 = __shfl_sync(0xffffffffu, coef_mine, 16);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            tr[k].x = fma(coef0, lv[0][k].x, tr[k].x);
-            tr[k].y = fma(coef0, lv[0][k].y, tr[k].y);
-        }
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            tr[k].x = fma(coef1, lv[1][k].x, tr[k].x);
-            tr[k].y = fma(coef1, lv[1][k].y, tr[k].y);
-        }
-        stage = s;
-        phase = ph;
-        sbuf ^= 1;
-    }
-
-    double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * kPassThreads;
-        if (c < n_chunks) {
-            if (accumulate) {
-                const double2 prev = out[c];
-                out[c] = make_double2(prev.x + tr[k].x, prev.y + tr[k].y);
-            } else {
-                out[c] = tr[k];
-            }
-        }
-    }
-    if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
-}
-
-// Second version of the loop (same arithmetic in the same order): full row pairs without
-// "is there a second row" tests or zero fills, the odd last row peeled off, both records
-// waited for before the lookups of either start.  11 % fewer warp instructions per row pair
-// in SASS (274 against 307): 0.568 ms per pass against 0.609 ms at config 2 (0.579 ms per
-// iteration against 0.621 ms).  This is the version that runs; MXB_EM_CODED_V1=1 selects the
-// first one.
+// consecutive cells were all measured slower).  The loop runs over full row pairs without
+// "is there a second row" tests or zero fills, the odd last row is peeled off, and both
+// records are waited for before the lookups of either start: 274 warp instructions per row
+// pair in SASS against 307 for the first version of the loop, which kept those tests inside
+// (0.568 ms per pass against 0.609 ms, profiles/r1k against r1j).  accumulate != 0 adds the
+// column sums to what the launch before this one (the fp64 pass over the dense rows) left
+// in `partials`.  THREADS = 384 is the experimental MXB_EM_CODED_T384 shape.
 template <int NC, int THREADS = kPassThreads>
 __global__ void __launch_bounds__(THREADS, 1)
-em_pass_coded_v2_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
+em_pass_coded_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
                     int64_t n_rows, const double *__restrict__ weights,
                     const double *__restrict__ pi0, const double *__restrict__ pi1,
                     EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
@@ -2163,7 +1994,7 @@ static pass_fn pick_pass(int nc) {
     return nullptr;
 }
 // The coded pass and its CTA size.  Default: second loop version, 512 threads, chunk count
-// `nc`.  MXB_EM_CODED_V1=1: first loop version.  Experimental, not yet run on a GPU:
+// `nc`.  Experimental, not yet run on a GPU:
 // MXB_EM_CODED_V3=1 (pipelined rows, no block barrier) and MXB_EM_CODED_T384=1 (second loop
 // version with 384 threads: 16 instead of 12 cells per thread at H = 5408, so the per-row-pair
 // reduction, division and ring bookkeeping of a warp are spread over a third more cells).
@@ -2200,7 +2031,6 @@ static CodedPass pick_pass_coded(int nc, int64_t ld, int pair_threads) {
     }
     static const bool v3 = getenv("MXB_EM_CODED_V3") != nullptr;
     static const bool t384 = getenv("MXB_EM_CODED_T384") != nullptr;
-    static const bool v2 = getenv("MXB_EM_CODED_V1") == nullptr;
     if (v3) {
         switch (nc) {
             case 1: return {em_pass_coded_v3_kernel<1>, kPassThreads};
@@ -2216,24 +2046,11 @@ static CodedPass pick_pass_coded(int nc, int64_t ld, int pair_threads) {
     }
     if (t384) {
         switch ((int)ceil_div(ld / 2, 384)) {
-            case 6: return {em_pass_coded_v2_kernel<6, 384>, 384};
-            case 7: return {em_pass_coded_v2_kernel<7, 384>, 384};
-            case 8: return {em_pass_coded_v2_kernel<8, 384>, 384};
+            case 6: return {em_pass_coded_kernel<6, 384>, 384};
+            case 7: return {em_pass_coded_kernel<7, 384>, 384};
+            case 8: return {em_pass_coded_kernel<8, 384>, 384};
         }
         // other widths keep the 512-thread kernel
-    }
-    if (v2) {
-        switch (nc) {
-            case 1: return {em_pass_coded_v2_kernel<1>, kPassThreads};
-            case 2: return {em_pass_coded_v2_kernel<2>, kPassThreads};
-            case 3: return {em_pass_coded_v2_kernel<3>, kPassThreads};
-            case 4: return {em_pass_coded_v2_kernel<4>, kPassThreads};
-            case 5: return {em_pass_coded_v2_kernel<5>, kPassThreads};
-            case 6: return {em_pass_coded_v2_kernel<6>, kPassThreads};
-            case 7: return {em_pass_coded_v2_kernel<7>, kPassThreads};
-            case 8: return {em_pass_coded_v2_kernel<8>, kPassThreads};
-        }
-        return {nullptr, 0};
     }
     switch (nc) {
         case 1: return {em_pass_coded_kernel<1>, kPassThreads};

@@ -6,8 +6,8 @@ Variants are selected by environment flags that csrc/em.cu reads once per proces
 (pick_pass_coded), so each one runs in its own child under `timeout` -- the pipelined
 variant synchronises through mbarriers and has not run on a GPU yet; a deadlock must not
 take the box down.  Prints ms per iteration, ms per pass and the largest difference of the
-log-proportions after the iterations against the default variant (v1, v2 and v3 add the
-same numbers in the same order: expected 0; t384 maps columns to threads differently and
+log-proportions after the iterations against the default variant (v3 adds the same numbers
+in the same order: expected 0; t384 maps columns to threads differently and
 `pairs` codes a slightly different set of rows: expected ~1e-15).
 """
 import ctypes
@@ -21,13 +21,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-VARIANTS = [("v2 (default)", {}),
-            ("v1", {"MXB_EM_CODED_V1": "1"}),
+VARIANTS = [("default", {}),
             ("v3 pipelined", {"MXB_EM_CODED_V3": "1"}),
-            ("v2 384 threads", {"MXB_EM_CODED_T384": "1"}),
+            ("384 threads", {"MXB_EM_CODED_T384": "1"}),
             ("pairs (chunk dictionary)", {"MXB_EM_CODED_PAIRS": "1"}),
             ("pairs, 384 threads", {"MXB_EM_CODED_PAIRS": "1", "MXB_EM_CODED_T384": "1"}),
-            ("v2, coded rows only", {"MXB_EM_CODED_COMPACT": "1"}),
+            ("coded rows only", {"MXB_EM_CODED_COMPACT": "1"}),
             ("pairs, 384, coded only", {"MXB_EM_CODED_PAIRS": "1", "MXB_EM_CODED_T384": "1",
                                         "MXB_EM_CODED_COMPACT": "1"}),
             ("fp64 rows", {"MXB_EM_NO_PACK": "1"})]
@@ -71,7 +70,7 @@ def main():
     for name, env in VARIANTS:
         out = os.path.join(ROOT, "gpurun_out", "variant_%d.npy" % VARIANTS.index((name, env)))
         e = dict(os.environ)
-        for k in ("MXB_EM_CODED_V1", "MXB_EM_CODED_V3", "MXB_EM_CODED_T384", "MXB_EM_CODED_PAIRS",
+        for k in ("MXB_EM_CODED_V3", "MXB_EM_CODED_T384", "MXB_EM_CODED_PAIRS",
                   "MXB_EM_CODED_COMPACT", "MXB_EM_NO_PACK"):
             e.pop(k, None)
         e.update(env)

@@ -54,8 +54,7 @@ print("ok", n, h, info_c["iterations"])
 """
 
 VARIANTS = {
-    "v2": {},
-    "v1": {"MXB_EM_CODED_V1": "1"},
+    "default": {},
     "v3": {"MXB_EM_CODED_V3": "1"},
     "t384": {"MXB_EM_CODED_T384": "1"},
     "pairs": {"MXB_EM_CODED_PAIRS": "1"},
@@ -67,7 +66,7 @@ VARIANTS = {
 
 def run_child(env_extra, fragments, n_multi):
     env = dict(os.environ)
-    for key in ("MXB_EM_CODED_V1", "MXB_EM_CODED_V3", "MXB_EM_CODED_T384", "MXB_EM_CODED_PAIRS",
+    for key in ("MXB_EM_CODED_V3", "MXB_EM_CODED_T384", "MXB_EM_CODED_PAIRS",
                 "MXB_EM_CODED_COMPACT", "MXB_EM_NO_PACK"):
         env.pop(key, None)
     env.update(env_extra)
