@@ -772,7 +772,7 @@ em_pass_coded_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes,
     if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
 }
 
-// The second loop version over chunk-coded records (em_pack_pairs_kernel): one 8-byte load
+// em_pass_coded_kernel over chunk-coded records (em_pack_pairs_kernel): one 8-byte load
 // brings a thread's codes of a row, one 16-byte lookup the two values of a chunk.
 // Experimental, MXB_EM_CODED_PAIRS=1.
 template <int NC, int THREADS = kPassThreads>
@@ -1993,10 +1993,10 @@ static pass_fn pick_pass(int nc) {
     }
     return nullptr;
 }
-// The coded pass and its CTA size.  Default: second loop version, 512 threads, chunk count
+// The coded pass and its CTA size.  Default: em_pass_coded_kernel, 512 threads, chunk count
 // `nc`.  Experimental, not yet run on a GPU:
-// MXB_EM_CODED_V3=1 (pipelined rows, no block barrier) and MXB_EM_CODED_T384=1 (second loop
-// version with 384 threads: 16 instead of 12 cells per thread at H = 5408, so the per-row-pair
+// MXB_EM_CODED_V3=1 (pipelined rows, no block barrier) and MXB_EM_CODED_T384=1 (the same
+// kernel with 384 threads: 16 instead of 12 cells per thread at H = 5408, so the per-row-pair
 // reduction, division and ring bookkeeping of a warp are spread over a third more cells).
 struct CodedPass {
     pass_fn fn;
