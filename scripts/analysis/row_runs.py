@@ -1,6 +1,6 @@
 """Run-length structure of the rows of the config-2 matrix under different column orders
 (analysis only, CPU oracle build)."""
-import os, sys, time
+import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
