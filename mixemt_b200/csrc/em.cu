@@ -254,7 +254,7 @@ em_pack_kernel(const double *__restrict__ lin, int64_t n_rows, int64_t ld,
 // Experimental (MXB_EM_CODED_PAIRS=1, not yet run on a GPU): the dictionary holds the values
 // of a *chunk* -- the two adjacent cells 2c, 2c + 1 one pass-kernel thread handles together --
 // instead of single cells.  91.6 % of the config-2 rows have at most 256 distinct chunks
-// (92.4 % have at most 256 distinct cells: scripts/analysis/pair_codes.py), so about the same
+// (92.4 % have at most 256 distinct cells: tests/analysis/pair_codes.py), so about the same
 // rows stay coded, and a chunk costs the pass one table lookup (LDS.128) instead of two
 // (LDS.64) and half the index arithmetic.  Record of row r, pair_rec_bytes(T) bytes:
 //   [T x 8 code bytes: byte k of thread t = code of chunk t + k * T]   (T = threads of the pass)

@@ -1,5 +1,5 @@
 """Distinct (cell 2c, cell 2c+1) value pairs per row of the config-2 matrix, for 2- and 4-cell
-chunks (analysis only, CPU oracle build): would a dictionary of chunk values fit 256 entries?"""
+chunks (analysis only; lives under tests/ because it builds its sample with the CPU oracle): would a dictionary of chunk values fit 256 entries?"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

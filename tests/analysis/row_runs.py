@@ -1,5 +1,5 @@
 """Run-length structure of the rows of the config-2 matrix under different column orders
-(analysis only, CPU oracle build)."""
+(analysis only; lives under tests/ because it builds its sample with the CPU oracle)."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

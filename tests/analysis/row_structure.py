@@ -1,4 +1,4 @@
-"""Row structure of the config-2 matrix on a row sample (CPU oracle build; analysis only).
+"""Row structure of the config-2 matrix on a row sample (analysis only; lives under tests/ because it builds its sample with the CPU oracle).
 
 How many cells of a row differ from the most common value of their column group, for several
 group widths -- the size of a (group value + exception list) representation of L."""
