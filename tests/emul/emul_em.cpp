@@ -278,6 +278,10 @@ int main(int argc, char **argv) {
     int bad = 0;
     // narrow rows with padding columns and a ragged last chunk; odd and even row counts per CTA
     bad += run_shape<2, 2>(23, 1030, 3, 3, 1);
+    // one row per CTA (only the peeled last row runs), a single CTA with an odd row count
+    bad += run_shape<2, 2>(2, 1030, 2, 3, 4);
+    bad += run_shape<2, 2>(7, 1030, 1, 3, 5);
+    if (full) bad += run_shape<2, 2>(40, 1030, 3, 5, 6);
     // Build-17 width: 6 chunks per thread at 512 threads (ragged), 8 at 384
     bad += run_shape<6, 8>(full ? 41 : 17, 5408, full ? 3 : 2, 4, 2);
     if (full) bad += run_shape<4, 6>(29, 4096, 2, 16, 3);

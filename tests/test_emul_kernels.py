@@ -16,7 +16,7 @@ EMUL = os.path.join(ROOT, "tests", "emul")
 
 def test_pass_kernels_under_the_interleaving_model():
     subprocess.check_call(["make", "-s", "-C", EMUL])
-    res = subprocess.run([os.path.join(EMUL, "_build", "emul_em")], capture_output=True, text=True,
+    res = subprocess.run([os.path.join(EMUL, "_build", "emul_em"), "full"], capture_output=True, text=True,
                          timeout=900)
     tail = res.stdout[-3000:] + res.stderr[-1000:]
     assert res.returncode == 0, tail
