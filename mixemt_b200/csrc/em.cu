@@ -120,8 +120,57 @@ struct CodedPass {
     int threads;
 };
 static CodedPass pick_pass_coded(int nc, int64_t ld, int pair_threads) {
+    static const bool v3 = getenv("MXB_EM_CODED_V3") != nullptr;
+    static const bool t384 = getenv("MXB_EM_CODED_T384") != nullptr;
+    const int nc384 = (int)ceil_div(ld / 2, 384);   // chunks per thread of a 384-thread CTA
+    if (v3) {   // pipelined rows; over cell records or chunk records, 512 or 384 threads
+        if (pair_threads == 384) {
+            switch (nc384) {
+                case 1: return {em_pass_coded_v3_kernel<1, 384, true>, 384};
+                case 2: return {em_pass_coded_v3_kernel<2, 384, true>, 384};
+                case 3: return {em_pass_coded_v3_kernel<3, 384, true>, 384};
+                case 4: return {em_pass_coded_v3_kernel<4, 384, true>, 384};
+                case 5: return {em_pass_coded_v3_kernel<5, 384, true>, 384};
+                case 6: return {em_pass_coded_v3_kernel<6, 384, true>, 384};
+                case 7: return {em_pass_coded_v3_kernel<7, 384, true>, 384};
+                case 8: return {em_pass_coded_v3_kernel<8, 384, true>, 384};
+            }
+            return {nullptr, 0};
+        }
+        if (pair_threads != 0) {
+            switch (nc) {
+                case 1: return {em_pass_coded_v3_kernel<1, kPassThreads, true>, kPassThreads};
+                case 2: return {em_pass_coded_v3_kernel<2, kPassThreads, true>, kPassThreads};
+                case 3: return {em_pass_coded_v3_kernel<3, kPassThreads, true>, kPassThreads};
+                case 4: return {em_pass_coded_v3_kernel<4, kPassThreads, true>, kPassThreads};
+                case 5: return {em_pass_coded_v3_kernel<5, kPassThreads, true>, kPassThreads};
+                case 6: return {em_pass_coded_v3_kernel<6, kPassThreads, true>, kPassThreads};
+                case 7: return {em_pass_coded_v3_kernel<7, kPassThreads, true>, kPassThreads};
+                case 8: return {em_pass_coded_v3_kernel<8, kPassThreads, true>, kPassThreads};
+            }
+            return {nullptr, 0};
+        }
+        if (t384 && nc384 >= 6 && nc384 <= 8) {
+            switch (nc384) {
+                case 6: return {em_pass_coded_v3_kernel<6, 384, false>, 384};
+                case 7: return {em_pass_coded_v3_kernel<7, 384, false>, 384};
+                case 8: return {em_pass_coded_v3_kernel<8, 384, false>, 384};
+            }
+        }
+        switch (nc) {
+            case 1: return {em_pass_coded_v3_kernel<1>, kPassThreads};
+            case 2: return {em_pass_coded_v3_kernel<2>, kPassThreads};
+            case 3: return {em_pass_coded_v3_kernel<3>, kPassThreads};
+            case 4: return {em_pass_coded_v3_kernel<4>, kPassThreads};
+            case 5: return {em_pass_coded_v3_kernel<5>, kPassThreads};
+            case 6: return {em_pass_coded_v3_kernel<6>, kPassThreads};
+            case 7: return {em_pass_coded_v3_kernel<7>, kPassThreads};
+            case 8: return {em_pass_coded_v3_kernel<8>, kPassThreads};
+        }
+        return {nullptr, 0};
+    }
     if (pair_threads == 384) {
-        switch ((int)ceil_div(ld / 2, 384)) {
+        switch (nc384) {
             case 1: return {em_pass_coded_pairs_kernel<1, 384>, 384};
             case 2: return {em_pass_coded_pairs_kernel<2, 384>, 384};
             case 3: return {em_pass_coded_pairs_kernel<3, 384>, 384};
@@ -146,28 +195,12 @@ static CodedPass pick_pass_coded(int nc, int64_t ld, int pair_threads) {
         }
         return {nullptr, 0};
     }
-    static const bool v3 = getenv("MXB_EM_CODED_V3") != nullptr;
-    static const bool t384 = getenv("MXB_EM_CODED_T384") != nullptr;
-    if (v3) {
-        switch (nc) {
-            case 1: return {em_pass_coded_v3_kernel<1>, kPassThreads};
-            case 2: return {em_pass_coded_v3_kernel<2>, kPassThreads};
-            case 3: return {em_pass_coded_v3_kernel<3>, kPassThreads};
-            case 4: return {em_pass_coded_v3_kernel<4>, kPassThreads};
-            case 5: return {em_pass_coded_v3_kernel<5>, kPassThreads};
-            case 6: return {em_pass_coded_v3_kernel<6>, kPassThreads};
-            case 7: return {em_pass_coded_v3_kernel<7>, kPassThreads};
-            case 8: return {em_pass_coded_v3_kernel<8>, kPassThreads};
-        }
-        return {nullptr, 0};
-    }
-    if (t384) {
-        switch ((int)ceil_div(ld / 2, 384)) {
+    if (t384 && nc384 >= 6 && nc384 <= 8) {   // other widths keep the 512-thread kernel
+        switch (nc384) {
             case 6: return {em_pass_coded_kernel<6, 384>, 384};
             case 7: return {em_pass_coded_kernel<7, 384>, 384};
             case 8: return {em_pass_coded_kernel<8, 384>, 384};
         }
-        // other widths keep the 512-thread kernel
     }
     switch (nc) {
         case 1: return {em_pass_coded_kernel<1>, kPassThreads};

@@ -978,15 +978,17 @@ em_pass_coded_pairs_kernel(const unsigned char *__restrict__ rows, uint32_t row_
 // published number depends on all of them), so its ring slot can be refilled.
 constexpr int kSumBufs = 4;
 
-template <int NC>
-__global__ void __launch_bounds__(kPassThreads, 1)
+template <int NC, int THREADS = kPassThreads, bool kPairs = false>
+__global__ void __launch_bounds__(THREADS, 1)
 em_pass_coded_v3_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
                         int64_t n_rows, const double *__restrict__ weights,
                         const double *__restrict__ pi0, const double *__restrict__ pi1,
                         EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
                         int accumulate) {
-    static_assert(kPassWarps == 16 && kSumBufs * kPassWarps <= 2 * kPassWarps * kPassGroup,
+    static_assert(kPassWarps == 16 && kSumBufs * kPassWarps <= 2 * kPassWarps * kPassGroup &&
+                      THREADS % 32 == 0 && THREADS <= kPassThreads && (!kPairs || NC <= 8),
                   "totals buffers live in the scratch area of the two-row kernels");
+    constexpr int kWarps = THREADS / 32;
     pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
 
     MXB_DYN_SHARED __align__(128) unsigned char smem_raw[];
@@ -1008,9 +1010,12 @@ em_pass_coded_v3_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
-        for (int b = 0; b < kSumBufs; ++b) mbar_init(&sum[b], kPassWarps);
+        for (int b = 0; b < kSumBufs; ++b) mbar_init(&sum[b], kWarps);
         mbar_init_fence();
     }
+    // totals slots of the warps a smaller CTA does not have (read by the 16-lane butterfly)
+    if (THREADS < kPassThreads && tid < kSumBufs * kPassWarps && (tid & 15) >= kWarps)
+        scratch[tid] = 0.0;
     __syncthreads();
     if (tid == 0) {
         for (int q = 0; q < n_my && q < n_stages; ++q) {
@@ -1030,22 +1035,34 @@ em_pass_coded_v3_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
     double2 pr[NC], tr[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * kPassThreads;
+        const int c = tid + k * THREADS;
         pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
         tr[k] = make_double2(0.0, 0.0);
     }
-    const bool last_live = tid + (NC - 1) * kPassThreads < n_chunks;  // only chunk NC-1 can be ragged
+    const bool last_live = tid + (NC - 1) * THREADS < n_chunks;  // only chunk NC-1 can be ragged
 
     int bad = 0;
     // the values of a row: table lookups of this thread's 2 NC cells in ring slot s
     auto lookups = [&](double2 (&lv)[NC], const int s) {
+        if (kPairs) {   // chunk-coded record: 8 code bytes per thread, table of double2
+            const uint32_t rec_u32 = stages_u32 + (uint32_t)s * row_bytes;
+            const uint2 cw = lds_v2_u32(rec_u32 + (uint32_t)tid * 8u);
+            const uint32_t tab_u32 = rec_u32 + (uint32_t)(THREADS * 8);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const unsigned word = (k < 4) ? cw.x : cw.y;
+                const unsigned off = ((word >> (8 * (k & 3))) & 0xFFu) << 4;
+                lv[k] = lds_v2_f64(tab_u32 + off);
+            }
+            return;
+        }
         const unsigned char *srec = smem_raw + (size_t)s * row_bytes;
         const uint16_t *codes = reinterpret_cast<const uint16_t *>(srec) + tid;
         const double *tab = reinterpret_cast<const double *>(srec + ld);
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             if (k < NC - 1 || last_live) {
-                const unsigned cc = codes[k * kPassThreads];   // cells 2c, 2c + 1
+                const unsigned cc = codes[k * THREADS];   // cells 2c, 2c + 1
                 lv[k] = make_double2(tab[cc & 0xFFu], tab[cc >> 8]);
             } else {
                 lv[k] = make_double2(0.0, 0.0);
@@ -1131,7 +1148,7 @@ em_pass_coded_v3_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
     double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * kPassThreads;
+        const int c = tid + k * THREADS;
         if (c < n_chunks) {
             if (accumulate) {
                 const double2 prev = out[c];

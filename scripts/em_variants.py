@@ -23,6 +23,12 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [("default", {}),
             ("v3 pipelined", {"MXB_EM_CODED_V3": "1"}),
+            ("v3, 384 threads", {"MXB_EM_CODED_V3": "1", "MXB_EM_CODED_T384": "1"}),
+            ("v3, pairs", {"MXB_EM_CODED_V3": "1", "MXB_EM_CODED_PAIRS": "1"}),
+            ("v3, pairs, 384 threads", {"MXB_EM_CODED_V3": "1", "MXB_EM_CODED_PAIRS": "1",
+                                        "MXB_EM_CODED_T384": "1"}),
+            ("v3, pairs, 384, coded only", {"MXB_EM_CODED_V3": "1", "MXB_EM_CODED_PAIRS": "1",
+                                            "MXB_EM_CODED_T384": "1", "MXB_EM_CODED_COMPACT": "1"}),
             ("384 threads", {"MXB_EM_CODED_T384": "1"}),
             ("pairs (chunk dictionary)", {"MXB_EM_CODED_PAIRS": "1"}),
             ("pairs, 384 threads", {"MXB_EM_CODED_PAIRS": "1", "MXB_EM_CODED_T384": "1"}),
@@ -78,14 +84,14 @@ def main():
                out]
         r = subprocess.run(cmd, env=e, capture_output=True, text=True)
         if r.returncode != 0:
-            print("%-26s FAILED rc=%d %s" % (name, r.returncode, r.stderr.strip()[-300:]))
+            print("%-30s FAILED rc=%d %s" % (name, r.returncode, r.stderr.strip()[-300:]))
             continue
         info = json.loads(r.stdout.strip().splitlines()[-1])
         lnp = np.load(out)
         if ref is None:
             ref = lnp
         live = np.isfinite(ref) & np.isfinite(lnp)
-        print("%-26s %.4f ms per iteration, %.4f ms per pass, max |d ln pi| vs default %.3g"
+        print("%-30s %.4f ms per iteration, %.4f ms per pass, max |d ln pi| vs default %.3g"
               % (name, info["ms_per_iteration"], info["ms_per_pass"],
                  float(np.abs(lnp[live] - ref[live]).max())))
 

@@ -94,7 +94,7 @@ int check(const char *what, const Problem &p, const std::vector<double> &partial
         worst = std::max(worst, err);
     }
     const bool ok = worst < 1e-12;
-    printf("%-58s %s  (max relative error %.2e)\n", what, ok ? "ok" : "FAILED", worst);
+    printf("%-66s %s  (max relative error %.2e)\n", what, ok ? "ok" : "FAILED", worst);
     return ok ? 0 : 1;
 }
 
@@ -227,6 +227,12 @@ int run_shape(int64_t n_rows, int64_t n_cols, int grid, int stages, unsigned see
                                    em_pass_coded_kernel<NC3, 384>);
         bad += single_restart<NC5>("em_pass_coded_v3_kernel (pipelined rows)", p, cells, grid, 512, stages,
                                    seed, e, em_pass_coded_v3_kernel<NC5>);
+        bad += single_restart<NC5>("em_pass_coded_v3_kernel, 384 threads", p, cells, grid, 384, stages, seed, e,
+                                   em_pass_coded_v3_kernel<NC3, 384, false>);
+        bad += single_restart<NC5>("em_pass_coded_v3_kernel over chunk records, 512 threads", p, pairs512, grid,
+                                   512, stages, seed, e, em_pass_coded_v3_kernel<NC5, 512, true>);
+        bad += single_restart<NC5>("em_pass_coded_v3_kernel over chunk records, 384 threads", p, pairs384, grid,
+                                   384, stages, seed, e, em_pass_coded_v3_kernel<NC3, 384, true>);
         bad += single_restart<NC5>("em_pass_coded_kernel over coded rows only", p, cells_compact, grid, 512,
                                    stages, seed, e, em_pass_coded_kernel<NC5, 512>);
         bad += single_restart<NC5>("em_pass_coded_pairs_kernel, 512 threads", p, pairs512, grid, 512, stages,

@@ -57,6 +57,9 @@ VARIANTS = {
     "default": {},
     "v3": {"MXB_EM_CODED_V3": "1"},
     "t384": {"MXB_EM_CODED_T384": "1"},
+    "v3_t384": {"MXB_EM_CODED_V3": "1", "MXB_EM_CODED_T384": "1"},
+    "v3_pairs": {"MXB_EM_CODED_V3": "1", "MXB_EM_CODED_PAIRS": "1"},
+    "v3_pairs_t384": {"MXB_EM_CODED_V3": "1", "MXB_EM_CODED_PAIRS": "1", "MXB_EM_CODED_T384": "1"},
     "pairs": {"MXB_EM_CODED_PAIRS": "1"},
     "pairs_t384": {"MXB_EM_CODED_PAIRS": "1", "MXB_EM_CODED_T384": "1"},
     "compact": {"MXB_EM_CODED_COMPACT": "1"},

@@ -23,7 +23,10 @@ def test_pass_kernels_under_the_interleaving_model():
     assert "all checks passed" in res.stdout, tail
     # every variant that is compiled into the library was exercised
     for name in ("em_pass_fast_kernel", "em_pass_coded_kernel, 512 threads",
-                 "em_pass_coded_kernel, 384 threads", "em_pass_coded_v3_kernel",
+                 "em_pass_coded_kernel, 384 threads", "em_pass_coded_v3_kernel (pipelined rows)",
+                 "em_pass_coded_v3_kernel, 384 threads",
+                 "em_pass_coded_v3_kernel over chunk records, 512 threads",
+                 "em_pass_coded_v3_kernel over chunk records, 384 threads",
                  "em_pass_coded_pairs_kernel, 512 threads", "em_pass_coded_pairs_kernel, 384 threads",
                  "over coded rows only", "em_pass_pair_kernel", "em_pass_pair_coded_kernel"):
         assert name in res.stdout, name
