@@ -291,6 +291,13 @@ int main(int argc, char **argv) {
     // Build-17 width: 6 chunks per thread at 512 threads (ragged), 8 at 384
     bad += run_shape<6, 8>(full ? 41 : 17, 5408, full ? 3 : 2, 4, 2);
     if (full) bad += run_shape<4, 6>(29, 4096, 2, 16, 3);
+    if (argc > 1 && std::string(argv[1]) == "sweep") {   // a longer one-off run over more schedules
+        for (unsigned seed = 10; seed < 10 + (argc > 2 ? (unsigned)atoi(argv[2]) : 6u); ++seed) {
+            bad += run_shape<2, 2>(9 + seed % 7, 1030, 1 + (int)(seed % 3), 3 + (int)(seed % 4), seed);
+            bad += run_shape<3, 3>(8 + seed % 5, 2100, 1 + (int)(seed % 2), 3 + (int)(seed % 3), seed + 100);
+            bad += run_shape<3, 4>(6 + seed % 6, 3000, 2, 3 + (int)(seed % 5), seed + 200);
+        }
+    }
     printf(bad ? "FAILED: %d checks\n" : "all checks passed (%d failures)\n", bad);
     printf("fiber switches: %ld\n", emul::switches);
     return bad ? 1 : 0;
