@@ -212,36 +212,68 @@ def cpu_baseline_port(budget_s=15.0):
 
 
 def run_reference(opts):
-    """CPU reference arm: the reference is pure Python/numpy/scipy and is not
-    present on the GPU box, so its numpy restatement is timed -- em_step through
-    the same scipy.special.logsumexp call sites (em.py:82, :87-89), one core,
-    like the reference."""
+    """CPU reference arm: the UNMODIFIED reference's own ``mixemt.em.em_step``
+    (em.py:57-91), one core like the reference, on a bounded row
+    sample of the config-2 workload.  The reference is imported from
+    /root/reference when mounted, else from the copy oracle/stage_ref.py staged
+    under oracle/_ref (git-ignored; travels to the GPU box).  Nothing of
+    mixemt_b200 is imported on this path: the sample comes from oracle/workload.py
+    (reference Phylotree + reduce_reads, matrix by the numpy restatement).  Only
+    when no reference is reachable the numpy/scipy restatement is timed instead
+    (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import scipy
-    from oracle import oracle_np
+    from oracle import refload, workload, oracle_np
+    assert "mixemt_b200" not in sys.modules
+    have_ref = refload.available()
+    if have_ref:
+        _, ref_pre, ref_em = refload.load()
+        step = ref_em.em_step
+        kind = "reference"
+        what = ("unmodified mixemt.em.em_step (%s)"
+                % ("staged copy oracle/_ref" if refload.staged() else refload.REFERENCE_ROOT))
+    else:
+        step = oracle_np.em_step_scipy
+        kind = "port"
+        what = "numpy/scipy restatement of em.em_step (oracle_np.em_step_scipy; no reference found)"
+    if not have_ref:
+        raise SystemExit(json.dumps({"impl": "reference", "unavailable":
+                                     "reference neither mounted nor staged (oracle/stage_ref.py)"}))
     budget = 100.0
     rows = opts.cpu_rows or 256
-    mat, wts, h, _ = cpu_sample_matrix(rows, seed=opts.seed)
+    phylo, refseq, reads, haps, wts, mat = workload.sample_matrix(rows, seed=opts.seed)
+    h = len(haps)
     lnp = np.log(np.random.RandomState(0).dirichlet([1.0] * h))
     if not opts.cpu_rows:
         t0 = time.perf_counter()
-        oracle_np.em_step_scipy(mat, wts, lnp, np.empty_like(mat))
+        step(mat, wts, lnp, np.empty_like(mat))
         per_row = (time.perf_counter() - t0) / mat.shape[0]
         rows = int(max(128, min(8192, budget / ((opts.steps + opts.warmup) * per_row))))
-        mat, wts, h, _ = cpu_sample_matrix(rows, seed=opts.seed)
+        phylo, refseq, reads, haps, wts, mat = workload.sample_matrix(rows, seed=opts.seed)
     mix = np.empty_like(mat)
     for _ in range(opts.warmup):
-        oracle_np.em_step_scipy(mat, wts, lnp, mix)
+        step(mat, wts, lnp, mix)
     t0 = time.perf_counter()
     for _ in range(opts.steps):
-        _, lnp_new = oracle_np.em_step_scipy(mat, wts, lnp, mix)
+        step(mat, wts, lnp, mix)
     total = time.perf_counter() - t0
     value = mat.size * opts.steps / total
-    sample = ("numpy/scipy restatement of em.em_step (oracle_np.em_step_scipy) on %d rows x %d "
-              "haplotypes of the config-2 matrix, numpy %s scipy %s, 1 thread"
-              % (mat.shape[0], h, np.__version__, scipy.__version__))
+    # kernel 1 of the reference: its own build_em_matrix on a few rows (SURVEY 8d: >= 40 rows)
+    build = None
+    if have_ref:
+        nb = min(40, len(reads))
+        t0 = time.perf_counter()
+        ref_mat = ref_pre.build_em_matrix(refseq, phylo, reads[:nb], haps,
+                                          argparse.Namespace(verbose=False))
+        build_s = time.perf_counter() - t0
+        build = {"cells_per_s": ref_mat.size / build_s, "rows": nb, "seconds": build_s,
+                 "call": "unmodified mixemt.preprocess.build_em_matrix",
+                 "sample_matrix_bit_identical": bool(np.array_equal(ref_mat, mat[:nb]))}
+    sample = ("%s on %d rows x %d haplotypes of the config-2 matrix, numpy %s scipy %s, 1 thread "
+              "of %d cores" % (what, mat.shape[0], h, np.__version__, scipy.__version__,
+                               os.cpu_count() or 1))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
             "ms_per_step": 1e3 * total / opts.steps, "higher_is_better": True,
@@ -249,8 +281,8 @@ def run_reference(opts):
             "config": {"workload": "config2: 3-way mixture H1/L3e/U5a1 50/30/20, 1M fragments x "
                        "300bp x %d Phylotree-17 haplotypes [CPU arm: bounded sample of %d "
                        "signature rows of it per step]" % (h, mat.shape[0])},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                             "sample": sample, "build": build},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

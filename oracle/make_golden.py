@@ -24,6 +24,10 @@ its source is copied.  Outputs are small input/output vectors:
                          output (oracle_np.synthetic_em_result)
   golden_reduce.npz      preprocess.reduce_reads and the row order / weights of
                          build_em_input on seeded fragments (oracle_np.synthetic_read_obs)
+  golden_cli1.npz        BASELINE.json config 1 through the unmodified CLI (bin/mixemt main()):
+                         H1 70% + L3e 30%, 10 000 fragments, Build 17, default options, -S 1;
+                         stdout, stderr and every output file of the reference CPU run
+                         (about 50 minutes on one core; `python oracle/make_golden.py cli1`)
 """
 import argparse
 import os
@@ -269,11 +273,38 @@ def reduce():
     print("golden_reduce.npz written")
 
 
+def cli1():
+    """Config 1 end to end through the reference's own CLI, on the CPU."""
+    import tempfile
+    from oracle import cli_sim
+    CLI1 = cli_sim.CONFIG1_CLI
+    phy, refseq = load_build17(anon_haps=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        bam = os.path.join(tmp, "config1.bam")
+        cli_sim.write_mixture_bam(bam, phy, refseq, CLI1["mixture"], CLI1["n_fragments"],
+                                  frag_len=CLI1["frag_len"], err=CLI1["err"],
+                                  seed=CLI1["bam_seed"])
+        prefix = os.path.join(tmp, "out")
+        t0 = time.time()
+        res = cli_sim.run_cli(CLI1["argv"] + ["-o", prefix, "-t", prefix, "-b", prefix, bam])
+        secs = time.time() - t0
+        print("reference CLI on config 1: rc %s in %.0f s" % (res.rc, secs))
+        print(res.stdout)
+        files = cli_sim.read_outputs(prefix, res.contributors())
+    out = {"stdout": np.array(res.stdout), "stderr": np.array(res.stderr),
+           "rc": np.array(res.rc), "seconds": np.array(secs),
+           "file_names": np.array("\n".join(sorted(files)))}
+    for name in files:
+        out["file_" + name] = np.array(files[name])
+    np.savez_compressed(os.path.join(GOLD, "golden_cli1.npz"), **out)
+    print("golden_cli1.npz written")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["toy", "build17", "cfg5", "consumers", "reduce"]
     for name in which:
         {"toy": toy, "build17": build17, "cfg5": cfg5, "consumers": consumers,
-         "reduce": reduce}[name]()
+         "reduce": reduce, "cli1": cli1}[name]()
     for f in sorted(os.listdir(GOLD)):
         print("%-28s %8.1f KB" % (f, os.path.getsize(os.path.join(GOLD, f)) / 1024.0))

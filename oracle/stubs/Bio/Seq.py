@@ -1,5 +1,5 @@
-"""Stand-in module; never called by the hot path."""
+"""Stand-in for Bio.Seq (test infrastructure; see ../pysam)."""
 
 
-class Seq(object):
+class Seq(str):
     pass

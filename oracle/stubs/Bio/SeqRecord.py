@@ -1,5 +1,8 @@
-"""Stand-in module; never called by the hot path."""
+"""Stand-in for Bio.SeqRecord (test infrastructure; see ../pysam)."""
 
 
 class SeqRecord(object):
-    pass
+    def __init__(self, seq, id="<unknown id>", description="<unknown description>"):
+        self.seq = seq
+        self.id = id
+        self.description = description
