@@ -62,6 +62,15 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the restart-sweep leg")
+    ap.add_argument("--restarts", type=int, default=100,
+                    help="restarts of the config-4 leg (BASELINE.json: 100)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (N > 1)")
+    ap.add_argument("--no-config3", action="store_true", help="skip the config-3 leg (N = 8)")
+    ap.add_argument("--config3", action="store_true", help="run the config-3 leg at any N > 1")
+    ap.add_argument("--config3-rows", type=int, default=1250000,
+                    help="signature rows per GPU of the config-3 leg")
+    ap.add_argument("--pageable-result", action="store_true",
+                    help="e2e: leave the result in pageable memory (no pinned pool)")
     ap.add_argument("--cpu-rows", type=int, default=0, help="row sample of the CPU legs (0 = auto)")
     return ap.parse_args()
 
@@ -292,12 +301,20 @@ def run_reference(opts):
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
+def csr_rows(csr, lo, hi):
+    """Rows [lo, hi) of a SignatureCSR."""
+    from mixemt_b200.preprocess import SignatureCSR
+    a, b = int(csr.row_ptr[lo]), int(csr.row_ptr[hi])
+    return SignatureCSR(csr.row_ptr[lo:hi + 1] - csr.row_ptr[lo], csr.pos_idx[a:b],
+                        csr.base_code[a:b])
+
+
 def run_b200(opts):
     import ctypes
     import torch
     import torch.distributed as dist
     import mixemt_b200
-    from mixemt_b200 import _lib, em as b200_em
+    from mixemt_b200 import _lib, em as b200_em, sharding
     from mixemt_b200._lib import lib, check, ptr
     from mixemt_b200.preprocess import HapVarBaseMatrix, build_matrix_from_csr
     from mixemt_b200.runtime import get_context
@@ -318,31 +335,46 @@ def run_b200(opts):
         if world > 1:
             dist.barrier()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
+
+    def max_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.MAX if world > 1 else None)
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_ranks(x, dist.ReduceOp.SUM if world > 1 else None)
 
-    # ---- workload: every rank its own shard -------------------------------------
+    def new_session(dmat, weights, sharded):
+        sess = ctypes.c_void_p()
+        check(lib.mxb_em_create(ctx.handle, dmat.handle, ptr(weights), 1 if sharded else 0,
+                                ctypes.byref(sess)))
+        nbytes, flag = ctypes.c_int64(), ctypes.c_int64()
+        check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nbytes), ctypes.byref(flag)))
+        return sess, int(nbytes.value), flag.value == 0     # flag 0: class tiles, -1: fp64 rows
+
+    def profile(sess, iters):
+        ms = (ctypes.c_float * 4)()
+        check(lib.mxb_em_profile(sess, iters, ms))
+        return {"class_sums": ms[0], "pass": ms[1], "gather": ms[2], "tail": ms[3]}
+
+    peak, peak_src = measured_peak()
+    sharded = world > 1
+
+    # ---- workload: every rank its own shard (weak scaling) ---------------------------
     phylo, haps, mix = load_workload(opts.fragments, opts.seed + rank, rows=opts.rows)
     if opts.rows > 400000:
         opts.no_e2e = True      # the drop-in call needs two N x H host arrays
     tables = HapVarBaseMatrix(phylo.refseq, phylo, haps).pack()
     csr = mix.csr(tables)
     n, h = csr.n_rows, len(haps)
+    ld = ((h + 15) // 16) * 16
     weights = mix.weights.astype(np.float64)
-    launches0 = ctx.launch_count
 
-    # ---- kernel 1: build (device resident) --------------------------------------
+    # ---- kernel 1: build (device resident) --------------------------------------------
     build_ms = []
     dmat = None
     for _ in range(3):
@@ -353,18 +385,13 @@ def run_b200(opts):
         build_ms.append(ms)
     build_best = min(build_ms)
 
-    # ---- kernel 2: EM iterations, inputs resident -------------------------------
-    sess = ctypes.c_void_p()
-    check(lib.mxb_em_create(ctx.handle, dmat.handle, ptr(weights), 1 if world > 1 else 0,
-                            ctypes.byref(sess)))
-    hbm_bytes, n_dense_rows = ctypes.c_int64(), ctypes.c_int64()
-    check(lib.mxb_em_pass_bytes(sess, ctypes.byref(hbm_bytes), ctypes.byref(n_dense_rows)))
+    # ---- kernel 2: EM iterations, inputs resident ---------------------------------------
+    sess, pass_bytes, tiled = new_session(dmat, weights, sharded)
     lnp0 = np.log(np.random.RandomState(1).dirichlet([1.0] * h))
     check(lib.mxb_em_set_lnprops(sess, ptr(lnp0)))
-    el, ps = ctypes.c_float(), ctypes.c_float()
+    el = ctypes.c_float()
     if opts.warmup > 0:
         check(lib.mxb_em_iterate_fixed(sess, opts.warmup, ctypes.byref(el), None))
-    peak, peak_src = measured_peak()
     with ClockSampler(local) as clocks:
         barrier()
         l0 = ctx.launch_count
@@ -374,125 +401,162 @@ def run_b200(opts):
         wall = time.perf_counter() - t0
         launches = ctx.launch_count - l0
         dev_s = max_over_ranks(el.value / 1e3)
-        # the dominant kernel alone (event pair around every launch), rank-local
-        check(lib.mxb_em_iterate_fixed(sess, min(opts.steps, 100), ctypes.byref(el),
-                                       ctypes.byref(ps)))
-        pass_s = ps.value / 1e3 / min(opts.steps, 100)
+        # per-kernel attribution (an event between the kernels of every iteration), rank-local
+        kern = profile(sess, min(opts.steps, 100))
     cells_total = sum_over_ranks(float(n) * h)
     value = cells_total * opts.steps / dev_s
     lib.mxb_em_destroy(sess)
 
     # the same iterations over plain fp64 rows (MXB_EM_NO_PACK=1): the pass that sits at the HBM
-    # roofline, reported next to the coded pass that replaces it where rows compress
-    fp64_pass = None
-    if n_dense_rows.value >= 0:
-        os.environ["MXB_EM_NO_PACK"] = "1"
-        try:
-            sess2 = ctypes.c_void_p()
-            check(lib.mxb_em_create(ctx.handle, dmat.handle, ptr(weights), 1 if world > 1 else 0,
-                                    ctypes.byref(sess2)))
-            check(lib.mxb_em_set_lnprops(sess2, ptr(lnp0)))
-            el2, ps2 = ctypes.c_float(), ctypes.c_float()
-            k2 = min(opts.steps, 100)
-            check(lib.mxb_em_iterate_fixed(sess2, max(3, opts.warmup), ctypes.byref(el2), None))
-            barrier()
-            check(lib.mxb_em_iterate_fixed(sess2, k2, ctypes.byref(el2), ctypes.byref(ps2)))
-            lib.mxb_em_destroy(sess2)
-            ld2 = ((h + 15) // 16) * 16
-            gbs = float(n) * ld2 * 8 / (ps2.value / 1e3 / k2) / 1e9
-            fp64_pass = {"kernel": "em_pass_fast_kernel (fp64 rows, MXB_EM_NO_PACK=1)",
-                         "ms_per_launch": ps2.value / k2, "ms_per_step": el2.value / k2,
-                         "algorithmic_bytes_per_launch": float(n) * ld2 * 8,
-                         "achieved": gbs, "unit": "GB/s", "peak": peak, "frac": gbs / peak,
-                         "frac_of_nominal_8TBs": gbs / 8000.0,
-                         "traffic": (ncu_traffic() or {}).get("em_pass_fast_kernel_bytes_per_launch")
-                         if opts.rows == 0 and opts.fragments == 1000000 else None}
-        finally:
-            os.environ.pop("MXB_EM_NO_PACK", None)
-
-    # The pass reads every row once per iteration.  Rows with at most 256 distinct values are
-    # stored as one byte per cell plus a 2 KB table (lossless, csrc/em.cu em_pack_kernel); the
-    # algorithmic bytes of the pass are what that layout holds, fp64_rows_bytes what the plain
-    # fp64 layout of SURVEY section 8(d) would hold (8 B per cell).
-    ld = ((h + 15) // 16) * 16
+    # roofline on the 8 bytes per cell of SURVEY section 8(d)
     fp64_bytes = float(n) * ld * 8
-    pass_bytes = float(hbm_bytes.value)
-    coded = n_dense_rows.value >= 0
-    achieved = pass_bytes / pass_s / 1e9
-    traffic = ncu_traffic()
-    key = "em_pass_coded_bytes_per_launch" if coded else "em_pass_fast_kernel_bytes_per_launch"
-    roofline = {"bound": "hbm",
-                "kernel": ("em_pass_coded_kernel (dictionary-coded records of all rows) + "
-                           "em_pass_fast_kernel over the %d fp64 rows with more than 256 distinct "
-                           "values" % n_dense_rows.value)
-                if coded else "em_pass_fast_kernel (fp64 rows)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": pass_bytes,
-                "ms_per_launch": pass_s * 1e3,
-                "fp64_rows_bytes": fp64_bytes,
-                "fp64_rows_equivalent_GBs": fp64_bytes / pass_s / 1e9,
-                # the committed ncu capture is of the config-2 launch
-                "traffic": (traffic or {}).get(key)
-                if opts.rows == 0 and opts.fragments == 1000000 else None,
-                "fp64_pass": fp64_pass}
+    os.environ["MXB_EM_NO_PACK"] = "1"
+    try:
+        sess2, bytes2, _ = new_session(dmat, weights, sharded)
+        check(lib.mxb_em_set_lnprops(sess2, ptr(lnp0)))
+        check(lib.mxb_em_iterate_fixed(sess2, max(3, opts.warmup), ctypes.byref(el), None))
+        barrier()
+        k2 = min(opts.steps, 50)
+        check(lib.mxb_em_iterate_fixed(sess2, k2, ctypes.byref(el), None))
+        fp64_step_ms = el.value / k2
+        kern64 = profile(sess2, k2)
+        lib.mxb_em_destroy(sess2)
+    finally:
+        os.environ.pop("MXB_EM_NO_PACK", None)
 
-    # ---- restart sweep (config 4): two restarts share every read of the matrix ----
-    # One GPU: 4 restarts, two per pass and one per pass.  N GPUs: the matrix of rank 0 is
-    # replicated (every rank rebuilds it from rank 0's seed), 4 N restarts are dealt round
-    # robin (args.b200_shard = "restarts") and the log-proportions are combined by all-reduce.
+    # ---- roofline: both readings, per kernel ---------------------
+    # frac_contract: SURVEY 8(d)'s 8 bytes per matrix cell over the kernel's time and the
+    # measured HBM peak; frac_traffic: the bytes the kernel actually has to read (its data
+    # layout, = ncu dram bytes where a capture is committed) over the same.
+    traffic = ncu_traffic() or {}
+    on_cfg2 = opts.rows == 0 and opts.fragments == 1000000
+
+    def entry(name, ms, layout_bytes, traffic_key=None, contract_bytes=fp64_bytes):
+        if not ms:
+            return None
+        t = ms / 1e3
+        e = {"kernel": name, "ms_per_launch": ms,
+             "contract_bytes_per_launch": contract_bytes,
+             "layout_bytes_per_launch": layout_bytes,
+             "frac_contract": contract_bytes / t / 1e9 / peak if contract_bytes else None,
+             "frac_traffic": layout_bytes / t / 1e9 / peak,
+             "achieved_GBs": layout_bytes / t / 1e9}
+        if traffic_key and on_cfg2:
+            e["ncu_dram_bytes_per_launch"] = traffic.get(traffic_key)
+        return e
+
+    n_batches = (n + 127) // 128
+    map_bytes = float(n_batches) * ((h + 7) // 8 * 8) * 2
+    tile_pass_bytes = pass_bytes - 3 * map_bytes if tiled else pass_bytes
+    pass_name = ("tile_pass_kernel (class tiles: rows x column classes per 128-row batch)"
+                 if tiled else "em_pass_fast_kernel (fp64 rows)")
+    kernels = [entry(pass_name, kern["pass"], tile_pass_bytes,
+                     "tile_pass_kernel_bytes_per_launch" if tiled
+                     else "em_pass_fast_kernel_bytes_per_launch"),
+               entry("tile_pi_kernel (class sums of the proportions)", kern["class_sums"],
+                     2 * map_bytes, "tile_pi_kernel_bytes_per_launch", 0.0),
+               entry("tile_gather_kernel (class sums back to columns)", kern["gather"],
+                     map_bytes, "tile_gather_kernel_bytes_per_launch", 0.0),
+               entry("em_finish_kernel (M-step, convergence test%s)"
+                     % (", peer exchange" if sharded else ""), kern["tail"],
+                     (32 if tiled else 148) * ld * 8.0, None, 0.0),
+               entry("em_pass_fast_kernel (same matrix as fp64 rows, MXB_EM_NO_PACK=1)",
+                     kern64["pass"], fp64_bytes, "em_pass_fast_kernel_bytes_per_launch"),
+               entry("build_matrix_kernel (kernel 1, N x H x 8 B written once)", build_best,
+                     fp64_bytes, "build_matrix_kernel_bytes_per_launch")]
+    kernels = [k for k in kernels if k]
+    step_ms = 1e3 * dev_s / opts.steps
+    dom = kernels[0]
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "unit": "GB/s", "peak": peak,
+                "peak_source": peak_src,
+                # the dominant kernel on the bytes its layout holds (what it must read)
+                "achieved": dom["achieved_GBs"], "frac": dom["frac_traffic"],
+                "frac_traffic": dom["frac_traffic"], "frac_contract": dom["frac_contract"],
+                "algorithmic_bytes_per_launch": dom["layout_bytes_per_launch"],
+                "contract_bytes_per_launch": fp64_bytes,
+                "ms_per_launch": dom["ms_per_launch"],
+                "traffic": dom.get("ncu_dram_bytes_per_launch"),
+                # the whole iteration against the contract bytes (8 B x N x H per iteration)
+                "iteration": {"ms": step_ms, "frac_contract": fp64_bytes / (step_ms / 1e3) / 1e9 / peak,
+                              "layout_bytes": float(pass_bytes),
+                              "frac_traffic": pass_bytes / (step_ms / 1e3) / 1e9 / peak},
+                "fp64_rows_iteration_ms": fp64_step_ms,
+                "per_kernel": kernels,
+                "note": "frac_contract = 8 B x cells / time / peak (SURVEY 8d); frac_traffic = "
+                        "bytes of the kernel's own data layout / time / peak; every frac can be "
+                        "recomputed from *_bytes_per_launch, ms_per_launch and peak"}
+
+    # ---- multi-GPU legs ------------------------------------------------------------------
+    parity = strong = config3 = None
+    if world > 1:
+        parity = parity_leg(ctx, tables, phylo, haps, rank, world, barrier)
+        if not opts.no_strong and opts.rows == 0:
+            strong = strong_leg(ctx, tables, phylo, haps, opts, rank, world, barrier,
+                                max_over_ranks, lnp0)
+        if (world == 8 or opts.config3) and opts.rows == 0 and not opts.no_config3:
+            dmat.free()
+            dmat = None
+            ctx.trim()
+            config3 = config3_leg(ctx, tables, phylo, haps, opts, rank, world, barrier,
+                                  max_over_ranks, sum_over_ranks, peak)
+            _, _, dmat, _ = build_matrix_from_csr(tables, csr, ctx=ctx, want_host=False,
+                                                  keep_device=True)
+
+    # ---- config 4: restart sweep to convergence ------------------------------------------
+    # n_multi random-init restarts (default 100, fixed seed) on the config-2 matrix; under
+    # torchrun the matrix of rank 0's seed is replicated, the restarts are dealt in contiguous
+    # blocks (args.b200_shard = "restarts") and combined like em.py:145-163 combines them.
     sweep = None
-    if not opts.no_sweep and (world == 1 or opts.rows == 0):
-        n_multi, sweep_iters = 4 * world, min(100, max(10, opts.steps))
+    if not opts.no_sweep and opts.rows == 0 and opts.restarts > 0:
+        n_multi = opts.restarts
         inits = np.log(np.random.RandomState(3).dirichlet([1.0] * h, size=n_multi))
-        sargs = argparse.Namespace(verbose=False, init_alpha=1.0, tolerance=-1.0,
-                                   max_iter=sweep_iters, n_multi=n_multi,
-                                   b200_shard="restarts" if world > 1 else None)
-        sweep = {"n_multi": n_multi, "iterations_per_restart": sweep_iters}
+        sargs = argparse.Namespace(verbose=False, init_alpha=1.0, tolerance=1e-4, max_iter=10000,
+                                   n_multi=n_multi, b200_shard="restarts" if world > 1 else None)
         smat, swts = dmat, weights
         if world > 1 and rank != 0:
             _, _, mix0 = load_workload(opts.fragments, opts.seed)
             _, _, smat, _ = build_matrix_from_csr(tables, mix0.csr(tables), ctx=ctx,
                                                   want_host=False, keep_device=True)
             swts = mix0.weights.astype(np.float64)
-        sn = smat.shape[0]
-        # one short untimed call first (first-use costs of the restart path: result blocks,
-        # pinned polling scratch), like the warm-up steps of the kernel leg
         wargs = argparse.Namespace(**vars(sargs))
-        wargs.max_iter, wargs.n_multi = 3, 2 * world
+        wargs.max_iter, wargs.n_multi = 3, 2 * world      # first-use costs of the restart path
         b200_em.run_em_device(smat, swts, wargs, want_host=False, inits=inits[:2 * world])
-        for mode in ("two_per_pass", "one_per_pass") if world == 1 else ("two_per_pass",):
-            if mode == "one_per_pass":
-                os.environ["MXB_EM_NO_BATCH"] = "1"
-            try:
-                barrier()
-                t0 = time.perf_counter()
-                b200_em.run_em_device(smat, swts, sargs, want_host=False, inits=inits)
-                barrier()
-                dt = max_over_ranks(time.perf_counter() - t0)
-            finally:
-                os.environ.pop("MXB_EM_NO_BATCH", None)
-            sweep[mode + "_cell_updates_per_s"] = float(sn) * h * n_multi * sweep_iters / dt
-            sweep[mode + "_seconds"] = dt
-        if world > 1:
-            sweep["parallelism"] = ("matrix replicated, %d restarts dealt round robin over %d GPUs, "
-                                    "log-proportions and read matrices combined over NCCL"
-                                    % (n_multi, world))
+        barrier()
+        t0 = time.perf_counter()
+        s_props, _, s_info, _ = b200_em.run_em_device(smat, swts, sargs, want_host=False,
+                                                      inits=inits)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        iters_total = sum_over_ranks(float(sum(s_info["iterations"])))
+        sweep = {"n_multi": n_multi, "seconds": dt, "restarts_per_s": n_multi / dt,
+                 "iterations_total": iters_total,
+                 "cell_updates_per_s": float(smat.shape[0]) * h * iters_total / dt,
+                 "props_sum": float(s_props.sum()),
+                 "top_haplogroups": [[haps[i], float(s_props[i])]
+                                     for i in np.argsort(s_props)[::-1][:3]],
+                 "call": "run_em(config-2 matrix, n_multi=%d, tolerance 1e-4, fixed seed) to "
+                         "convergence, read matrices folded on the device" % n_multi,
+                 "parallelism": ("matrix replicated, restarts in contiguous blocks over %d GPUs, "
+                                 "read matrices combined by an all-to-all of row shards + local "
+                                 "logaddexp fold" % world) if world > 1 else "single GPU"}
         if smat is not dmat:
             smat.free()
 
-    # ---- e2e: the drop-in call with host buffers ---------------------------------
+    # ---- e2e: the drop-in call with host buffers -----------------------------------------
+    # Input: an ordinary (pageable) numpy array, like a caller of the reference API holds.
+    # Result: pooled pinned host memory, reserved before the untimed warm-up call (what a
+    # service does once; MIXEMT_B200_PINNED / reserve_pinned).
     e2e = None
     if not opts.no_e2e:
-        host = torch.empty((n, h), dtype=torch.float64, pin_memory=True).numpy()
+        host = np.empty((n, h), dtype=np.float64)      # pageable
         dmat.to_host(out=host)
+        if not opts.pageable_result:
+            _lib.reserve_pinned(host.nbytes, 1)
         args = argparse.Namespace(verbose=False, init_alpha=1.0, tolerance=1e-4, max_iter=10000,
                                   n_multi=1, b200_shard="rows" if world > 1 else None)
         import io
         import re
         import contextlib
-        # one untimed call first, like the warm-up steps of the kernel leg: first-touch costs of
-        # the process (pinned staging ring, device block cache) are not what the call costs
         warm = argparse.Namespace(**vars(args))
         warm.max_iter = 20
         np.random.seed(opts.seed)
@@ -500,6 +564,7 @@ def run_b200(opts):
         np.random.seed(opts.seed)
         args.verbose = True
         buf = io.StringIO()
+        check(lib.mxb_stage_timing(1))
         with ClockSampler(local) as clocks_e2e:
             barrier()
             t0 = time.perf_counter()
@@ -507,15 +572,24 @@ def run_b200(opts):
                 props, read_mix = mixemt_b200.run_em(host, weights, args)
             barrier()
             e2e_s = max_over_ranks(time.perf_counter() - t0)
+        stage = (ctypes.c_double * 6)()
+        check(lib.mxb_stage_times(stage, 6))
+        check(lib.mxb_stage_timing(0))
         found = re.findall(r"Converged! \((\d+)\)", buf.getvalue())
         iters = int(found[0]) if found else args.max_iter
         top = np.argsort(props)[::-1][:3]
         e2e = {"value": cells_total * iters / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": (host.nbytes + weights.nbytes + 8 * h) / iters,
                "d2h_bytes_per_step": (read_mix.nbytes + 8 * h) / iters,
-               "call": "mixemt_b200.run_em(host ndarray, weights, args) to convergence "
+               "call": "mixemt_b200.run_em(pageable host ndarray, weights, args) to convergence "
                        "(tolerance 1e-4, Dirichlet(1) start, seed %d)" % opts.seed,
+               "input_memory": "pageable numpy array",
+               "result_memory": "pageable numpy array" if opts.pageable_result
+               else "pooled pinned block (reserved before the warm-up call)",
                "iterations": iters, "seconds": e2e_s,
+               "breakdown_ms": {"h2d": stage[0], "setup_tiles": stage[1], "iterate": stage[2],
+                                "read_mix": stage[3], "d2h": stage[4], "release": stage[5],
+                                "note": "rank 0, wall clock between stream synchronisations"},
                "h2d_bytes": host.nbytes + weights.nbytes, "d2h_bytes": read_mix.nbytes,
                "em_iters_per_s": iters / e2e_s,
                "top_haplogroups": [[haps[i], float(props[i])] for i in top],
@@ -551,19 +625,25 @@ def run_b200(opts):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": opts.steps, "warmup": opts.warmup,
-                "ms_per_step": 1e3 * dev_s / opts.steps, "higher_is_better": True,
+                "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(opts.fragments, n, h, opts.rows),
-                           "rows_per_gpu": n, "haplotypes": h, "parallelism":
+                           "rows_per_gpu": n, "haplotypes": h,
+                           "row_order": "string-sorted signatures, as build_em_input hands them "
+                                        "over (preprocess.py:219)",
+                           "layout": "class tiles" if tiled else "fp64 rows",
+                           "parallelism":
                            ("rows sharded x%d, H column sums exchanged per iteration by %s"
                             % (world, "peer stores inside the EM tail kernel (CUDA IPC over NVLink)"
                                if lib.mxb_comm_p2p_enabled(ctx.handle) else "ncclAllReduce(fp64)"))
                            if world > 1 else "single GPU",
-                           "l2_policy": "input (%.2f GB per pass) larger than L2, no flush needed"
-                           % (pass_bytes / 1e9)},
+                           "l2_policy": ("%.3f GB read per iteration, larger than the 126 MB L2: "
+                                         "no flush needed" % (pass_bytes / 1e9))},
                 "em_iters_per_s": opts.steps / dev_s,
                 "wall_ms_per_step": 1e3 * wall / opts.steps,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "restart_sweep": sweep,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "restart_sweep": sweep, "parity": parity, "strong_scaling": strong,
+                "config3": config3,
                 "gpu_launches": int(launches), "clocks": clocks.summary(),
                 "build": {"ms": build_best, "cells_per_s": float(n) * h / (build_best / 1e3),
                           "write_GBs": float(n) * h * 8 / (build_best / 1e3) / 1e9,
@@ -574,6 +654,132 @@ def run_b200(opts):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def parity_leg(ctx, tables, phylo, haps, rank, world, barrier):
+    """The path the multi-GPU numbers run on -- class tiles on every rank's row shard, column
+    sums exchanged inside the tail kernel -- against the CPU oracle on the whole matrix
+    (oracle/ as the checker, rank 0)."""
+    import ctypes
+    from mixemt_b200 import em as b200_em, sharding, synth
+    from mixemt_b200._lib import lib, check, ptr
+    from mixemt_b200.preprocess import build_matrix_from_csr
+    mix = synth.make_mixture(phylo, phylo.refseq, MIXTURE, 6000, seed=11, strings=False)
+    csr = mix.csr(tables)
+    n, h = csr.n_rows, len(haps)
+    lo, hi = sharding.row_shard(n, rank, world)
+    _, _, shard, _ = build_matrix_from_csr(tables, csr_rows(csr, lo, hi), ctx=ctx,
+                                           want_host=False, keep_device=True)
+    wts = mix.weights.astype(np.float64)
+    sess = ctypes.c_void_p()
+    check(lib.mxb_em_create(ctx.handle, shard.handle, ptr(wts[lo:hi]), 1, ctypes.byref(sess)))
+    nb, flag = ctypes.c_int64(), ctypes.c_int64()
+    check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nb), ctypes.byref(flag)))
+    lib.mxb_em_destroy(sess)
+    inits = np.log(np.random.RandomState(12).dirichlet([1.0] * h, size=1))
+    args = argparse.Namespace(verbose=False, init_alpha=1.0, tolerance=1e-7, max_iter=120,
+                              n_multi=1, b200_shard="rows")
+    props, _, info, mix_dev = b200_em.run_em_device(shard, wts[lo:hi], args, inits=inits,
+                                                    want_host=False, keep_device=True)
+    votes = mix_dev.argmax_rows()
+    mix_dev.free()
+    shard.free()
+    out = None
+    if rank == 0:
+        from oracle import oracle_c
+        full, _ = oracle_c.build_matrix(tables, csr, want_counts=False)
+        o_props, o_mix, o_iters = oracle_c.run_em(full, wts, inits, args.max_iter, args.tolerance)
+        d = float(np.abs(props - o_props).max())
+        same_votes = bool(np.array_equal(votes, np.argmax(o_mix[lo:hi], 1)))
+        it_equal = list(o_iters) == info["iterations"]
+        out = {"ok": bool(d < 1e-6 and it_equal and same_votes), "max_abs_dprops": d,
+               "iterations_equal": it_equal, "iterations": info["iterations"],
+               "argmax_votes_equal_rank0_shard": same_votes,
+               "layout": "class tiles" if flag.value == 0 else "fp64 rows",
+               "rows": n, "checker": "oracle.c run_em on the whole matrix (CPU, rank 0)"}
+    barrier()
+    return out
+
+
+def strong_leg(ctx, tables, phylo, haps, opts, rank, world, barrier, max_over_ranks, lnp0):
+    """One sample (the config-2 matrix of --seed) row-split over the ranks: what a user with
+    one BAM gets from N GPUs."""
+    import ctypes
+    from mixemt_b200 import sharding
+    from mixemt_b200._lib import lib, check, ptr
+    from mixemt_b200.preprocess import build_matrix_from_csr
+    _, _, mix = load_workload(opts.fragments, opts.seed)
+    csr = mix.csr(tables)
+    n, h = csr.n_rows, len(haps)
+    lo, hi = sharding.row_shard(n, rank, world)
+    _, _, shard, _ = build_matrix_from_csr(tables, csr_rows(csr, lo, hi), ctx=ctx,
+                                           want_host=False, keep_device=True)
+    wts = mix.weights.astype(np.float64)[lo:hi].copy()
+    sess = ctypes.c_void_p()
+    check(lib.mxb_em_create(ctx.handle, shard.handle, ptr(wts), 1, ctypes.byref(sess)))
+    check(lib.mxb_em_set_lnprops(sess, ptr(lnp0)))
+    el = ctypes.c_float()
+    check(lib.mxb_em_iterate_fixed(sess, max(3, opts.warmup), ctypes.byref(el), None))
+    barrier()
+    check(lib.mxb_em_iterate_fixed(sess, opts.steps, ctypes.byref(el), None))
+    barrier()
+    ms = max_over_ranks(el.value) / opts.steps
+    lib.mxb_em_destroy(sess)
+    shard.free()
+    return {"rows_total": n, "rows_per_gpu": hi - lo, "ms_per_iteration": ms,
+            "em_iters_per_s": 1e3 / ms, "cells_per_s": float(n) * h * 1e3 / ms,
+            "workload": "the config-2 matrix of one sample row-split over %d GPUs" % world}
+
+
+def config3_leg(ctx, tables, phylo, haps, opts, rank, world, barrier, max_over_ranks,
+                sum_over_ranks, peak):
+    """BASELINE.json configs[2]: 5-way low-fraction mixture, 10 M signature rows row-sharded
+    over 8 GPUs (1.25 M rows x 5408 per GPU, rows grouped like the reference orders them)."""
+    import ctypes
+    import torch
+    from mixemt_b200 import synth
+    from mixemt_b200._lib import lib, check, ptr
+    from mixemt_b200.preprocess import build_matrix_from_csr
+    rows = opts.config3_rows
+    mix = synth.random_rows(phylo, phylo.refseq, MIXTURE5, rows, seed=100 + rank)
+    csr = mix.csr(tables)
+    n, h = csr.n_rows, len(haps)
+    _, _, dmat, build_ms = build_matrix_from_csr(tables, csr, ctx=ctx, want_host=False,
+                                                 keep_device=True)
+    wts = mix.weights.astype(np.float64)
+    sess = ctypes.c_void_p()
+    t0 = time.perf_counter()
+    check(lib.mxb_em_create(ctx.handle, dmat.handle, ptr(wts), 1, ctypes.byref(sess)))
+    ctx.synchronize()
+    setup_s = time.perf_counter() - t0
+    nb, flag = ctypes.c_int64(), ctypes.c_int64()
+    check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nb), ctypes.byref(flag)))
+    lnp0 = np.log(np.random.RandomState(1).dirichlet([1.0] * h))
+    check(lib.mxb_em_set_lnprops(sess, ptr(lnp0)))
+    el = ctypes.c_float()
+    check(lib.mxb_em_iterate_fixed(sess, 3, ctypes.byref(el), None))
+    barrier()
+    steps = min(opts.steps, 50)
+    check(lib.mxb_em_iterate_fixed(sess, steps, ctypes.byref(el), None))
+    barrier()
+    ms = max_over_ranks(el.value) / steps
+    free_b, total_b = torch.cuda.mem_get_info()
+    lib.mxb_em_destroy(sess)
+    dmat.free()
+    ctx.trim()
+    ld = ((h + 15) // 16) * 16
+    cells = sum_over_ranks(float(n) * h)
+    contract = float(n) * ld * 8
+    return {"workload": "config3: 5-way mixture H1/L3e/U5a1/M7/D4a 60/25/10/4/1, %d signature "
+                        "rows per GPU x %d haplogroups on %d GPUs (%.0f GB of fp64 cells in all)"
+                        % (n, h, world, cells * 8 / 1e9),
+            "rows_per_gpu": n, "layout": "class tiles" if flag.value == 0 else "fp64 rows",
+            "ms_per_iteration": ms, "cells_per_s": cells * 1e3 / ms,
+            "bytes_read_per_iteration_per_gpu": float(nb.value),
+            "frac_contract": contract / (ms / 1e3) / 1e9 / peak,
+            "frac_traffic": nb.value / (ms / 1e3) / 1e9 / peak,
+            "build_ms": build_ms, "session_setup_s": setup_s,
+            "hbm_free_GB_during_iterations": free_b / 1e9, "hbm_total_GB": total_b / 1e9}
 
 
 def main():

@@ -23,6 +23,7 @@
 #ifndef MIXEMT_B200_H
 #define MIXEMT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -62,6 +63,24 @@ int mxb_ctx_synchronize(mxb_ctx *ctx);
  * up to MXB_CACHE_MB (default: a quarter of the device memory; 0 disables) -- cudaMalloc
  * and cudaFree of multi-GB blocks are slow and jittery.  mxb_ctx_trim hands them back. */
 int mxb_ctx_trim(mxb_ctx *ctx);
+/* Pinned host memory for matrix-sized results (no counterpart in the reference, which returns
+ * numpy arrays: em.py:111, preprocess.py:183).  An N x H result that lives in one of these
+ * blocks is downloaded by one DMA without staging copy or page faults.  Blocks are pooled
+ * process-wide: mxb_host_free keeps them for the next mxb_host_alloc of about the same size
+ * (up to MXB_PINNED_CACHE_MB, default a quarter of the host memory), mxb_host_trim releases
+ * them.  mxb_host_alloc leaves *out NULL (and returns MXB_OK) when pinning fails or when
+ * only_if_cached is set and no pooled block fits: the caller then uses pageable memory.
+ * mxb_host_reserve pins `count` blocks ahead of time (pinning costs about a second per 6 GB). */
+int mxb_host_alloc(size_t bytes, int only_if_cached, void **out);
+int mxb_host_free(void *ptr);
+int mxb_host_reserve(size_t bytes, int count);
+int mxb_host_trim(void);
+/* Stage times of the one-call entry points since the last mxb_stage_timing(1), milliseconds:
+ * [0] host->device copies of matrices, [1] session set-up (class tiles or fp64 rows, result
+ * allocation), [2] EM iterations, [3] read-matrix kernels, [4] device->host copy of the
+ * result, [5] release.  Bench instrumentation; off by default (adds stream synchronisations). */
+int mxb_stage_timing(int on);
+int mxb_stage_times(double *ms_out, int n);
 /* Kernel launches issued through this context since creation (bench evidence). */
 int64_t mxb_ctx_launch_count(const mxb_ctx *ctx);
 /* Multi-GPU: one process per GPU.  Rank 0 calls mxb_comm_unique_id, the host
@@ -204,6 +223,11 @@ int mxb_em_pass_bytes(const mxb_em *em, int64_t *bytes_per_pass, int64_t *n_dens
  * (adds an event pair per iteration). */
 int mxb_em_iterate_fixed(mxb_em *em, int64_t n_iter, float *elapsed_ms,
                          float *pass_ms);
+/* Per-kernel attribution of an iteration (bench instrumentation): n_iter iterations with an
+ * event between the kernels; ms_out[4] = average milliseconds of {class sums (tile_pi_kernel),
+ * pass (tile_pass_kernel or em_pass_fast_kernel), gather (tile_gather_kernel), tail
+ * (em_finish_kernel)}; the first and third are 0 for a session over fp64 rows. */
+int mxb_em_profile(mxb_em *em, int64_t n_iter, float *ms_out);
 /* which: 0 = latest log-proportions (new_props), 1 = the ones before them. */
 int mxb_em_get_lnprops(mxb_em *em, int which, double *out);
 /* Read matrix from the *previous* log-proportions (em.py:130 / F5), written or

@@ -6,6 +6,7 @@ visible.
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 
@@ -60,6 +61,12 @@ _PROTOS = {
     "mxb_ctx_synchronize": (ctypes.c_int, [P]),
     "mxb_ctx_trim": (ctypes.c_int, [P]),
     "mxb_ctx_launch_count": (c_i64, [P]),
+    "mxb_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, c_void_pp]),
+    "mxb_host_free": (ctypes.c_int, [P]),
+    "mxb_host_reserve": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int]),
+    "mxb_host_trim": (ctypes.c_int, []),
+    "mxb_stage_timing": (ctypes.c_int, [ctypes.c_int]),
+    "mxb_stage_times": (ctypes.c_int, [P, ctypes.c_int]),
     "mxb_comm_unique_id": (ctypes.c_int, [P]),
     "mxb_comm_init": (ctypes.c_int, [P, P, ctypes.c_int, ctypes.c_int]),
     "mxb_comm_destroy": (ctypes.c_int, [P]),
@@ -98,6 +105,7 @@ _PROTOS = {
     "mxb_em_pass_bytes": (ctypes.c_int, [P, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "mxb_em_iterate_fixed": (ctypes.c_int, [P, c_i64, ctypes.POINTER(ctypes.c_float),
                                             ctypes.POINTER(ctypes.c_float)]),
+    "mxb_em_profile": (ctypes.c_int, [P, c_i64, ctypes.POINTER(ctypes.c_float)]),
     "mxb_em_get_lnprops": (ctypes.c_int, [P, ctypes.c_int, P]),
     "mxb_em_read_mix": (ctypes.c_int, [P, P, ctypes.c_int, c_dbl]),
     "mxb_run_em": (ctypes.c_int, [P, P, P, c_i64, c_i64, P, c_i32, c_i64, c_dbl, c_i32,
@@ -155,3 +163,43 @@ def ptr(arr):
 
 def as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ---- results in pooled pinned host memory (mxb_host_alloc) -----------------------------
+_PIN_MIN_BYTES = 32 << 20
+
+
+def pinned_mode():
+    """``MIXEMT_B200_PINNED``: ``0`` results are plain numpy arrays; ``1`` every
+    matrix-sized result lives in a pooled pinned block (the first one of a size
+    pays for the pinning, about a second per 6 GB); default ``auto``: pinned
+    when the pool holds a block that fits (``reserve_pinned`` or an earlier
+    pinned result put it there), pageable otherwise."""
+    return os.environ.get("MIXEMT_B200_PINNED", "auto")
+
+
+def result_empty(shape, dtype=np.float64):
+    """An uninitialised C-contiguous result array, in pooled pinned host memory
+    when the mode allows it (see :func:`pinned_mode`), else ``np.empty``.
+    The block goes back to the pool when the array (and every view of it) dies."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    mode = pinned_mode()
+    if mode != "0" and nbytes >= _PIN_MIN_BYTES:
+        out = ctypes.c_void_p()
+        check(lib.mxb_host_alloc(nbytes, 0 if mode == "1" else 1, ctypes.byref(out)))
+        if out.value:
+            buf = (ctypes.c_char * nbytes).from_address(out.value)
+            weakref.finalize(buf, lib.mxb_host_free, ctypes.c_void_p(out.value))
+            return np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return np.empty(shape, dtype=dtype)
+
+
+def reserve_pinned(nbytes, count=1):
+    """Pin ``count`` blocks of ``nbytes`` ahead of time and leave them in the
+    pool (what a long-running service does once; results of that size are then
+    downloaded by plain DMA from the first call on)."""
+    check(lib.mxb_host_reserve(int(nbytes), int(count)))
+
+
+def trim_pinned():
+    check(lib.mxb_host_trim())

@@ -20,7 +20,8 @@ import numpy
 
 from . import _lib
 from ._lib import lib, check, ptr
-from .runtime import DeviceMatrix, get_context, lookup_resident, remember_resident
+from .runtime import (DeviceMatrix, get_context, lookup_resident, remember_resident,
+                      resident_mode)
 
 
 class _OnDevice(object):
@@ -69,13 +70,18 @@ def reduce_em_matrix(em_mat, haplogroups, contrib_props):
     haps_to_keep = {con[1] for con in contrib_props}
     indexes = [i for i in range(len(haplogroups)) if haplogroups[i] in haps_to_keep]
     new_haps = [haplogroups[i] for i in indexes]
+    was_resident = isinstance(em_mat, numpy.ndarray) and lookup_resident(em_mat) is not None
     with _OnDevice(em_mat) as dev:
         small = gather_columns(dev, indexes)
     if isinstance(em_mat, DeviceMatrix):
         return small, new_haps
     host = small.to_host()
-    host.flags.writeable = False
-    remember_resident(host, small)
+    if was_resident or resident_mode():
+        # opt-in residency only: the HBM copy stays registered behind a read-only array
+        host.flags.writeable = False
+        remember_resident(host, small)
+    else:
+        small.free()    # the reference hands back a fresh writable array (preprocess.py:251)
     return host, new_haps
 
 

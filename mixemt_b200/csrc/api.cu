@@ -8,8 +8,10 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <thread>
+#include <mutex>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -37,6 +39,10 @@ typedef int (*fn_comm_destroy)(void *);
 typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*fn_allgather)(const void *, void *, size_t, int, void *, cudaStream_t);
 typedef const char *(*fn_error_string)(int);
+typedef int (*fn_send)(const void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_recv)(void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_bcast)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_group)(void);
 
 struct NcclApi {
     void *handle = nullptr;
@@ -46,6 +52,10 @@ struct NcclApi {
     fn_allreduce allreduce = nullptr;
     fn_allgather allgather = nullptr;
     fn_error_string error_string = nullptr;
+    fn_send send = nullptr;
+    fn_recv recv = nullptr;
+    fn_bcast bcast = nullptr;
+    fn_group group_start = nullptr, group_end = nullptr;
 };
 
 static NcclApi g_nccl;
@@ -69,6 +79,11 @@ static int load_nccl() {
     g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
     g_nccl.allgather = (fn_allgather)dlsym(h, "ncclAllGather");
     g_nccl.error_string = (fn_error_string)dlsym(h, "ncclGetErrorString");
+    g_nccl.send = (fn_send)dlsym(h, "ncclSend");
+    g_nccl.recv = (fn_recv)dlsym(h, "ncclRecv");
+    g_nccl.bcast = (fn_bcast)dlsym(h, "ncclBroadcast");
+    g_nccl.group_start = (fn_group)dlsym(h, "ncclGroupStart");
+    g_nccl.group_end = (fn_group)dlsym(h, "ncclGroupEnd");
     if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.allreduce) {
         set_error("libnccl is missing a required symbol");
         dlclose(h);
@@ -94,6 +109,52 @@ int nccl_allreduce_f64(mxb_ctx *ctx, double *dev_buf, int64_t n, int op_is_max) 
     if (!ctx->nccl_comm || ctx->world <= 1) return MXB_OK;
     MXB_NCCL(g_nccl.allreduce(dev_buf, dev_buf, (size_t)n, 8, op_is_max ? 2 : 0,
                               ctx->nccl_comm, ctx->stream));
+    return MXB_OK;
+}
+
+// Row shards of an N x H matrix (rank q owns rows [N q / W, N (q + 1) / W)): every rank sends
+// shard q of its matrix `src` to rank q and receives the W versions of its own shard into
+// `recv` (W slots of max_rows x n_cols doubles; the own slot is not filled: read `src`).
+int nccl_alltoall_rows(mxb_ctx *ctx, const double *src, double *recv, int64_t n_rows,
+                       int64_t n_cols, int64_t slot_doubles) {
+    if (!ctx->nccl_comm || ctx->world <= 1) return MXB_OK;
+    if (!g_nccl.send || !g_nccl.recv || !g_nccl.group_start || !g_nccl.group_end) {
+        set_error("libnccl lacks ncclSend/ncclRecv");
+        return MXB_ERR_CUDA;
+    }
+    const int W = ctx->world, me = ctx->rank;
+    const int64_t my_lo = n_rows * me / W, my_hi = n_rows * (me + 1) / W;
+    MXB_NCCL(g_nccl.group_start());
+    for (int q = 0; q < W; ++q) {
+        if (q == me) continue;
+        const int64_t lo = n_rows * q / W, hi = n_rows * (q + 1) / W;
+        if (hi > lo)
+            MXB_NCCL(g_nccl.send(src + lo * n_cols, (size_t)((hi - lo) * n_cols), 8, q,
+                                 ctx->nccl_comm, ctx->stream));
+        if (my_hi > my_lo)
+            MXB_NCCL(g_nccl.recv(recv + (int64_t)q * slot_doubles, (size_t)((my_hi - my_lo) * n_cols),
+                                 8, q, ctx->nccl_comm, ctx->stream));
+    }
+    MXB_NCCL(g_nccl.group_end());
+    return MXB_OK;
+}
+
+// Every rank broadcasts its row shard of `m` (in place): afterwards all ranks hold all rows.
+int nccl_allgather_rows(mxb_ctx *ctx, double *m, int64_t n_rows, int64_t n_cols) {
+    if (!ctx->nccl_comm || ctx->world <= 1) return MXB_OK;
+    if (!g_nccl.bcast || !g_nccl.group_start || !g_nccl.group_end) {
+        set_error("libnccl lacks ncclBroadcast");
+        return MXB_ERR_CUDA;
+    }
+    const int W = ctx->world;
+    MXB_NCCL(g_nccl.group_start());
+    for (int q = 0; q < W; ++q) {
+        const int64_t lo = n_rows * q / W, hi = n_rows * (q + 1) / W;
+        if (hi > lo)
+            MXB_NCCL(g_nccl.bcast(m + lo * n_cols, m + lo * n_cols, (size_t)((hi - lo) * n_cols), 8,
+                                  q, ctx->nccl_comm, ctx->stream));
+    }
+    MXB_NCCL(g_nccl.group_end());
     return MXB_OK;
 }
 
@@ -236,6 +297,7 @@ int copy_d2h(mxb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
 // Cache of large device blocks (see common.cuh).
 // ---------------------------------------------------------------------------
 struct BlockCache {
+    std::mutex mu;   // dev_free may run on whichever Python thread triggers a GC (ctypes drops the GIL)
     std::unordered_map<void *, size_t> live;           // blocks handed out by dev_alloc
     std::vector<std::pair<size_t, void *>> free_list;  // cached blocks
     size_t cached_bytes = 0;
@@ -251,7 +313,9 @@ void *pinned_scratch(mxb_ctx *ctx) {
     return ctx->pinned;
 }
 
+static std::mutex g_cache_create_mu;
 static BlockCache *cache_of(mxb_ctx *ctx) {
+    std::lock_guard<std::mutex> create_lock(g_cache_create_mu);
     if (!ctx->block_cache) {
         BlockCache *bc = new (std::nothrow) BlockCache();
         if (!bc) return nullptr;
@@ -271,6 +335,7 @@ static BlockCache *cache_of(mxb_ctx *ctx) {
 void dev_cache_release(mxb_ctx *ctx) {
     BlockCache *bc = (BlockCache *)ctx->block_cache;
     if (!bc) return;
+    std::lock_guard<std::mutex> lock(bc->mu);
     for (auto &ent : bc->free_list) cudaFree(ent.second);
     bc->free_list.clear();
     bc->cached_bytes = 0;
@@ -281,6 +346,7 @@ cudaError_t dev_alloc(mxb_ctx *ctx, void **out, size_t bytes) {
     if (bytes == 0) return cudaSuccess;
     BlockCache *bc = bytes >= kCacheMinBlock ? cache_of(ctx) : nullptr;
     if (bc) {
+        std::lock_guard<std::mutex> lock(bc->mu);
         // smallest cached block that fits without wasting more than 1/8
         int best = -1;
         for (int i = 0; i < (int)bc->free_list.size(); ++i) {
@@ -304,6 +370,7 @@ cudaError_t dev_alloc(mxb_ctx *ctx, void **out, size_t bytes) {
         e = cudaMalloc(out, bytes);
     }
     if (e == cudaSuccess && bc) {
+        std::lock_guard<std::mutex> lock(bc->mu);
         try { bc->live[*out] = bytes; } catch (...) {}
     }
     return e;
@@ -313,13 +380,20 @@ void dev_free(mxb_ctx *ctx, void *ptr) {
     if (!ptr) return;
     BlockCache *bc = ctx ? (BlockCache *)ctx->block_cache : nullptr;
     if (bc) {
-        auto it = bc->live.find(ptr);
-        if (it != bc->live.end()) {
-            const size_t sz = it->second;
-            bc->live.erase(it);
+        size_t sz = 0;
+        {
+            std::lock_guard<std::mutex> lock(bc->mu);
+            auto it = bc->live.find(ptr);
+            if (it != bc->live.end()) {
+                sz = it->second;
+                bc->live.erase(it);
+            }
+        }
+        if (sz != 0) {
+            // the block may still be read by work queued on the context's stream
+            cudaStreamSynchronize(ctx->stream);
+            std::lock_guard<std::mutex> lock(bc->mu);
             if (bc->cached_bytes + sz <= bc->limit) {
-                // the block may still be read by work queued on the context's stream
-                cudaStreamSynchronize(ctx->stream);
                 try {
                     bc->free_list.emplace_back(sz, ptr);
                     bc->cached_bytes += sz;
@@ -329,6 +403,39 @@ void dev_free(mxb_ctx *ctx, void *ptr) {
         }
     }
     cudaFree(ptr);
+}
+
+// ---------------------------------------------------------------------------
+// Pool of pinned host blocks for matrix-sized *results* (process-wide; pinned memory is
+// allocated portable).  The drop-in calls hand N x H arrays back to Python; when such an
+// array lives in a pooled pinned block the device->host copy is one DMA at PCIe speed with no
+// staging memcpy and no first-touch page faults -- which is what limits eight ranks sharing
+// the host cores of one box.  Pinning is slow (about a second per 6 GB), so blocks are kept
+// when their arrays die and handed out again (mxb_host_trim releases them).
+// ---------------------------------------------------------------------------
+bool g_stage_on = false;
+double g_stage_ms[kNumStages] = {};
+
+struct HostPool {
+    std::mutex mu;
+    std::unordered_map<void *, size_t> live;
+    std::vector<std::pair<size_t, void *>> free_list;
+    size_t cached_bytes = 0;
+};
+static HostPool g_host_pool;
+
+static size_t host_pool_limit() {
+    static size_t limit = 0;
+    if (limit == 0) {
+        const char *env = getenv("MXB_PINNED_CACHE_MB");
+        if (env) {
+            limit = ((size_t)atoll(env) << 20) + 1;
+        } else {
+            const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+            limit = pages > 0 && psz > 0 ? (size_t)pages * (size_t)psz / 4 : ((size_t)16 << 30);
+        }
+    }
+    return limit;
 }
 
 struct PrefaultImpl {
@@ -384,6 +491,8 @@ static void p2p_teardown(mxb_ctx *ctx) {
         else cudaIpcCloseMemHandle(ctx->p2p_block[r]);
         ctx->p2p_block[r] = nullptr;
     }
+    if (ctx->p2p_vote) cudaFree(ctx->p2p_vote);
+    ctx->p2p_vote = nullptr;
     ctx->p2p_ready = false;
 }
 
@@ -428,12 +537,29 @@ static int p2p_setup(mxb_ctx *ctx) {
     MXB_CUDA(cudaMemcpyAsync(&v, vote, sizeof(v), cudaMemcpyDeviceToHost, s));
     MXB_CUDA(cudaStreamSynchronize(s));
     cudaFree(dh);
-    cudaFree(vote);
     if (v != 0.0) {
+        cudaFree(vote);
         p2p_teardown(ctx);
         return MXB_OK;  // NCCL all-reduce path stays in use
     }
+    ctx->p2p_vote = vote;
     ctx->p2p_ready = true;
+    return MXB_OK;
+}
+
+// Start of a row-sharded session: put every rank's mailbox flags and launch sequence number
+// back to zero behind a barrier.  A rank that timed out, failed, or ran a different number of
+// tail launches than its peers in an earlier session would otherwise leave the sequence
+// numbers out of step for good (every later session would wait for a number that never comes).
+int p2p_resync(mxb_ctx *ctx) {
+    if (!ctx->p2p_ready || ctx->world <= 1) return MXB_OK;
+    cudaStream_t s = ctx->stream;
+    MXB_CUDA(cudaStreamSynchronize(s));                 // my own tail launches are done
+    MXB_CUDA(cudaMemsetAsync(ctx->p2p_vote, 0, sizeof(double), s));
+    MXB_TRY(nccl_allreduce_f64(ctx, ctx->p2p_vote, 1, 0));   // ... and so are everybody else's
+    MXB_CUDA(cudaMemsetAsync(ctx->p2p_block[ctx->rank], 0, kP2PInboxOffset, s));
+    MXB_TRY(nccl_allreduce_f64(ctx, ctx->p2p_vote, 1, 0));   // nobody stores before all are zeroed
+    MXB_CUDA(cudaStreamSynchronize(s));
     return MXB_OK;
 }
 
@@ -517,6 +643,96 @@ int mxb_ctx_trim(mxb_ctx *ctx) {
     MXB_CUDA(cudaSetDevice(ctx->device));
     MXB_CUDA(cudaStreamSynchronize(ctx->stream));
     dev_cache_release(ctx);
+    return MXB_OK;
+}
+
+int mxb_host_alloc(size_t bytes, int only_if_cached, void **out) {
+    MXB_REQUIRE(out != nullptr && bytes > 0, "bad argument");
+    *out = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_host_pool.mu);
+        int best = -1;
+        for (int i = 0; i < (int)g_host_pool.free_list.size(); ++i) {
+            const size_t sz = g_host_pool.free_list[i].first;
+            if (sz >= bytes && sz - bytes <= bytes / 4 &&
+                (best < 0 || sz < g_host_pool.free_list[best].first))
+                best = i;
+        }
+        if (best >= 0) {
+            *out = g_host_pool.free_list[best].second;
+            g_host_pool.cached_bytes -= g_host_pool.free_list[best].first;
+            g_host_pool.live[*out] = g_host_pool.free_list[best].first;
+            g_host_pool.free_list.erase(g_host_pool.free_list.begin() + best);
+            return MXB_OK;
+        }
+    }
+    if (only_if_cached) return MXB_OK;   // *out stays NULL: the caller uses pageable memory
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return MXB_OK;                   // not an error: pageable memory still works
+    }
+    std::lock_guard<std::mutex> lock(g_host_pool.mu);
+    try { g_host_pool.live[p] = bytes; } catch (...) { cudaFreeHost(p); return MXB_OK; }
+    *out = p;
+    return MXB_OK;
+}
+
+int mxb_host_free(void *ptr) {
+    if (!ptr) return MXB_OK;
+    size_t sz = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_host_pool.mu);
+        auto it = g_host_pool.live.find(ptr);
+        MXB_REQUIRE(it != g_host_pool.live.end(), "not a block of mxb_host_alloc");
+        sz = it->second;
+        g_host_pool.live.erase(it);
+        if (g_host_pool.cached_bytes + sz <= host_pool_limit()) {
+            try {
+                g_host_pool.free_list.emplace_back(sz, ptr);
+                g_host_pool.cached_bytes += sz;
+                return MXB_OK;
+            } catch (...) {}
+        }
+    }
+    cudaFreeHost(ptr);
+    return MXB_OK;
+}
+
+int mxb_host_reserve(size_t bytes, int count) {
+    MXB_REQUIRE(bytes > 0 && count >= 1 && count <= 16, "bad argument");
+    std::vector<void *> got;
+    int rc = MXB_OK;
+    for (int i = 0; i < count && rc == MXB_OK; ++i) {
+        void *p = nullptr;
+        rc = mxb_host_alloc(bytes, 0, &p);
+        if (rc == MXB_OK && !p) {
+            set_error("mxb_host_reserve: could not pin %zu bytes", bytes);
+            rc = MXB_ERR_NOMEM;
+        }
+        if (p) got.push_back(p);
+    }
+    for (void *p : got) mxb_host_free(p);
+    return rc;
+}
+
+int mxb_stage_timing(int on) {
+    g_stage_on = on != 0 || getenv("MXB_TIMING") != nullptr;
+    for (int i = 0; i < kNumStages; ++i) g_stage_ms[i] = 0.0;
+    return MXB_OK;
+}
+
+int mxb_stage_times(double *ms_out, int n) {
+    MXB_REQUIRE(ms_out != nullptr && n >= 0, "bad argument");
+    for (int i = 0; i < n; ++i) ms_out[i] = i < kNumStages ? g_stage_ms[i] : 0.0;
+    return MXB_OK;
+}
+
+int mxb_host_trim(void) {
+    std::lock_guard<std::mutex> lock(g_host_pool.mu);
+    for (auto &ent : g_host_pool.free_list) cudaFreeHost(ent.second);
+    g_host_pool.free_list.clear();
+    g_host_pool.cached_bytes = 0;
     return MXB_OK;
 }
 
@@ -613,7 +829,11 @@ int mxb_matrix_upload(mxb_ctx *ctx, const double *host, int64_t n_rows,
     MXB_TRY(mxb_matrix_alloc(ctx, n_rows, n_cols, out));
     size_t bytes = (size_t)n_rows * (size_t)n_cols * sizeof(double);
     if (bytes) {
+        const auto t0 = std::chrono::steady_clock::now();
         const int rc = copy_h2d(ctx, (*out)->data, host, bytes);
+        if (g_stage_on)
+            g_stage_ms[kStageH2D] += std::chrono::duration<double, std::milli>(
+                std::chrono::steady_clock::now() - t0).count();
         if (rc != MXB_OK) {
             mxb_matrix_destroy(*out);
             *out = nullptr;

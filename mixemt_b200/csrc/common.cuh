@@ -70,6 +70,7 @@ struct mxb_ctx {
     // cudaMalloc'ed block [flags: 2 x world u64][seq u64][inbox: 2 x world x kP2PMaxLd doubles]
     // and maps the blocks of its peers through CUDA IPC over NVLink.
     bool p2p_ready = false;
+    double *p2p_vote = nullptr;   // one device double for the barriers of p2p_resync
     unsigned char *p2p_block[mxb::kP2PMaxWorld] = {};  // [r] = rank r's block as seen from here
 };
 
@@ -99,6 +100,10 @@ namespace mxb {
 
 int nccl_allreduce_sum_f64(mxb_ctx *ctx, double *dev_buf, int64_t n);
 int nccl_allreduce_f64(mxb_ctx *ctx, double *dev_buf, int64_t n, int op_is_max);
+int nccl_alltoall_rows(mxb_ctx *ctx, const double *src, double *recv, int64_t n_rows,
+                       int64_t n_cols, int64_t slot_doubles);
+int nccl_allgather_rows(mxb_ctx *ctx, double *m, int64_t n_rows, int64_t n_cols);
+int p2p_resync(mxb_ctx *ctx);   // zero the peer mailboxes behind a barrier (start of a sharded session)
 
 // Host <-> device copies of matrix-sized buffers (api.cu).  Pageable host memory
 // goes through a pinned staging ring filled/drained by several host threads
@@ -111,7 +116,8 @@ int copy_d2h(mxb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 // visible next to a 1.4 s run_em call; freed blocks of >= 1 MiB are therefore kept
 // per context (up to MXB_CACHE_MB, default a quarter of the device memory) and
 // handed out again to requests of about the same size.  An allocation that fails
-// releases the cache and retries.  Not thread-safe: one host thread per context.
+// releases the cache and retries.  The cache is guarded by a mutex (a Python GC may free a
+// matrix from any thread).
 constexpr size_t kPinnedScratchBytes = 4096;
 void *pinned_scratch(mxb_ctx *ctx);  // kPinnedScratchBytes of pinned host memory, NULL on failure
 cudaError_t dev_alloc(mxb_ctx *ctx, void **out, size_t bytes);
@@ -126,6 +132,14 @@ struct Prefault {
     void join();
     ~Prefault() { join(); }
 };
+
+// Wall-clock stage times of the one-call entry points (upload, session set-up, iterations,
+// read-matrix kernel, download), collected when mxb_stage_timing(1) is on (or MXB_TIMING=1,
+// which also prints them): bench.py's e2e breakdown.  Index = Stage.
+enum Stage { kStageH2D = 0, kStageSetup, kStageIterate, kStageReadMix, kStageD2H, kStageOther,
+             kNumStages };
+extern bool g_stage_on;
+extern double g_stage_ms[kNumStages];
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

@@ -40,6 +40,7 @@
 
 #include "common.cuh"
 #include "em_kernels.cuh"
+#include "em_tiles.cuh"
 
 
 using namespace mxb;
@@ -73,21 +74,18 @@ struct mxb_em {
     // Restart slots: a batched session (run_em with n_multi > 1) iterates two restarts per
     // read of L.  Slot s lives at lnp[b] + s*ld, pi[b] + s*ld, partials + s*n_part*ld, state + s.
     int n_slots = 1;
-    // Dictionary-coded rows (em_pack_kernel): when `coded` the pass reads `rec` (all rows,
-    // dense rows as empty records) and `dense_lin` (the gathered dense rows) instead of `lin`.
-    bool coded = false;
-    int pair_threads = 0;             // != 0: records hold chunk dictionaries laid out for a pass
-                                      // kernel of that many threads (em_pack_pairs_kernel)
-    unsigned char *rec = nullptr;     // [n_coded][rec_bytes]
-    int64_t n_coded = 0;              // rows of `rec`: all rows, or the coded ones only (compact)
-    size_t rec_bytes = 0;
-    double *w_coded = nullptr;        // [n_rows] weight, 0 for dense rows
-    double *dense_lin = nullptr;      // [n_dense][ld]
-    double *w_dense = nullptr;        // [n_dense]
-    int64_t n_dense = 0;
-    int coded_stages = 0;
-    size_t coded_smem = 0;
-    int grid_dense = 0;
+    // Class tiles (em_tiles.cuh): when `tiled` the pass reads `tile_v` instead of `lin`.
+    bool tiled = false;
+    int n_batches = 0, tile_hs = 0, tile_parts = 0, tile_grid = 0;
+    unsigned char *tile_block = nullptr;   // [perm][cmap][desc][order]
+    unsigned char *tile_vecs = nullptr;    // [pi_cls][u_cls]
+    unsigned short *tile_perm = nullptr, *tile_cmap = nullptr;
+    TileDesc *tile_desc = nullptr;
+    int *tile_order = nullptr;
+    double *tile_pi = nullptr, *tile_u = nullptr;
+    double *tile_v = nullptr;
+    int64_t tile_cells = 0;                // doubles in tile_v
+    int64_t tile_bytes_per_pass = 0;
     unsigned char *small = nullptr;  // one device block behind weights ... state (fewer driver calls)
     bool zero_iter = false;  // last iterate() ran no iteration
 };
@@ -95,7 +93,7 @@ struct mxb_em {
 namespace mxb {
 
 typedef void (*pass_fn)(const unsigned char *, uint32_t, int64_t, int64_t, const double *,
-                        const double *, const double *, EmState *, double *, int, int);
+                        const double *, const double *, EmState *, double *, int);
 
 static pass_fn pick_pass(int nc) {
     switch (nc) {
@@ -110,111 +108,6 @@ static pass_fn pick_pass(int nc) {
     }
     return nullptr;
 }
-// The coded pass and its CTA size.  Default: em_pass_coded_kernel, 512 threads, chunk count
-// `nc`.  Experimental, not yet run on a GPU:
-// MXB_EM_CODED_V3=1 (pipelined rows, no block barrier) and MXB_EM_CODED_T384=1 (the same
-// kernel with 384 threads: 16 instead of 12 cells per thread at H = 5408, so the per-row-pair
-// reduction, division and ring bookkeeping of a warp are spread over a third more cells).
-struct CodedPass {
-    pass_fn fn;
-    int threads;
-};
-static CodedPass pick_pass_coded(int nc, int64_t ld, int pair_threads) {
-    static const bool v3 = getenv("MXB_EM_CODED_V3") != nullptr;
-    static const bool t384 = getenv("MXB_EM_CODED_T384") != nullptr;
-    const int nc384 = (int)ceil_div(ld / 2, 384);   // chunks per thread of a 384-thread CTA
-    if (v3) {   // pipelined rows; over cell records or chunk records, 512 or 384 threads
-        if (pair_threads == 384) {
-            switch (nc384) {
-                case 1: return {em_pass_coded_v3_kernel<1, 384, true>, 384};
-                case 2: return {em_pass_coded_v3_kernel<2, 384, true>, 384};
-                case 3: return {em_pass_coded_v3_kernel<3, 384, true>, 384};
-                case 4: return {em_pass_coded_v3_kernel<4, 384, true>, 384};
-                case 5: return {em_pass_coded_v3_kernel<5, 384, true>, 384};
-                case 6: return {em_pass_coded_v3_kernel<6, 384, true>, 384};
-                case 7: return {em_pass_coded_v3_kernel<7, 384, true>, 384};
-                case 8: return {em_pass_coded_v3_kernel<8, 384, true>, 384};
-            }
-            return {nullptr, 0};
-        }
-        if (pair_threads != 0) {
-            switch (nc) {
-                case 1: return {em_pass_coded_v3_kernel<1, kPassThreads, true>, kPassThreads};
-                case 2: return {em_pass_coded_v3_kernel<2, kPassThreads, true>, kPassThreads};
-                case 3: return {em_pass_coded_v3_kernel<3, kPassThreads, true>, kPassThreads};
-                case 4: return {em_pass_coded_v3_kernel<4, kPassThreads, true>, kPassThreads};
-                case 5: return {em_pass_coded_v3_kernel<5, kPassThreads, true>, kPassThreads};
-                case 6: return {em_pass_coded_v3_kernel<6, kPassThreads, true>, kPassThreads};
-                case 7: return {em_pass_coded_v3_kernel<7, kPassThreads, true>, kPassThreads};
-                case 8: return {em_pass_coded_v3_kernel<8, kPassThreads, true>, kPassThreads};
-            }
-            return {nullptr, 0};
-        }
-        if (t384 && nc384 >= 6 && nc384 <= 8) {
-            switch (nc384) {
-                case 6: return {em_pass_coded_v3_kernel<6, 384, false>, 384};
-                case 7: return {em_pass_coded_v3_kernel<7, 384, false>, 384};
-                case 8: return {em_pass_coded_v3_kernel<8, 384, false>, 384};
-            }
-        }
-        switch (nc) {
-            case 1: return {em_pass_coded_v3_kernel<1>, kPassThreads};
-            case 2: return {em_pass_coded_v3_kernel<2>, kPassThreads};
-            case 3: return {em_pass_coded_v3_kernel<3>, kPassThreads};
-            case 4: return {em_pass_coded_v3_kernel<4>, kPassThreads};
-            case 5: return {em_pass_coded_v3_kernel<5>, kPassThreads};
-            case 6: return {em_pass_coded_v3_kernel<6>, kPassThreads};
-            case 7: return {em_pass_coded_v3_kernel<7>, kPassThreads};
-            case 8: return {em_pass_coded_v3_kernel<8>, kPassThreads};
-        }
-        return {nullptr, 0};
-    }
-    if (pair_threads == 384) {
-        switch (nc384) {
-            case 1: return {em_pass_coded_pairs_kernel<1, 384>, 384};
-            case 2: return {em_pass_coded_pairs_kernel<2, 384>, 384};
-            case 3: return {em_pass_coded_pairs_kernel<3, 384>, 384};
-            case 4: return {em_pass_coded_pairs_kernel<4, 384>, 384};
-            case 5: return {em_pass_coded_pairs_kernel<5, 384>, 384};
-            case 6: return {em_pass_coded_pairs_kernel<6, 384>, 384};
-            case 7: return {em_pass_coded_pairs_kernel<7, 384>, 384};
-            case 8: return {em_pass_coded_pairs_kernel<8, 384>, 384};
-        }
-        return {nullptr, 0};
-    }
-    if (pair_threads != 0) {
-        switch (nc) {
-            case 1: return {em_pass_coded_pairs_kernel<1>, kPassThreads};
-            case 2: return {em_pass_coded_pairs_kernel<2>, kPassThreads};
-            case 3: return {em_pass_coded_pairs_kernel<3>, kPassThreads};
-            case 4: return {em_pass_coded_pairs_kernel<4>, kPassThreads};
-            case 5: return {em_pass_coded_pairs_kernel<5>, kPassThreads};
-            case 6: return {em_pass_coded_pairs_kernel<6>, kPassThreads};
-            case 7: return {em_pass_coded_pairs_kernel<7>, kPassThreads};
-            case 8: return {em_pass_coded_pairs_kernel<8>, kPassThreads};
-        }
-        return {nullptr, 0};
-    }
-    if (t384 && nc384 >= 6 && nc384 <= 8) {   // other widths keep the 512-thread kernel
-        switch (nc384) {
-            case 6: return {em_pass_coded_kernel<6, 384>, 384};
-            case 7: return {em_pass_coded_kernel<7, 384>, 384};
-            case 8: return {em_pass_coded_kernel<8, 384>, 384};
-        }
-    }
-    switch (nc) {
-        case 1: return {em_pass_coded_kernel<1>, kPassThreads};
-        case 2: return {em_pass_coded_kernel<2>, kPassThreads};
-        case 3: return {em_pass_coded_kernel<3>, kPassThreads};
-        case 4: return {em_pass_coded_kernel<4>, kPassThreads};
-        case 5: return {em_pass_coded_kernel<5>, kPassThreads};
-        case 6: return {em_pass_coded_kernel<6>, kPassThreads};
-        case 7: return {em_pass_coded_kernel<7>, kPassThreads};
-        case 8: return {em_pass_coded_kernel<8>, kPassThreads};
-    }
-    return {nullptr, 0};
-}
-
 typedef void (*pair_fn)(const double *, int64_t, int64_t, const double *, const double *,
                         const double *, const double *, const double *, EmState *, double *,
                         double *, int);
@@ -226,32 +119,6 @@ static pair_fn pick_pair(int nc) {
         case 4: return em_pass_pair_kernel<4>;
         case 5: return em_pass_pair_kernel<5>;
         case 6: return em_pass_pair_kernel<6>;
-    }
-    return nullptr;
-}
-// the fp64 pair pass adding its column sums to what the coded pair pass left (dense rows)
-static pair_fn pick_pair_accumulate(int nc) {
-    switch (nc) {
-        case 1: return em_pass_pair_kernel<1, true>;
-        case 2: return em_pass_pair_kernel<2, true>;
-        case 3: return em_pass_pair_kernel<3, true>;
-        case 4: return em_pass_pair_kernel<4, true>;
-        case 5: return em_pass_pair_kernel<5, true>;
-        case 6: return em_pass_pair_kernel<6, true>;
-    }
-    return nullptr;
-}
-typedef void (*pair_coded_fn)(const unsigned char *, int64_t, int64_t, const double *,
-                              const double *, const double *, const double *, const double *,
-                              EmState *, double *, double *, int);
-static pair_coded_fn pick_pair_coded(int nc) {
-    switch (nc) {
-        case 1: return em_pass_pair_coded_kernel<1>;
-        case 2: return em_pass_pair_coded_kernel<2>;
-        case 3: return em_pass_pair_coded_kernel<3>;
-        case 4: return em_pass_pair_coded_kernel<4>;
-        case 5: return em_pass_pair_coded_kernel<5>;
-        case 6: return em_pass_pair_coded_kernel<6>;
     }
     return nullptr;
 }
@@ -279,30 +146,16 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 // One EM iteration on em->ctx->stream (no host sync).
+// `marks` (optional, 3 events) are recorded after the class sums, after the pass and after the
+// gather of a tiled iteration (after the pass only for fp64 rows): per-kernel attribution.
 static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
-                             cudaEvent_t pass_end = nullptr) {
+                             cudaEvent_t pass_end = nullptr, cudaEvent_t *marks = nullptr) {
     mxb_ctx *ctx = em->ctx;
     cudaStream_t s = ctx->stream;
     if (pass_begin) MXB_CUDA(cudaEventRecord(pass_begin, s));
     if (em->n_slots == 2) {
         const size_t ps = (size_t)em->n_part * em->ld;
-        if (em->coded) {
-            // chunk-coded records of all rows, then the fp64 rows of the dense ones on top
-            MXB_CUDA(launch_pdl(pick_pair_coded(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
-                                em->coded_smem, s, (const unsigned char *)em->rec, em->ld,
-                                em->n_coded, em->w_coded, em->pi[0], em->pi[1], em->pi[0] + em->ld,
-                                em->pi[1] + em->ld, em->state, em->partials, em->partials + ps,
-                                em->coded_stages));
-            ctx->launches += 1;
-            if (em->n_dense > 0) {
-                MXB_CUDA(launch_pdl(pick_pair_accumulate(em->nc), dim3(em->grid_fast),
-                                    dim3(kPassThreads), em->smem_bytes, s, em->dense_lin, em->ld,
-                                    em->n_dense, em->w_dense, em->pi[0], em->pi[1],
-                                    em->pi[0] + em->ld, em->pi[1] + em->ld, em->state,
-                                    em->partials, em->partials + ps, em->n_stages));
-                ctx->launches += 1;
-            }
-        } else {
+        {
             MXB_CUDA(launch_pdl(pick_pair(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
                                 em->smem_bytes, s, em->lin, em->ld, em->n_rows, em->weights,
                                 em->pi[0], em->pi[1], em->pi[0] + em->ld, em->pi[1] + em->ld,
@@ -318,29 +171,33 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
         ctx->launches += 1;
         return MXB_OK;
     }
-    if (em->coded) {
-        // dense rows first (their own small matrix), then the coded records of all rows on top;
-        // both launches use the same grid, so partials[cta] is written, then added to
-        if (em->n_dense > 0) {
-            MXB_CUDA(launch_pdl(pick_pass(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
-                                em->smem_bytes, s, (const unsigned char *)em->dense_lin,
-                                (uint32_t)(em->ld * sizeof(double)), em->ld, em->n_dense,
-                                em->w_dense, em->pi[0], em->pi[1], em->state, em->partials,
-                                em->n_stages, 0));
-            ctx->launches += 1;
-        }
-        const CodedPass cp = pick_pass_coded(em->nc, em->ld, em->pair_threads);
-        MXB_CUDA(launch_pdl(cp.fn, dim3(em->grid_fast), dim3(cp.threads),
-                            em->coded_smem, s, (const unsigned char *)em->rec,
-                            (uint32_t)em->rec_bytes, em->ld, em->n_coded, em->w_coded, em->pi[0],
-                            em->pi[1], em->state, em->partials, em->coded_stages,
-                            em->n_dense > 0 ? 1 : 0));
-        ctx->launches += 1;
+    if (em->tiled) {
+        MXB_CUDA(launch_pdl(tile_pi_kernel, dim3(std::min(em->n_batches, 3 * em->tile_grid)),
+                            dim3(kTileThreads), 0, s,
+                            (const unsigned short *)em->tile_perm,
+                            (const unsigned short *)em->tile_cmap, em->tile_hs, (int)em->n_cols,
+                            (const TileDesc *)em->tile_desc, em->n_batches,
+                            (const double *)em->pi[0], (const double *)em->pi[1],
+                            (const EmState *)em->state, em->tile_pi));
+        if (marks) MXB_CUDA(cudaEventRecord(marks[0], s));
+        MXB_CUDA(launch_pdl(tile_pass_kernel, dim3(em->tile_grid), dim3(kTileThreads),
+                            kTileSmemBytes, s, (const TileDesc *)em->tile_desc,
+                            (const int *)em->tile_order, em->n_batches,
+                            (const double *)em->tile_v, (const double *)em->tile_pi,
+                            (const double *)em->weights, em->state, em->tile_u));
+        if (marks) MXB_CUDA(cudaEventRecord(marks[1], s));
+        MXB_CUDA(launch_pdl(tile_gather_kernel, dim3((unsigned)ceil_div(em->ld, 256), em->tile_parts),
+                            dim3(256), 0, s, (const unsigned short *)em->tile_cmap, em->tile_hs,
+                            (int)em->n_cols, em->ld, (const TileDesc *)em->tile_desc,
+                            em->n_batches, (const double *)em->tile_u,
+                            (const EmState *)em->state, em->partials));
+        if (marks) MXB_CUDA(cudaEventRecord(marks[2], s));
+        ctx->launches += 3;
     } else if (em->fast) {
         MXB_CUDA(launch_pdl(pick_pass(em->nc), dim3(em->grid_fast), dim3(kPassThreads),
                             em->smem_bytes, s, (const unsigned char *)em->lin,
                             (uint32_t)(em->ld * sizeof(double)), em->ld, em->n_rows, em->weights,
-                            em->pi[0], em->pi[1], em->state, em->partials, em->n_stages, 0));
+                            em->pi[0], em->pi[1], em->state, em->partials, em->n_stages));
         ctx->launches += 1;
     } else {
         const int rd_blocks = (int)std::max<int64_t>(
@@ -353,6 +210,9 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
         ctx->launches += 2;
     }
     if (pass_end) MXB_CUDA(cudaEventRecord(pass_end, s));
+    if (marks && !em->tiled) {
+        for (int i = 0; i < 3; ++i) MXB_CUDA(cudaEventRecord(marks[i], s));
+    }
     if (em->fused_tail) {
         P2PArgs pa;
         memset(&pa, 0, sizeof(pa));
@@ -382,20 +242,24 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
     return MXB_OK;
 }
 
-// MXB_TIMING=1: wall-clock stage times of the one-call entry points on stderr.
+// Wall-clock stage times of the one-call entry points: collected into g_stage_ms when
+// mxb_stage_timing(1) is on, printed on stderr as well with MXB_TIMING=1.
 struct StageTimer {
-    bool on;
+    bool on, print;
     cudaStream_t stream;
     std::chrono::steady_clock::time_point t;
-    explicit StageTimer(cudaStream_t s) : on(getenv("MXB_TIMING") != nullptr), stream(s) {
+    explicit StageTimer(cudaStream_t s)
+        : on(g_stage_on || getenv("MXB_TIMING") != nullptr), print(getenv("MXB_TIMING") != nullptr),
+          stream(s) {
         if (on) t = std::chrono::steady_clock::now();
     }
-    void mark(const char *what) {
+    void mark(const char *what, int stage) {
         if (!on) return;
         cudaStreamSynchronize(stream);
         auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[mxb timing] %-28s %9.3f ms\n", what,
-                std::chrono::duration<double, std::milli>(now - t).count());
+        const double ms = std::chrono::duration<double, std::milli>(now - t).count();
+        g_stage_ms[stage] += ms;
+        if (print) fprintf(stderr, "[mxb timing] %-28s %9.3f ms\n", what, ms);
         t = now;
     }
 };
@@ -422,8 +286,9 @@ int mxb_em_destroy(mxb_em *em) {
     cudaSetDevice(em->ctx->device);
     cudaStreamSynchronize(em->ctx->stream);
     dev_free(em->ctx, em->lin);
-    dev_free(em->ctx, em->rec);
-    dev_free(em->ctx, em->dense_lin);
+    dev_free(em->ctx, em->tile_block);
+    dev_free(em->ctx, em->tile_vecs);
+    dev_free(em->ctx, em->tile_v);
     dev_free(em->ctx, em->small);
     for (int i = 0; i < 2; ++i)
         if (em->poll_ev[i]) cudaEventDestroy(em->poll_ev[i]);
@@ -445,142 +310,188 @@ __global__ void em_reset_state_kernel(EmState *st, long long max_iter, double to
     st->delta = 0.0;
 }
 
-// Dictionary-code the rows of em->lin (see em_pack_kernel).  On success with enough
-// codable rows the session switches to the coded pass and gives em->lin back; otherwise it
-// stays as it is.  MXB_EM_NO_PACK=1 keeps the fp64 rows (cross-check).
-static int em_pack_rows(mxb_em *em) {
+// Class tiles of the session's matrix (em_tiles.cuh), built straight from M: no N x ld copy of
+// L is ever allocated when this succeeds.  Falls through (MXB_OK, em->tiled == false) when the
+// matrix does not compress to less than half of its fp64 rows, when memory is short, or when
+// a batch fails the exact class check; the caller then sets up the fp64 rows.
+// MXB_EM_NO_PACK=1 keeps the fp64 rows (cross-check).
+template <int ITEMS>
+static cudaError_t launch_tile_class(mxb_ctx *ctx, int grid, const unsigned long long *hash, int hs,
+                                     int n_cols, int n_batches, unsigned short *perm,
+                                     unsigned short *cmap, unsigned short *rep, int *n_cls) {
+    using Sort = cub::BlockRadixSort<unsigned long long, kTileThreads, ITEMS, unsigned short>;
+    using Scan = cub::BlockScan<int, kTileThreads>;
+    const size_t smem = std::max(sizeof(typename Sort::TempStorage), sizeof(typename Scan::TempStorage));
+    cudaError_t e = cudaFuncSetAttribute((const void *)tile_class_kernel<ITEMS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tile_class_kernel<ITEMS><<<grid, kTileThreads, smem, ctx->stream>>>(hash, hs, n_cols, n_batches,
+                                                                        perm, cmap, rep, n_cls);
+    return cudaGetLastError();
+}
+
+static int em_pack_tiles(mxb_em *em) {
     mxb_ctx *ctx = em->ctx;
-    if (!em->fast || em->n_rows == 0 || getenv("MXB_EM_NO_PACK")) return MXB_OK;
-    // restart pairs read fp64 rows unless the chunk dictionary is asked for (experimental)
-    const bool two_slots = em->n_slots == 2;
-    if (two_slots && getenv("MXB_EM_CODED_PAIRS") == nullptr) return MXB_OK;
-    if (em->n_slots > 2) return MXB_OK;
-    const size_t row_bytes = (size_t)em->ld * sizeof(double);
-    // MXB_EM_CODED_PAIRS=1 (experimental): dictionaries of cell pairs, see em_pack_pairs_kernel
-    // (with MXB_EM_CODED_T384=1 laid out for the 384-thread pass kernel where the row fits it)
-    int pair_threads = 0;
-    if (getenv("MXB_EM_CODED_PAIRS") != nullptr && em->nc <= 8)
-        pair_threads = (!two_slots && getenv("MXB_EM_CODED_T384") != nullptr &&
-                        ceil_div(em->ld / 2, 384) <= 8) ? 384 : kPassThreads;
-    if (two_slots && pair_threads == 0) return MXB_OK;
-    const bool pairs = pair_threads != 0;
-    const size_t rec_bytes = pairs ? (size_t)pair_rec_bytes(pair_threads)
-                                   : (size_t)em->ld + kDictSize * sizeof(double);
-    constexpr int kMaxCodedStages = 16;
-    const size_t fixed = 2 * kPassWarps * kPassGroup * sizeof(double) +
-                         kMaxCodedStages * sizeof(uint64_t) + 256;
-    if (ctx->smem_optin <= fixed) return MXB_OK;
-    const int stages = (int)std::min<size_t>(kMaxCodedStages, (ctx->smem_optin - fixed) / rec_bytes);
-    if (stages < kPassGroup + 1) return MXB_OK;
-    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t n = (size_t)em->n_rows;
-    unsigned char *rec = nullptr, *tmp = nullptr;
-    cudaError_t e = dev_alloc(ctx, (void **)&rec, up(n * rec_bytes) + up(n * sizeof(double)));
-    if (e == cudaSuccess)
-        e = dev_alloc(ctx, (void **)&tmp, up(n * sizeof(int)) + up(n * sizeof(int64_t)) + 256);
-    if (e != cudaSuccess) {   // not enough memory for the coded copy: keep the fp64 rows
-        cudaGetLastError();
-        dev_free(ctx, rec);
-        dev_free(ctx, tmp);
+    if (!em->fast || !em->fused_tail || em->n_rows == 0 || em->n_cols > kTileMaxCols ||
+        getenv("MXB_EM_NO_PACK"))
         return MXB_OK;
-    }
-    double *w_coded = reinterpret_cast<double *>(rec + up(n * rec_bytes));
-    int *flag = reinterpret_cast<int *>(tmp);
-    int64_t *list = reinterpret_cast<int64_t *>(tmp + up(n * sizeof(int)));
-    int64_t *d_count = reinterpret_cast<int64_t *>(tmp + up(n * sizeof(int)) + up(n * sizeof(int64_t)));
-    int64_t n_dense = 0;
-    double *dense = nullptr;
-    const int grid = (int)std::min<int64_t>(em->n_rows, (int64_t)ctx->num_sms * 8);
-    if (pairs)
-        em_pack_pairs_kernel<<<grid, kPackThreads, (size_t)(em->ld / 2) * sizeof(unsigned short),
-                               ctx->stream>>>(em->lin, em->n_rows, em->ld, em->weights, rec,
-                                              pair_threads, flag, w_coded);
-    else
-        em_pack_kernel<<<grid, kPackThreads, (size_t)em->ld * sizeof(unsigned short), ctx->stream>>>(
-            em->lin, em->n_rows, em->ld, em->weights, rec, (int64_t)rec_bytes, flag, w_coded);
-    em_dense_list_kernel<<<1, 1024, 0, ctx->stream>>>(flag, em->n_rows, list, d_count);
-    ctx->launches += 2;
-    e = cudaGetLastError();
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(&n_dense, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    // worth it when the coded pass reads less than two thirds of the fp64 rows
-    const bool worth = e == cudaSuccess &&
-                       (double)n * rec_bytes + (double)n_dense * row_bytes < 0.66 * (double)n * row_bytes;
-    if (worth && n_dense > 0) {
-        e = dev_alloc(ctx, (void **)&dense, up((size_t)n_dense * row_bytes) + up((size_t)n_dense * sizeof(double)));
-        if (e == cudaSuccess) {
-            double *w_dense = reinterpret_cast<double *>((unsigned char *)dense + up((size_t)n_dense * row_bytes));
-            const int g = (int)std::min<int64_t>(n_dense, (int64_t)ctx->num_sms * 8);
-            em_gather_rows_kernel<<<g, 256, 0, ctx->stream>>>(em->lin, em->ld, em->weights, list,
-                                                               n_dense, dense, w_dense);
-            ctx->launches += 1;
-            e = cudaGetLastError();
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            em->w_dense = w_dense;
-        }
-    }
-    int64_t n_coded = em->n_rows;
-    if (e == cudaSuccess && worth && n_dense > 0 && getenv("MXB_EM_CODED_COMPACT") != nullptr) {
-        // records of the coded rows only (the flags and the list buffer are reused)
-        const int64_t n_keep = em->n_rows - n_dense;
-        unsigned char *rec2 = nullptr;
-        e = dev_alloc(ctx, (void **)&rec2, up((size_t)n_keep * rec_bytes) + up((size_t)n_keep * sizeof(double)) + 256);
-        if (e == cudaSuccess) {
-            double *w2 = reinterpret_cast<double *>(rec2 + up((size_t)n_keep * rec_bytes));
-            em_flag_invert_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(flag, em->n_rows);
-            em_dense_list_kernel<<<1, 1024, 0, ctx->stream>>>(flag, em->n_rows, list, d_count);
-            const int g = (int)std::max<int64_t>(1, std::min<int64_t>(n_keep, (int64_t)ctx->num_sms * 8));
-            em_gather_records_kernel<<<g, 256, 0, ctx->stream>>>(rec, (int64_t)rec_bytes, w_coded, list,
-                                                                  n_keep, rec2, w2);
-            ctx->launches += 3;
-            e = cudaGetLastError();
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e == cudaSuccess) {
-                dev_free(ctx, rec);
-                rec = rec2;
-                w_coded = w2;
-                n_coded = n_keep;
-            } else {
-                dev_free(ctx, rec2);
-            }
-        } else {       // no room for the compact copy: keep the records of all rows
-            cudaGetLastError();
-            e = cudaSuccess;
-        }
-    }
-    if (e == cudaSuccess && worth)
-        e = cudaFuncSetAttribute(two_slots ? (const void *)pick_pair_coded(em->nc)
-                                           : (const void *)pick_pass_coded(em->nc, em->ld, pair_threads).fn,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)((size_t)stages * rec_bytes + fixed));
-    if (e == cudaSuccess && worth && two_slots && n_dense > 0)
-        e = cudaFuncSetAttribute((const void *)pick_pair_accumulate(em->nc),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em->smem_bytes);
-    dev_free(ctx, tmp);
-    if (e != cudaSuccess || !worth) {
-        dev_free(ctx, rec);
-        dev_free(ctx, dense);
-        em->w_dense = nullptr;
-        if (e != cudaSuccess) {
-            set_error("em_pack_rows: %s", cudaGetErrorString(e));
+    const int64_t n = em->n_rows, h = em->n_cols;
+    const int nb = (int)ceil_div(n, kTileRows);
+    const int hs = (int)round_up(h, 8);
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_map = up((size_t)nb * hs * sizeof(unsigned short));
+    unsigned char *tmp = nullptr, *block = nullptr;
+    double *v = nullptr;
+    // scratch: [hash][rep][n_cls][bad]
+    const size_t b_hash = up((size_t)nb * hs * sizeof(unsigned long long));
+    const size_t b_int = up((size_t)nb * sizeof(int));
+    int rc = MXB_OK;
+    cudaError_t e = dev_alloc(ctx, (void **)&tmp, b_hash + b_map + 2 * b_int);
+    const bool verbose = getenv("MXB_TIMING") != nullptr;
+    auto give_up = [&](bool hard, const char *what) {
+        if (verbose)
+            fprintf(stderr, "[mxb tiles] not used: %s (%s)\n", what, cudaGetErrorString(e));
+        if (e != cudaSuccess) cudaGetLastError();
+        dev_free(ctx, tmp);
+        dev_free(ctx, block);
+        dev_free(ctx, v);
+        if (hard) {
+            set_error("em_pack_tiles (%s): %s", what, cudaGetErrorString(e));
             return e == cudaErrorMemoryAllocation ? MXB_ERR_NOMEM : MXB_ERR_CUDA;
         }
         return MXB_OK;
+    };
+    if (e != cudaSuccess) return give_up(false, "scratch");
+    unsigned long long *hash = reinterpret_cast<unsigned long long *>(tmp);
+    unsigned short *rep = reinterpret_cast<unsigned short *>(tmp + b_hash);
+    int *d_ncls = reinterpret_cast<int *>(tmp + b_hash + b_map);
+    int *d_bad = reinterpret_cast<int *>(tmp + b_hash + b_map + b_int);
+    // persistent: [perm][cmap][desc][order] first, class vectors appended once their size is known
+    const size_t b_desc = up((size_t)nb * sizeof(TileDesc));
+    const size_t head_bytes = 2 * b_map + b_desc + b_int;
+    // (allocated with room for the class vectors of the widest possible layout only after the
+    // class counts are known; the maps are written into a first block and kept)
+    unsigned char *maps = nullptr;
+    e = dev_alloc(ctx, (void **)&maps, head_bytes);
+    if (e != cudaSuccess) return give_up(false, "maps");
+    block = maps;
+    unsigned short *perm = reinterpret_cast<unsigned short *>(maps);
+    unsigned short *cmap = reinterpret_cast<unsigned short *>(maps + b_map);
+    TileDesc *d_desc = reinterpret_cast<TileDesc *>(maps + 2 * b_map);
+    int *d_order = reinterpret_cast<int *>(maps + 2 * b_map + b_desc);
+
+    const int grid = std::min(nb, ctx->num_sms * 2);
+    tile_hash_kernel<<<std::min(nb, ctx->num_sms * 4), kTileThreads, 0, ctx->stream>>>(
+        em->mat->data, n, h, nb, hash, hs);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        const int items = (int)ceil_div(h, kTileThreads);
+        if (items <= 4) e = launch_tile_class<4>(ctx, grid, hash, hs, (int)h, nb, perm, cmap, rep, d_ncls);
+        else if (items <= 8) e = launch_tile_class<8>(ctx, grid, hash, hs, (int)h, nb, perm, cmap, rep, d_ncls);
+        else if (items <= 12) e = launch_tile_class<12>(ctx, grid, hash, hs, (int)h, nb, perm, cmap, rep, d_ncls);
+        else e = launch_tile_class<16>(ctx, grid, hash, hs, (int)h, nb, perm, cmap, rep, d_ncls);
     }
-    em->coded = true;
-    em->pair_threads = pair_threads;
-    em->rec = rec;
-    em->n_coded = n_coded;
-    em->rec_bytes = rec_bytes;
-    em->w_coded = w_coded;
-    em->dense_lin = dense;
-    em->n_dense = n_dense;
-    em->coded_stages = stages;
-    em->coded_smem = (size_t)stages * rec_bytes + fixed;
-    dev_free(ctx, em->lin);   // every pass reads the records and the dense rows from now on
-    em->lin = nullptr;
-    return MXB_OK;
+    ctx->launches += 2;
+    std::vector<int> ncls((size_t)nb);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ncls.data(), d_ncls, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost,
+                            ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return give_up(true, "classes");
+
+    // layout: team width and chunk count per batch, tile and class-vector offsets
+    std::vector<TileDesc> desc((size_t)nb);
+    std::vector<int> order((size_t)nb);
+    int64_t v_cells = 0, p_cells = 0;
+    for (int b = 0; b < nb; ++b) {
+        TileDesc &d = desc[(size_t)b];
+        d.row0 = b * kTileRows;
+        d.n_rows = (int)std::min<int64_t>(kTileRows, n - (int64_t)b * kTileRows);
+        d.n_cls = ncls[(size_t)b];
+        int tw = 1;
+        while (tw < kTileWarps && d.n_cls > 512 * tw) tw *= 2;
+        d.tw = tw;
+        d.nk = (int)std::max<int64_t>(1, ceil_div(d.n_cls, 64 * tw));
+        d.c_pad = 64 * tw * d.nk;
+        d.v_off = v_cells;
+        d.p_off = p_cells;
+        v_cells += (int64_t)d.n_rows * d.c_pad;
+        p_cells += d.c_pad;
+        order[(size_t)b] = b;
+    }
+    // a team handles its rows one after the other and a CTA holds 16 / tw teams: the time of a
+    // batch grows with tw (fewer rows at a time) and with the chunks per thread
+    auto batch_cost = [&](int b) {
+        const TileDesc &d = desc[(size_t)b];
+        return (int64_t)d.n_rows * d.tw * (48 + 8 * d.nk);
+    };
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return batch_cost(a) > batch_cost(b); });
+    const double tile_bytes = (double)v_cells * 8 + 3.0 * (double)nb * hs * 2 + 4.0 * (double)p_cells * 8;
+    const double fp64_bytes = (double)n * (double)em->ld * 8;
+    if (verbose) {
+        int64_t c_sum = 0, c_max = 0, wide = 0;
+        for (int b = 0; b < nb; ++b) {
+            c_sum += desc[(size_t)b].n_cls;
+            c_max = std::max<int64_t>(c_max, desc[(size_t)b].n_cls);
+            wide += desc[(size_t)b].tw > 1;
+        }
+        fprintf(stderr, "[mxb tiles] %d batches of %d rows: classes mean %.1f max %lld, %lld wide "
+                "batches, tiles %.3f GB (+ maps and vectors: %.3f GB) vs fp64 rows %.3f GB\n",
+                nb, kTileRows, (double)c_sum / nb, (long long)c_max, (long long)wide,
+                (double)v_cells * 8 / 1e9, tile_bytes / 1e9, fp64_bytes / 1e9);
+    }
+    if (tile_bytes > 0.5 * fp64_bytes) return give_up(false, "not worth it");
+
+    e = dev_alloc(ctx, (void **)&v, (size_t)v_cells * sizeof(double));
+    unsigned char *vecs = nullptr;
+    if (e == cudaSuccess) e = dev_alloc(ctx, (void **)&vecs, 2 * up((size_t)p_cells * sizeof(double)));
+    if (e != cudaSuccess) { dev_free(ctx, vecs); return give_up(false, "tiles"); }
+    double *pi_cls = reinterpret_cast<double *>(vecs);
+    double *u_cls = reinterpret_cast<double *>(vecs + up((size_t)p_cells * sizeof(double)));
+    e = cudaMemcpyAsync(d_desc, desc.data(), (size_t)nb * sizeof(TileDesc), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_order, order.data(), (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(vecs, 0, 2 * up((size_t)p_cells * sizeof(double)), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, (size_t)nb * sizeof(int), ctx->stream);
+    if (e == cudaSuccess) {
+        tile_fill_kernel<<<std::min(nb, ctx->num_sms * 4), kTileThreads, 0, ctx->stream>>>(
+            em->mat->data, h, d_desc, nb, cmap, rep, hs, v, d_bad);
+        ctx->launches += 1;
+        e = cudaGetLastError();
+    }
+    std::vector<int> bad((size_t)nb);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(bad.data(), d_bad, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute((const void *)tile_pass_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+    if (e != cudaSuccess) { dev_free(ctx, vecs); return give_up(true, "fill"); }
+    bool any_bad = false;
+    for (int b = 0; b < nb; ++b) any_bad |= bad[(size_t)b] != 0;
+    if (any_bad) { dev_free(ctx, vecs); return give_up(false, "hash collision"); }
+
+    dev_free(ctx, tmp);
+    em->tiled = true;
+    em->n_batches = nb;
+    em->tile_hs = hs;
+    em->tile_block = maps;
+    em->tile_vecs = vecs;
+    em->tile_perm = perm;
+    em->tile_cmap = cmap;
+    em->tile_desc = d_desc;
+    em->tile_order = d_order;
+    em->tile_pi = pi_cls;
+    em->tile_u = u_cls;
+    em->tile_v = v;
+    em->tile_cells = v_cells;
+    em->tile_grid = std::min(nb, ctx->num_sms);
+    em->tile_parts = std::max(1, std::min(32, nb / 8));
+    em->n_part = em->tile_parts;
+    // what an iteration reads: the tiles, perm + cmap (Pi), cmap (gather), the class vectors
+    em->tile_bytes_per_pass = v_cells * 8 + 3 * (int64_t)nb * hs * 2 + 4 * p_cells * 8 + n * 8;
+    return rc;
 }
 
 static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int sharded,
@@ -643,7 +554,6 @@ static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weigh
 
     cudaError_t e = cudaSuccess;
 #define STEP(call) do { if (e == cudaSuccess) e = (call); } while (0)
-    STEP(dev_alloc(ctx, (void **)&em->lin, (size_t)em->n_rows * row_bytes));
     const size_t ns = (size_t)em->n_slots;
     {   // everything else of the session in one block: [weights][coef][lnp x2][pi x2][partials]
         // [tsum][props_in][state], each 256-byte aligned
@@ -677,7 +587,18 @@ static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weigh
     if (em->n_rows > 0)
         STEP(cudaMemcpyAsync(em->weights, weights, em->n_rows * sizeof(double),
                              cudaMemcpyHostToDevice, ctx->stream));
-    if (e == cudaSuccess && em->n_rows > 0) {
+    STEP(cudaStreamSynchronize(ctx->stream));
+    if (e == cudaSuccess) {
+        // class tiles straight from M; only a matrix that does not compress gets fp64 rows of L
+        const int rc = em_pack_tiles(em);
+        if (rc != MXB_OK) {
+            mxb_em_destroy(em);
+            return rc;
+        }
+        if (em->tiled) em->n_slots = 1;   // restarts run one at a time over the tiles
+    }
+    if (!em->tiled) STEP(dev_alloc(ctx, (void **)&em->lin, (size_t)em->n_rows * row_bytes));
+    if (e == cudaSuccess && em->n_rows > 0 && !em->tiled) {
         const int grid = (int)std::min<int64_t>(em->n_rows, (int64_t)ctx->num_sms * 8);
         to_linear_kernel<<<grid, 256, 0, ctx->stream>>>(m->data, em->n_rows, em->n_cols, em->ld,
                                                         em->lin);
@@ -692,7 +613,9 @@ static int em_create_impl(mxb_ctx *ctx, const mxb_matrix *m, const double *weigh
         mxb_em_destroy(em);
         return e == cudaErrorMemoryAllocation ? MXB_ERR_NOMEM : MXB_ERR_CUDA;
     }
-    const int rc = em_pack_rows(em);
+    int rc = MXB_OK;
+    // a sharded session starts from zeroed peer mailboxes on every rank (collective)
+    if (rc == MXB_OK && em->sharded && ctx->world > 1 && em->fused_tail) rc = p2p_resync(ctx);
     if (rc != MXB_OK) {
         mxb_em_destroy(em);
         return rc;
@@ -713,10 +636,13 @@ int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights, int 
 int mxb_em_pass_bytes(const mxb_em *em, int64_t *bytes_per_pass, int64_t *n_dense_rows) {
     MXB_REQUIRE(em != nullptr, "NULL argument");
     const int64_t row_bytes = em->ld * (int64_t)sizeof(double);
-    if (bytes_per_pass)
-        *bytes_per_pass = em->coded ? em->n_coded * (int64_t)em->rec_bytes + em->n_dense * row_bytes
-                                    : em->n_rows * row_bytes;
-    if (n_dense_rows) *n_dense_rows = em->coded ? em->n_dense : -1;
+    if (bytes_per_pass && em->tiled) {
+        *bytes_per_pass = em->tile_bytes_per_pass;
+        if (n_dense_rows) *n_dense_rows = 0;
+        return MXB_OK;
+    }
+    if (bytes_per_pass) *bytes_per_pass = em->n_rows * row_bytes;
+    if (n_dense_rows) *n_dense_rows = -1;
     return MXB_OK;
 }
 
@@ -847,6 +773,36 @@ int mxb_em_iterate_fixed(mxb_em *em, int64_t n_iter, float *elapsed_ms, float *p
     return MXB_OK;
 }
 
+int mxb_em_profile(mxb_em *em, int64_t n_iter, float *ms_out) {
+    MXB_REQUIRE(em != nullptr && ms_out != nullptr && n_iter >= 1 && n_iter <= 10000, "bad argument");
+    MXB_REQUIRE(em->n_slots == 1, "single-restart sessions only");
+    mxb_ctx *ctx = em->ctx;
+    MXB_CUDA(cudaSetDevice(ctx->device));
+    em->zero_iter = false;
+    MXB_TRY(reset_state(em, (long long)1 << 60, -1.0));
+    std::vector<cudaEvent_t> evs((size_t)n_iter * 5);
+    for (auto &e : evs) MXB_CUDA(cudaEventCreate(&e));
+    for (int64_t i = 0; i < n_iter; ++i) {
+        cudaEvent_t *e = &evs[(size_t)i * 5];
+        MXB_TRY(enqueue_iteration(em, e[0], nullptr, e + 1));
+        MXB_CUDA(cudaEventRecord(e[4], ctx->stream));
+    }
+    MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+    double tot[4] = {0, 0, 0, 0};
+    for (int64_t i = 0; i < n_iter; ++i) {
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            MXB_CUDA(cudaEventElapsedTime(&ms, evs[(size_t)i * 5 + k], evs[(size_t)i * 5 + k + 1]));
+            tot[k] += ms;
+        }
+    }
+    for (auto &e : evs) cudaEventDestroy(e);
+    // fp64 rows: the three marks coincide after the pass, so [0] holds the pass
+    if (!em->tiled) { tot[1] = tot[0]; tot[0] = 0.0; }
+    for (int k = 0; k < 4; ++k) ms_out[k] = (float)(tot[k] / (double)n_iter);
+    return MXB_OK;
+}
+
 int mxb_em_get_lnprops(mxb_em *em, int which, double *out) {
     MXB_REQUIRE(em != nullptr && out != nullptr && (which == 0 || which == 1), "bad argument");
     mxb_ctx *ctx = em->ctx;
@@ -887,26 +843,41 @@ int mxb_matrix_fold_ranks(mxb_ctx *ctx, mxb_matrix *m, double sub_log) {
     MXB_CUDA(cudaSetDevice(ctx->device));
     const int64_t n = m->n_rows * m->n_cols;
     if (n == 0) return MXB_OK;
-    const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 16);
-    double *mx = nullptr;
-    MXB_CUDA(cudaMalloc(&mx, n * sizeof(double)));
-    int rc = MXB_OK;
-    cudaError_t e = cudaMemcpyAsync(mx, m->data, n * sizeof(double), cudaMemcpyDeviceToDevice,
-                                    ctx->stream);
-    if (e != cudaSuccess) rc = MXB_ERR_CUDA;
-    if (rc == MXB_OK) rc = nccl_allreduce_f64(ctx, mx, n, 1);
-    if (rc == MXB_OK) {
-        fold_exp_kernel<<<grid, 256, 0, ctx->stream>>>(m->data, mx, n);
-        ctx->launches++;
-        rc = nccl_allreduce_f64(ctx, m->data, n, 0);
+    const int W = ctx->world, me = ctx->rank;
+    cudaStream_t s = ctx->stream;
+    if (W <= 1 || !ctx->nccl_comm) {
+        if (sub_log != 0.0) {
+            const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 16);
+            fold_shift_kernel<<<grid, 256, 0, s>>>(m->data, n, sub_log);
+            ctx->launches++;
+            MXB_CUDA(cudaGetLastError());
+        }
+        MXB_CUDA(cudaStreamSynchronize(s));
+        return MXB_OK;
     }
-    if (rc == MXB_OK) {
-        fold_log_kernel<<<grid, 256, 0, ctx->stream>>>(m->data, mx, n, sub_log);
+    // all-to-all of row shards, local logaddexp fold in rank order (restarts are
+    // dealt in contiguous blocks, so rank order is restart order), shards gathered back.
+    const int64_t lo = m->n_rows * me / W, hi = m->n_rows * (me + 1) / W;
+    const int64_t max_rows = ceil_div(m->n_rows, W);
+    const int64_t slot = max_rows * m->n_cols;
+    double *recv = nullptr;
+    if (dev_alloc(ctx, (void **)&recv, (size_t)W * (size_t)slot * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("mxb_matrix_fold_ranks: no memory for the %d receive slots", W);
+        return MXB_ERR_NOMEM;
+    }
+    int rc = nccl_alltoall_rows(ctx, m->data, recv, m->n_rows, m->n_cols, slot);
+    if (rc == MXB_OK && hi > lo) {
+        const int64_t cells = (hi - lo) * m->n_cols;
+        const int grid = (int)std::min<int64_t>(ceil_div(cells, 256), (int64_t)ctx->num_sms * 16);
+        fold_shards_kernel<<<grid, 256, 0, s>>>(m->data + lo * m->n_cols, recv, slot, cells, W, me,
+                                                 sub_log);
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) rc = MXB_ERR_CUDA;
     }
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == MXB_OK) rc = MXB_ERR_CUDA;
-    cudaFree(mx);
+    if (rc == MXB_OK) rc = nccl_allgather_rows(ctx, m->data, m->n_rows, m->n_cols);
+    if (cudaStreamSynchronize(s) != cudaSuccess && rc == MXB_OK) rc = MXB_ERR_CUDA;
+    dev_free(ctx, recv);
     if (rc == MXB_ERR_CUDA && mxb_last_error()[0] == 0) set_error("mxb_matrix_fold_ranks: CUDA failure");
     return rc;
 }
@@ -1070,9 +1041,9 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
     const int want_slots = (n_multi >= 2 && max_iter > 0 && !sharded &&
                             getenv("MXB_EM_NO_BATCH") == nullptr) ? 2 : 1;
     int rc = em_create_impl(ctx, m, weights, sharded, want_slots, &em);
-    tm.mark("em_create (alloc+to_linear)");
+    tm.mark("em_create (tiles or fp64 rows)", kStageSetup);
     if (rc == MXB_OK && want_mix) rc = mxb_matrix_alloc(ctx, m->n_rows, h, &mix);
-    tm.mark("alloc read_mix");
+    tm.mark("alloc read_mix", kStageSetup);
     // (started after the device allocations: page faults and cudaMalloc contend for the
     // process's mmap lock)
     if (rc == MXB_OK && read_mix_out)
@@ -1081,14 +1052,14 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
     if (batched) {
         rc = run_em_batched(em, init_lnprops, n_multi, max_iter, tol, raw, mix, props_out,
                             iters_out, converged_out);
-        tm.mark("iterate (two restarts per pass)");
+        tm.mark("iterate (two restarts per pass)", kStageIterate);
     }
     for (int32_t i = 0; rc == MXB_OK && !batched && i < n_multi; ++i) {
         int64_t iters = 0;
         int32_t conv = 0;
         rc = mxb_em_set_lnprops(em, init_lnprops + (size_t)i * h);
         if (rc == MXB_OK) rc = mxb_em_iterate(em, max_iter, tol, &iters, &conv);
-        tm.mark("iterate");
+        tm.mark("iterate", kStageIterate);
         if (iters_out) iters_out[i] = iters;
         if (converged_out) converged_out[i] = conv;
         if (rc == MXB_OK) rc = mxb_em_get_lnprops(em, 0, cur.data());
@@ -1101,7 +1072,7 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
             const bool last = (i == n_multi - 1);
             const double sub = (last && n_multi > 1 && !raw) ? log((double)n_multi) : 0.0;
             rc = mxb_em_read_mix(em, mix, i == 0 ? 0 : 1, sub);
-            tm.mark("read_mix kernel");
+            tm.mark("read_mix kernel", kStageReadMix);
         }
     }
     if (rc == MXB_OK) {
@@ -1116,7 +1087,7 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
         if (read_mix_out) {
             fault_mix.join();
             rc = mxb_matrix_download(ctx, mix, read_mix_out);
-            tm.mark("download read_mix");
+            tm.mark("download read_mix", kStageD2H);
         }
         else if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
             set_error("mxb_run_em: stream sync failed");
@@ -1126,7 +1097,7 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
     mxb_em_destroy(em);
     if (rc == MXB_OK && read_mix_dev) *read_mix_dev = mix;
     else mxb_matrix_destroy(mix);
-    tm.mark("free");
+    tm.mark("free", kStageOther);
     return rc;
 }
 

@@ -1,19 +1,11 @@
-// Device code of kernel 2 (the EM fit): everything csrc/em.cu launches.  See em.cu for the
-// formulation and the host side.  Kept in a header of its own so that tests/emul/ can compile
-// the very same kernel bodies for the host (MXB_CPU_EMUL: cooperative fibers stand in for the
-// threads of a CTA, a few dozen lines stand in for mbarriers, bulk copies and shuffles) and
-// check their index arithmetic and synchronisation without a GPU.  The product never defines
-// MXB_CPU_EMUL; nvcc sees exactly the code that used to sit at the top of em.cu.
+// Device code of kernel 2 (the EM fit) over fp64 rows: everything csrc/em.cu launches except
+// the class-tile kernels (em_tiles.cuh).  See em.cu for the formulation and the host side.
 #pragma once
 
-#ifdef MXB_CPU_EMUL
-#define MXB_DYN_SHARED extern          /* the emulator defines the arrays */
-#else
 #include <cooperative_groups.h>
 
 #include "common.cuh"
 #define MXB_DYN_SHARED extern __shared__
-#endif
 
 #include <math.h>
 #include <stdint.h>
@@ -42,9 +34,6 @@ constexpr int kMaxNC = 8;           // column chunks (double2) per thread
 constexpr int kLdAlign = 16;        // row stride of L in doubles (128 B)
 
 // ---- small PTX helpers ------------------------------------------------------
-// (tests/emul/ compiles the kernels of this file for the host with MXB_CPU_EMUL and its own
-// versions of these helpers: an interleaving model of the CTA, test infrastructure only)
-#ifndef MXB_CPU_EMUL
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -123,8 +112,6 @@ __device__ __forceinline__ double2 lds_v2_f64(uint32_t addr) {
     return v;
 }
 
-#endif  // MXB_CPU_EMUL
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -185,223 +172,6 @@ to_linear_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols, i
     }
 }
 
-// ---- dictionary-coded rows -----------------------------------------------------
-// A row of the matrix built by kernel 1 holds few distinct values (one per class of
-// haplotypes with the same match pattern: median 56, at most 256 for 93 % of the config-2
-// rows), and so does its row of L.  Such a row is stored losslessly as one byte per cell
-// plus a table of 256 doubles -- ld + 2048 bytes instead of 8 ld (5.8x fewer at H = 5408) --
-// and the pass kernel looks the values up in shared memory: the same numbers enter the same
-// sums in the same order, with a fraction of the HBM traffic.  Rows with more distinct
-// values ("dense rows") are gathered into a small fp64 matrix of their own and go through
-// the uncoded pass kernel.  Record of row r: [ld code bytes][256 doubles] at r * rec_bytes;
-// the record of a dense row has a zeroed table and weight 0, so it adds exactly nothing.
-constexpr int kDictSize = 256;
-constexpr int kDictSlots = 1024;      // hash slots of the coder (at most 512 ever taken)
-constexpr int kPackThreads = 256;
-constexpr unsigned long long kDictEmpty = 0xFFFFFFFFFFFFFFFFull;  // a NaN L never holds
-
-__global__ void __launch_bounds__(kPackThreads)
-em_pack_kernel(const double *__restrict__ lin, int64_t n_rows, int64_t ld,
-               const double *__restrict__ weights, unsigned char *__restrict__ rec,
-               int64_t rec_bytes, int *__restrict__ dense_flag, double *__restrict__ w_coded) {
-    __shared__ unsigned long long keys[kDictSlots];
-    __shared__ unsigned short ids[kDictSlots];
-    __shared__ int count;
-    MXB_DYN_SHARED unsigned short cell_slot[];   // [ld] hash slot of every cell
-    const int tid = threadIdx.x;
-    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
-        for (int i = tid; i < kDictSlots; i += kPackThreads) keys[i] = kDictEmpty;
-        if (tid == 0) count = 0;
-        __syncthreads();
-        const double *src = lin + r * ld;
-        for (int64_t j = tid; j < ld; j += kPackThreads) {
-            if (*reinterpret_cast<volatile int *>(&count) > kDictSize) break;
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(src[j]);
-            if (bits == kDictEmpty) { atomicAdd(&count, kDictSize + 1); break; }
-            unsigned h = (unsigned)((bits * 0x9E3779B97F4A7C15ull) >> 54);
-            while (true) {
-                const unsigned long long old = atomicCAS(&keys[h], kDictEmpty, bits);
-                if (old == kDictEmpty) {   // first sight of the value: next free code
-                    ids[h] = (unsigned short)atomicAdd(&count, 1);
-                    break;
-                }
-                if (old == bits) break;
-                h = (h + 1) & (kDictSlots - 1);
-            }
-            cell_slot[j] = (unsigned short)h;
-        }
-        __syncthreads();
-        const bool coded = count <= kDictSize;   // block-uniform
-        unsigned char *out = rec + r * rec_bytes;
-        double *tab = reinterpret_cast<double *>(out + ld);
-        for (int i = tid; i < kDictSize; i += kPackThreads) tab[i] = 0.0;
-        __syncthreads();
-        if (coded) {
-            for (int64_t j = tid; j < ld; j += kPackThreads) out[j] = (unsigned char)ids[cell_slot[j]];
-            for (int i = tid; i < kDictSlots; i += kPackThreads)
-                if (keys[i] != kDictEmpty) tab[ids[i]] = __longlong_as_double((long long)keys[i]);
-        } else {
-            for (int64_t j = tid; j < ld; j += kPackThreads) out[j] = 0;
-        }
-        if (tid == 0) {
-            dense_flag[r] = coded ? 0 : 1;
-            w_coded[r] = coded ? weights[r] : 0.0;
-        }
-        __syncthreads();
-    }
-}
-
-// Experimental (MXB_EM_CODED_PAIRS=1, not yet run on a GPU): the dictionary holds the values
-// of a *chunk* -- the two adjacent cells 2c, 2c + 1 one pass-kernel thread handles together --
-// instead of single cells.  91.6 % of the config-2 rows have at most 256 distinct chunks
-// (92.4 % have at most 256 distinct cells: tests/analysis/pair_codes.py), so about the same
-// rows stay coded, and a chunk costs the pass one table lookup (LDS.128) instead of two
-// (LDS.64) and half the index arithmetic.  Record of row r, pair_rec_bytes(T) bytes:
-//   [T x 8 code bytes: byte k of thread t = code of chunk t + k * T]   (T = threads of the pass)
-//   [256 x double2: the two values of a chunk]
-// so a thread fetches all its codes of a row with one 8-byte load.  The hash key of a chunk
-// is a 64-bit mix of its two values; every chunk is compared with the chunk that claimed its
-// slot afterwards, and a row with a key collision between different chunks simply stays dense.
-constexpr int kPairTableBytes = kDictSize * 16;
-// record bytes for a pass kernel of `pass_threads` threads: 8 code bytes per thread + the table
-__host__ __device__ constexpr int pair_rec_bytes(int pass_threads) {
-    return pass_threads * 8 + kPairTableBytes;
-}
-
-__device__ __forceinline__ unsigned long long pair_key(unsigned long long a, unsigned long long b) {
-    unsigned long long k = (a ^ (b << 29 | b >> 35)) * 0x9E3779B97F4A7C15ull;
-    k ^= b * 0xC2B2AE3D27D4EB4Full;
-    k ^= k >> 31;
-    return k == kDictEmpty ? 0x5851F42D4C957F2Dull : k;
-}
-
-__global__ void __launch_bounds__(kPackThreads)
-em_pack_pairs_kernel(const double *__restrict__ lin, int64_t n_rows, int64_t ld,
-                     const double *__restrict__ weights, unsigned char *__restrict__ rec,
-                     int pass_threads, int *__restrict__ dense_flag, double *__restrict__ w_coded) {
-    const int rec_bytes = pair_rec_bytes(pass_threads);
-    __shared__ unsigned long long keys[kDictSlots];
-    __shared__ int rep[kDictSlots];            // the chunk that claimed the slot
-    __shared__ unsigned short ids[kDictSlots];
-    __shared__ int count;
-    __shared__ int clash;
-    MXB_DYN_SHARED unsigned short chunk_slot[];   // [ld / 2] hash slot of every chunk
-    const int tid = threadIdx.x;
-    const int n_chunks = (int)(ld >> 1);
-    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
-        for (int i = tid; i < kDictSlots; i += kPackThreads) keys[i] = kDictEmpty;
-        if (tid == 0) { count = 0; clash = 0; }
-        __syncthreads();
-        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(lin + r * ld);
-        for (int c = tid; c < n_chunks; c += kPackThreads) {
-            if (*reinterpret_cast<volatile int *>(&count) > kDictSize) break;
-            const ulonglong2 ab = src[c];
-            const unsigned long long key = pair_key(ab.x, ab.y);
-            unsigned h = (unsigned)(key >> 54);
-            while (true) {
-                const unsigned long long old = atomicCAS(&keys[h], kDictEmpty, key);
-                if (old == kDictEmpty) {   // first sight of the key: next free code
-                    rep[h] = c;
-                    ids[h] = (unsigned short)atomicAdd(&count, 1);
-                    break;
-                }
-                if (old == key) break;
-                h = (h + 1) & (kDictSlots - 1);
-            }
-            chunk_slot[c] = (unsigned short)h;
-        }
-        __syncthreads();
-        bool coded = count <= kDictSize;   // block-uniform
-        if (coded) {
-            for (int c = tid; c < n_chunks; c += kPackThreads) {
-                const ulonglong2 ab = src[c], rp = src[rep[chunk_slot[c]]];
-                if (ab.x != rp.x || ab.y != rp.y) clash = 1;
-            }
-        }
-        __syncthreads();
-        coded = coded && clash == 0;
-        unsigned char *out = rec + r * (int64_t)rec_bytes;
-        for (int i = tid; i < rec_bytes / 8; i += kPackThreads)
-            reinterpret_cast<unsigned long long *>(out)[i] = 0ull;
-        __syncthreads();
-        if (coded) {
-            for (int c = tid; c < n_chunks; c += kPackThreads)
-                out[(c % pass_threads) * 8 + c / pass_threads] = (unsigned char)ids[chunk_slot[c]];
-            ulonglong2 *tab = reinterpret_cast<ulonglong2 *>(out + pass_threads * 8);
-            for (int i = tid; i < kDictSlots; i += kPackThreads)
-                if (keys[i] != kDictEmpty) tab[ids[i]] = src[rep[i]];
-        }
-        if (tid == 0) {
-            dense_flag[r] = coded ? 0 : 1;
-            w_coded[r] = coded ? weights[r] : 0.0;
-        }
-        __syncthreads();
-    }
-}
-
-// Positions of the dense rows, in row order (one block: deterministic, N / 1024 steps).
-__global__ void __launch_bounds__(1024)
-em_dense_list_kernel(const int *__restrict__ dense_flag, int64_t n_rows,
-                     int64_t *__restrict__ dense_rows, int64_t *__restrict__ n_dense) {
-    __shared__ int warp_tot[32];
-    __shared__ int64_t base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) base = 0;
-    __syncthreads();
-    for (int64_t r0 = 0; r0 < n_rows; r0 += 1024) {
-        const int64_t r = r0 + tid;
-        const int f = (r < n_rows) ? dense_flag[r] : 0;
-        const unsigned m = __ballot_sync(0xffffffffu, f != 0);
-        if (lane == 0) warp_tot[warp] = __popc(m);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < 32; ++w) {
-            const int t = warp_tot[w];
-            if (w < warp) before += t;
-            total += t;
-        }
-        if (f) dense_rows[base + before + __popc(m & ((1u << lane) - 1u))] = r;
-        __syncthreads();
-        if (tid == 0) base += total;
-        __syncthreads();
-    }
-    if (tid == 0) *n_dense = base;
-}
-
-// dst[i] = lin[dense_rows[i]], w_dst[i] = weights[dense_rows[i]]
-__global__ void __launch_bounds__(256)
-em_gather_rows_kernel(const double *__restrict__ lin, int64_t ld, const double *__restrict__ weights,
-                      const int64_t *__restrict__ dense_rows, int64_t n_dense,
-                      double *__restrict__ dst, double *__restrict__ w_dst) {
-    for (int64_t i = blockIdx.x; i < n_dense; i += gridDim.x) {
-        const int64_t r = dense_rows[i];
-        const double2 *src = reinterpret_cast<const double2 *>(lin + r * ld);
-        double2 *d = reinterpret_cast<double2 *>(dst + i * ld);
-        for (int64_t j = threadIdx.x; j < ld / 2; j += 256) d[j] = src[j];
-        if (threadIdx.x == 0) w_dst[i] = weights[r];
-    }
-}
-
-// MXB_EM_CODED_COMPACT=1 (experimental): the coded pass skips the dense rows instead of
-// running over their empty records -- records and weights of the coded rows only, in row order.
-__global__ void em_flag_invert_kernel(int *__restrict__ flag, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x)
-        flag[i] = flag[i] ? 0 : 1;
-}
-__global__ void __launch_bounds__(256)
-em_gather_records_kernel(const unsigned char *__restrict__ rec, int64_t rec_bytes,
-                         const double *__restrict__ w_src, const int64_t *__restrict__ rows,
-                         int64_t n_out, unsigned char *__restrict__ dst, double *__restrict__ w_dst) {
-    for (int64_t i = blockIdx.x; i < n_out; i += gridDim.x) {
-        const int64_t r = rows[i];
-        const uint4 *src = reinterpret_cast<const uint4 *>(rec + r * rec_bytes);
-        uint4 *d = reinterpret_cast<uint4 *>(dst + i * rec_bytes);
-        for (int64_t j = threadIdx.x; j < rec_bytes / 16; j += 256) d[j] = src[j];
-        if (threadIdx.x == 0) w_dst[i] = w_src[r];
-    }
-}
-
 // ---- fused E+M pass (fast path) ----------------------------------------------
 // Rows are handled two at a time between block barriers.  The two partial dot
 // products of a thread are reduced together: the first shuffle step hands row 0
@@ -414,14 +184,12 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int off) {
     return __shfl_xor_sync(0xffffffffu, v, off);
 }
 
-// accumulate != 0 adds the column sums to what the launch before this one left in `partials`.
 template <int NC>
 __global__ void __launch_bounds__(kPassThreads, 1)
 em_pass_fast_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
                     int64_t n_rows, const double *__restrict__ weights,
                     const double *__restrict__ pi0, const double *__restrict__ pi1,
-                    EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
-                    int accumulate) {
+                    EmState *__restrict__ st, double *__restrict__ partials, int n_stages) {
     static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
     pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
 
@@ -561,602 +329,7 @@ em_pass_fast_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, 
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
         const int c = tid + k * kPassThreads;
-        if (c < n_chunks) {
-            if (accumulate) {
-                const double2 prev = out[c];
-                out[c] = make_double2(prev.x + tr[k].x, prev.y + tr[k].y);
-            } else {
-                out[c] = tr[k];
-            }
-        }
-    }
-    if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
-}
-
-// ---- fused E+M pass over dictionary-coded rows ----------------------------------------
-// em_pass_fast_kernel over the records of em_pack_kernel ([ld code bytes][256 doubles], a
-// cell is table[code]): same ring, same column slices (chunk c = tid + k*THREADS covers cells
-// 2c, 2c+1, one 16-bit load brings both codes), same reduction; only the two values of a
-// chunk come from the row's table in shared memory instead of the stage itself.  A record
-// is 5.8x smaller than the fp64 row, so this kernel is bound by instruction issue (lookup
-// index arithmetic, butterflies, the division) and not by HBM: 0.50 ms for the 138 569
-// records of config 2 against 0.87 ms for the fp64 rows (more threads per CTA, eight rows
-// per barrier with the values looked up twice, and run-length aware lookups over
-// consecutive cells were all measured slower).  The loop runs over full row pairs without
-// "is there a second row" tests or zero fills, the odd last row is peeled off, and both
-// records are waited for before the lookups of either start: 274 warp instructions per row
-// pair in SASS against 307 for the first version of the loop, which kept those tests inside
-// (0.568 ms per pass against 0.609 ms, profiles/r1k against r1j).  accumulate != 0 adds the
-// column sums to what the launch before this one (the fp64 pass over the dense rows) left
-// in `partials`.  THREADS = 384 is the experimental MXB_EM_CODED_T384 shape.
-template <int NC, int THREADS = kPassThreads>
-__global__ void __launch_bounds__(THREADS, 1)
-em_pass_coded_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
-                    int64_t n_rows, const double *__restrict__ weights,
-                    const double *__restrict__ pi0, const double *__restrict__ pi1,
-                    EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
-                    int accumulate) {
-    static_assert(kPassGroup == 2 && THREADS % 32 == 0 && THREADS <= kPassThreads,
-                  "reduction layout below: at most 16 warp totals per row");
-    pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
-
-    MXB_DYN_SHARED __align__(128) unsigned char smem_raw[];
-    double *scratch = reinterpret_cast<double *>(
-        smem_raw + (((size_t)n_stages * row_bytes + 127) & ~(size_t)127));
-    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
-    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
-    const int n_my = (int)(r_end - r_begin);
-    const unsigned char *my_rows = rows + (size_t)r_begin * row_bytes;
-    const double *my_w = weights + r_begin;
-    const uint32_t stages_u32 = smem_u32(smem_raw);
-    const uint32_t full_u32 = smem_u32(full);
-
-    // Prologue: L and the weights do not depend on the previous iteration's tail, so the
-    // ring is primed before waiting for it (the loads overlap the tail kernel).
-    if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
-        mbar_init_fence();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int q = 0; q < n_my && q < n_stages; ++q) {
-            mbar_expect_tx(&full[q], row_bytes);
-            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
-                      &full[q]);
-        }
-    }
-    // totals slots of the warps a smaller CTA does not have (read by the 16-lane butterfly)
-    if (THREADS < kPassThreads && tid < 2 * kPassWarps * kPassGroup && (tid & 15) >= THREADS / 32)
-        scratch[tid] = 0.0;
-    pdl_wait();  // proportions and control block of the previous iteration are final
-    if (st->done) {
-        // finished run: the primed loads must land before this CTA's shared memory is released
-        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
-        return;
-    }
-    const double *__restrict__ pi = st->cur ? pi1 : pi0;
-
-    // Thread-private column slice: chunk c = tid + k*512 covers doubles 2c, 2c+1.
-    const int n_chunks = (int)(ld >> 1);
-    double2 pr[NC], tr[NC];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * THREADS;
-        pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
-        tr[k] = make_double2(0.0, 0.0);
-    }
-    const bool last_live = tid + (NC - 1) * THREADS < n_chunks;  // only chunk NC-1 can be ragged
-
-    int stage = 0;          // ring slot of row q0
-    uint32_t phase = 0;     // its mbarrier parity
-    int sbuf = 0;
-    int bad = 0;
-    const bool upper = lane >= 16;
-
-    // One group of rows between two block barriers: rows q0 and q0 + 1 (kBoth), or the last
-    // row alone when the CTA's row count is odd -- the loop over full pairs carries no
-    // "is there a second row" tests and no zero fills.  Both records are waited for before the
-    // lookups of either start, so the 4 NC table lookups of a thread are independent work.
-    auto step = [&](auto both_tag, const int q0) {
-        constexpr bool kBoth = decltype(both_tag)::value;
-        constexpr int G = kBoth ? 2 : 1;
-        double2 lv[G][NC];
-        double dot[G];
-        int s_of[G];
-        const double w_mine = (kBoth || !upper) ? my_w[q0 + (upper ? 1 : 0)] : 0.0;
-        int s = stage;
-        uint32_t ph = phase;
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            s_of[g] = s;
-            mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
-            if (++s == n_stages) { s = 0; ph ^= 1u; }
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const unsigned char *srec = smem_raw + (size_t)s_of[g] * row_bytes;
-            const uint16_t *codes = reinterpret_cast<const uint16_t *>(srec) + tid;
-            const double *tab = reinterpret_cast<const double *>(srec + ld);
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                if (k < NC - 1 || last_live) {
-                    const unsigned cc = codes[k * THREADS];   // cells 2c, 2c + 1
-                    lv[g][k] = make_double2(tab[cc & 0xFFu], tab[cc >> 8]);
-                } else {
-                    lv[g][k] = make_double2(0.0, 0.0);
-                }
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            double dx = 0.0, dy = 0.0;
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                dx = fma(lv[g][k].x, pr[k].x, dx);
-                dy = fma(lv[g][k].y, pr[k].y, dy);
-            }
-            dot[g] = dx + dy;
-        }
-        // both rows in one butterfly: lanes 0-15 end up with row 0, lanes 16-31 with row 1
-        const double dot1 = kBoth ? dot[G - 1] : 0.0;
-        double v = (upper ? dot1 : dot[0]) + shfl_xor_f64(upper ? dot[0] : dot1, 16);
-        v += shfl_xor_f64(v, 8);
-        v += shfl_xor_f64(v, 4);
-        v += shfl_xor_f64(v, 2);
-        v += shfl_xor_f64(v, 1);
-        double *sc = scratch + sbuf * (kPassWarps * kPassGroup);
-        if ((lane & 15) == 0) sc[(lane >> 4) * kPassWarps + warp] = v;
-        __syncthreads();  // all reads of this group's stages are done; warp totals visible
-        if (tid == 0) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const int q = q0 + g + n_stages;
-                if (q < n_my) {
-                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_of[g];
-                    mbar_expect_tx_u32(bar, row_bytes);
-                    bulk_load_u32(stages_u32 + (uint32_t)s_of[g] * row_bytes,
-                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
-                }
-            }
-        }
-        // 16 warp totals per row sit in sc[0..15] / sc[16..31]: one value per lane
-        double t = sc[lane];
-        t += shfl_xor_f64(t, 8);
-        t += shfl_xor_f64(t, 4);
-        t += shfl_xor_f64(t, 2);
-        t += shfl_xor_f64(t, 1);
-        double coef_mine = 0.0;
-        if (w_mine != 0.0) {
-            coef_mine = w_mine / t;
-            bad |= (t == 0.0);
-        }
-        const double coef0 = __shfl_sync(0xffffffffu, coef_mine, 0);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            tr[k].x = fma(coef0, lv[0][k].x, tr[k].x);
-            tr[k].y = fma(coef0, lv[0][k].y, tr[k].y);
-        }
-        if (kBoth) {
-            const double coef1 = __shfl_sync(0xffffffffu, coef_mine, 16);
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                tr[k].x = fma(coef1, lv[G - 1][k].x, tr[k].x);
-                tr[k].y = fma(coef1, lv[G - 1][k].y, tr[k].y);
-            }
-        }
-        stage = s;
-        phase = ph;
-        sbuf ^= 1;
-    };
-    int q0 = 0;
-    for (; q0 + 1 < n_my; q0 += kPassGroup) step(std::true_type{}, q0);
-    if (q0 < n_my) step(std::false_type{}, q0);
-
-    double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * THREADS;
-        if (c < n_chunks) {
-            if (accumulate) {
-                const double2 prev = out[c];
-                out[c] = make_double2(prev.x + tr[k].x, prev.y + tr[k].y);
-            } else {
-                out[c] = tr[k];
-            }
-        }
-    }
-    if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
-}
-
-// em_pass_coded_kernel over chunk-coded records (em_pack_pairs_kernel): one 8-byte load
-// brings a thread's codes of a row, one 16-byte lookup the two values of a chunk.
-// Experimental, MXB_EM_CODED_PAIRS=1.
-template <int NC, int THREADS = kPassThreads>
-__global__ void __launch_bounds__(THREADS, 1)
-em_pass_coded_pairs_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
-                    int64_t n_rows, const double *__restrict__ weights,
-                    const double *__restrict__ pi0, const double *__restrict__ pi1,
-                    EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
-                    int accumulate) {
-    static_assert(kPassGroup == 2 && THREADS % 32 == 0 && THREADS <= kPassThreads && NC <= 8,
-                  "at most 16 warp totals per row; a thread's codes of a row fit one 8-byte word");
-    pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
-
-    MXB_DYN_SHARED __align__(128) unsigned char smem_raw[];
-    double *scratch = reinterpret_cast<double *>(
-        smem_raw + (((size_t)n_stages * row_bytes + 127) & ~(size_t)127));
-    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
-    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
-    const int n_my = (int)(r_end - r_begin);
-    const unsigned char *my_rows = rows + (size_t)r_begin * row_bytes;
-    const double *my_w = weights + r_begin;
-    const uint32_t stages_u32 = smem_u32(smem_raw);
-    const uint32_t full_u32 = smem_u32(full);
-
-    // Prologue: L and the weights do not depend on the previous iteration's tail, so the
-    // ring is primed before waiting for it (the loads overlap the tail kernel).
-    if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
-        mbar_init_fence();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int q = 0; q < n_my && q < n_stages; ++q) {
-            mbar_expect_tx(&full[q], row_bytes);
-            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
-                      &full[q]);
-        }
-    }
-    // totals slots of the warps a smaller CTA does not have (read by the 16-lane butterfly)
-    if (THREADS < kPassThreads && tid < 2 * kPassWarps * kPassGroup && (tid & 15) >= THREADS / 32)
-        scratch[tid] = 0.0;
-    pdl_wait();  // proportions and control block of the previous iteration are final
-    if (st->done) {
-        // finished run: the primed loads must land before this CTA's shared memory is released
-        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
-        return;
-    }
-    const double *__restrict__ pi = st->cur ? pi1 : pi0;
-
-    // Thread-private column slice: chunk c = tid + k*512 covers doubles 2c, 2c+1.
-    const int n_chunks = (int)(ld >> 1);
-    double2 pr[NC], tr[NC];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * THREADS;
-        pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
-        tr[k] = make_double2(0.0, 0.0);
-    }
-
-    int stage = 0;          // ring slot of row q0
-    uint32_t phase = 0;     // its mbarrier parity
-    int sbuf = 0;
-    int bad = 0;
-    const bool upper = lane >= 16;
-
-    // One group of rows between two block barriers: rows q0 and q0 + 1 (kBoth), or the last
-    // row alone when the CTA's row count is odd -- the loop over full pairs carries no
-    // "is there a second row" tests and no zero fills.  Both records are waited for before the
-    // lookups of either start, so the 4 NC table lookups of a thread are independent work.
-    auto step = [&](auto both_tag, const int q0) {
-        constexpr bool kBoth = decltype(both_tag)::value;
-        constexpr int G = kBoth ? 2 : 1;
-        double2 lv[G][NC];
-        double dot[G];
-        int s_of[G];
-        const double w_mine = (kBoth || !upper) ? my_w[q0 + (upper ? 1 : 0)] : 0.0;
-        int s = stage;
-        uint32_t ph = phase;
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            s_of[g] = s;
-            mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
-            if (++s == n_stages) { s = 0; ph ^= 1u; }
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            // 32-bit shared-window addresses: record base (warp-uniform) + per-thread offset
-            const uint32_t rec_u32 = stages_u32 + (uint32_t)s_of[g] * row_bytes;
-            uint2 cw;   // this thread's codes of the row
-            cw = lds_v2_u32(rec_u32 + (uint32_t)tid * 8u);
-            const uint32_t tab_u32 = rec_u32 + (uint32_t)(THREADS * 8);
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                // a chunk past the end of the row has code 0 and proportion 0: whatever the
-                // table holds there adds nothing to the dot product, and its column sum is
-                // never written
-                const unsigned word = (k < 4) ? cw.x : cw.y;
-                const unsigned off = ((word >> (8 * (k & 3))) & 0xFFu) << 4;
-                lv[g][k] = lds_v2_f64(tab_u32 + off);
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            double dx = 0.0, dy = 0.0;
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                dx = fma(lv[g][k].x, pr[k].x, dx);
-                dy = fma(lv[g][k].y, pr[k].y, dy);
-            }
-            dot[g] = dx + dy;
-        }
-        // both rows in one butterfly: lanes 0-15 end up with row 0, lanes 16-31 with row 1
-        const double dot1 = kBoth ? dot[G - 1] : 0.0;
-        double v = (upper ? dot1 : dot[0]) + shfl_xor_f64(upper ? dot[0] : dot1, 16);
-        v += shfl_xor_f64(v, 8);
-        v += shfl_xor_f64(v, 4);
-        v += shfl_xor_f64(v, 2);
-        v += shfl_xor_f64(v, 1);
-        double *sc = scratch + sbuf * (kPassWarps * kPassGroup);
-        if ((lane & 15) == 0) sc[(lane >> 4) * kPassWarps + warp] = v;
-        __syncthreads();  // all reads of this group's stages are done; warp totals visible
-        if (tid == 0) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const int q = q0 + g + n_stages;
-                if (q < n_my) {
-                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_of[g];
-                    mbar_expect_tx_u32(bar, row_bytes);
-                    bulk_load_u32(stages_u32 + (uint32_t)s_of[g] * row_bytes,
-                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
-                }
-            }
-        }
-        // 16 warp totals per row sit in sc[0..15] / sc[16..31]: one value per lane
-        double t = sc[lane];
-        t += shfl_xor_f64(t, 8);
-        t += shfl_xor_f64(t, 4);
-        t += shfl_xor_f64(t, 2);
-        t += shfl_xor_f64(t, 1);
-        double coef_mine = 0.0;
-        if (w_mine != 0.0) {
-            coef_mine = w_mine / t;
-            bad |= (t == 0.0);
-        }
-        const double coef0 = __shfl_sync(0xffffffffu, coef_mine, 0);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            tr[k].x = fma(coef0, lv[0][k].x, tr[k].x);
-            tr[k].y = fma(coef0, lv[0][k].y, tr[k].y);
-        }
-        if (kBoth) {
-            const double coef1 = __shfl_sync(0xffffffffu, coef_mine, 16);
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                tr[k].x = fma(coef1, lv[G - 1][k].x, tr[k].x);
-                tr[k].y = fma(coef1, lv[G - 1][k].y, tr[k].y);
-            }
-        }
-        stage = s;
-        phase = ph;
-        sbuf ^= 1;
-    };
-    int q0 = 0;
-    for (; q0 + 1 < n_my; q0 += kPassGroup) step(std::true_type{}, q0);
-    if (q0 < n_my) step(std::false_type{}, q0);
-
-    double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * THREADS;
-        if (c < n_chunks) {
-            if (accumulate) {
-                const double2 prev = out[c];
-                out[c] = make_double2(prev.x + tr[k].x, prev.y + tr[k].y);
-            } else {
-                out[c] = tr[k];
-            }
-        }
-    }
-    if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
-}
-
-// Third version (experimental, MXB_EM_CODED_V3=1, not yet run on a GPU): the same sums in
-// the same order, one row at a time, software-pipelined and without a block barrier.
-//
-// The two-row loop above runs its 16 warps through the same phases in lock step: all of them
-// look values up (the LSU is saturated, ~960 of the ~2100 cycles a row pair takes), then all of
-// them sit in the butterfly / division chains (nothing to issue), then all of them add.  Here a
-// warp publishes its partial dot product of row r + 1 with an mbarrier *arrive* (non-blocking)
-// and only *waits* for the totals of row r, which every warp published one iteration earlier:
-// warps may drift a row apart, so the lookups of one overlap the reductions of another.
-//   iteration r of a warp:  lookups(r + 1) -> wait sum[r] -> [thread 0: refill the slot of row r]
-//                           -> totals(r), coefficient -> dot(r + 1), butterfly, publish(r + 1)
-//                           -> column sums += coefficient * values(r)
-// sum[b], b = r mod 4: mbarrier with one arrival per warp; totals buffer sc[b][16].  A warp
-// overwrites sc[(r + 1) mod 4] only after it saw sum[r] complete, i.e. after every warp has
-// published row r, which each does after reading the totals of row r - 1 >= r - 3.  "Every warp
-// has published row r" also means every warp has the values of row r in registers (the
-// published number depends on all of them), so its ring slot can be refilled.
-constexpr int kSumBufs = 4;
-
-template <int NC, int THREADS = kPassThreads, bool kPairs = false>
-__global__ void __launch_bounds__(THREADS, 1)
-em_pass_coded_v3_kernel(const unsigned char *__restrict__ rows, uint32_t row_bytes, int64_t ld,
-                        int64_t n_rows, const double *__restrict__ weights,
-                        const double *__restrict__ pi0, const double *__restrict__ pi1,
-                        EmState *__restrict__ st, double *__restrict__ partials, int n_stages,
-                        int accumulate) {
-    static_assert(kPassWarps == 16 && kSumBufs * kPassWarps <= 2 * kPassWarps * kPassGroup &&
-                      THREADS % 32 == 0 && THREADS <= kPassThreads && (!kPairs || NC <= 8),
-                  "totals buffers live in the scratch area of the two-row kernels");
-    constexpr int kWarps = THREADS / 32;
-    pdl_launch_dependents();  // the tail kernel may be scheduled as SMs drain
-
-    MXB_DYN_SHARED __align__(128) unsigned char smem_raw[];
-    double *scratch = reinterpret_cast<double *>(
-        smem_raw + (((size_t)n_stages * row_bytes + 127) & ~(size_t)127));
-    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
-    uint64_t *sum = full + 16;   // em_pack_rows: at most 16 stages, 256 spare bytes behind them
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
-    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
-    const int n_my = (int)(r_end - r_begin);
-    const unsigned char *my_rows = rows + (size_t)r_begin * row_bytes;
-    const double *my_w = weights + r_begin;
-    const uint32_t stages_u32 = smem_u32(smem_raw);
-    const uint32_t full_u32 = smem_u32(full);
-    const uint32_t sum_u32 = smem_u32(sum);
-
-    if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
-        for (int b = 0; b < kSumBufs; ++b) mbar_init(&sum[b], kWarps);
-        mbar_init_fence();
-    }
-    // totals slots of the warps a smaller CTA does not have (read by the 16-lane butterfly)
-    if (THREADS < kPassThreads && tid < kSumBufs * kPassWarps && (tid & 15) >= kWarps)
-        scratch[tid] = 0.0;
-    __syncthreads();
-    if (tid == 0) {
-        for (int q = 0; q < n_my && q < n_stages; ++q) {
-            mbar_expect_tx(&full[q], row_bytes);
-            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
-                      &full[q]);
-        }
-    }
-    pdl_wait();  // proportions and control block of the previous iteration are final
-    if (st->done) {
-        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
-        return;
-    }
-    const double *__restrict__ pi = st->cur ? pi1 : pi0;
-
-    const int n_chunks = (int)(ld >> 1);
-    double2 pr[NC], tr[NC];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * THREADS;
-        pr[k] = (c < n_chunks) ? reinterpret_cast<const double2 *>(pi)[c] : make_double2(0.0, 0.0);
-        tr[k] = make_double2(0.0, 0.0);
-    }
-    const bool last_live = tid + (NC - 1) * THREADS < n_chunks;  // only chunk NC-1 can be ragged
-
-    int bad = 0;
-    // the values of a row: table lookups of this thread's 2 NC cells in ring slot s
-    auto lookups = [&](double2 (&lv)[NC], const int s) {
-        if (kPairs) {   // chunk-coded record: 8 code bytes per thread, table of double2
-            const uint32_t rec_u32 = stages_u32 + (uint32_t)s * row_bytes;
-            const uint2 cw = lds_v2_u32(rec_u32 + (uint32_t)tid * 8u);
-            const uint32_t tab_u32 = rec_u32 + (uint32_t)(THREADS * 8);
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                const unsigned word = (k < 4) ? cw.x : cw.y;
-                const unsigned off = ((word >> (8 * (k & 3))) & 0xFFu) << 4;
-                lv[k] = lds_v2_f64(tab_u32 + off);
-            }
-            return;
-        }
-        const unsigned char *srec = smem_raw + (size_t)s * row_bytes;
-        const uint16_t *codes = reinterpret_cast<const uint16_t *>(srec) + tid;
-        const double *tab = reinterpret_cast<const double *>(srec + ld);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            if (k < NC - 1 || last_live) {
-                const unsigned cc = codes[k * THREADS];   // cells 2c, 2c + 1
-                lv[k] = make_double2(tab[cc & 0xFFu], tab[cc >> 8]);
-            } else {
-                lv[k] = make_double2(0.0, 0.0);
-            }
-        }
-    };
-    // this warp's part of row r's dot product -> sc[r mod 4][warp], one arrival on sum[r mod 4]
-    auto publish = [&](const double2 (&lv)[NC], const int r) {
-        double dx = 0.0, dy = 0.0;
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            dx = fma(lv[k].x, pr[k].x, dx);
-            dy = fma(lv[k].y, pr[k].y, dy);
-        }
-        double v = dx + dy;
-        v += shfl_xor_f64(v, 16);
-        v += shfl_xor_f64(v, 8);
-        v += shfl_xor_f64(v, 4);
-        v += shfl_xor_f64(v, 2);
-        v += shfl_xor_f64(v, 1);
-        if (lane == 0) {
-            const int b = r & (kSumBufs - 1);
-            scratch[b * kPassWarps + warp] = v;
-            mbar_arrive_u32(sum_u32 + 8u * (uint32_t)b);   // release: the store above is visible
-        }
-    };
-
-    if (n_my > 0) {
-        double2 lv0[NC], lv1[NC];
-        int s_next = 0;            // ring slot and parity of the row whose values are fetched next
-        uint32_t ph_next = 0;
-        mbar_wait_u32(full_u32, 0u);
-        lookups(lv0, 0);
-        if (++s_next == n_stages) { s_next = 0; ph_next ^= 1u; }
-        publish(lv0, 0);
-        // one row: `cur` holds the values of row r, `nxt` receives those of row r + 1
-        auto row_step = [&](double2 (&cur)[NC], double2 (&nxt)[NC], const int r) {
-            const double w_r = my_w[r];
-            const bool more = r + 1 < n_my;
-            const int s_cur = (s_next == 0 ? n_stages : s_next) - 1;   // slot of row r
-            if (more) {
-                mbar_wait_u32(full_u32 + 8u * (uint32_t)s_next, ph_next);
-                lookups(nxt, s_next);
-                if (++s_next == n_stages) { s_next = 0; ph_next ^= 1u; }
-            }
-            const int b = r & (kSumBufs - 1);
-            mbar_wait_u32(sum_u32 + 8u * (uint32_t)b, (uint32_t)(r >> 2) & 1u);
-            if (tid == 0) {
-                const int q = r + n_stages;
-                if (q < n_my) {
-                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_cur;
-                    mbar_expect_tx_u32(bar, row_bytes);
-                    bulk_load_u32(stages_u32 + (uint32_t)s_cur * row_bytes,
-                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
-                }
-            }
-            // 16 warp totals of row r: one per lane of each half-warp
-            double t = scratch[b * kPassWarps + (lane & 15)];
-            t += shfl_xor_f64(t, 8);
-            t += shfl_xor_f64(t, 4);
-            t += shfl_xor_f64(t, 2);
-            t += shfl_xor_f64(t, 1);
-            double coef = 0.0;
-            if (w_r != 0.0) {
-                coef = w_r / t;
-                bad |= (t == 0.0);
-            }
-            if (more) publish(nxt, r + 1);
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                tr[k].x = fma(coef, cur[k].x, tr[k].x);
-                tr[k].y = fma(coef, cur[k].y, tr[k].y);
-            }
-        };
-        int r = 0;
-        for (; r + 1 < n_my; r += 2) {
-            row_step(lv0, lv1, r);
-            row_step(lv1, lv0, r + 1);
-        }
-        if (r < n_my) row_step(lv0, lv1, r);
-    }
-
-    double2 *out = reinterpret_cast<double2 *>(partials + (size_t)blockIdx.x * ld);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * THREADS;
-        if (c < n_chunks) {
-            if (accumulate) {
-                const double2 prev = out[c];
-                out[c] = make_double2(prev.x + tr[k].x, prev.y + tr[k].y);
-            } else {
-                out[c] = tr[k];
-            }
-        }
+        if (c < n_chunks) out[c] = tr[k];
     }
     if (__any_sync(0xffffffffu, bad) && lane == 0 && warp == 0) atomicAdd(&st->bad, 1);
 }
@@ -1169,7 +342,7 @@ em_pass_coded_v3_kernel(const unsigned char *__restrict__ rows, uint32_t row_byt
 // from shared memory twice -- once for the two dot products, once for the two
 // column-sum updates -- and a second block barrier per row pair releases the stages.
 // The four (row, restart) dot products of a row pair ride one butterfly.
-template <int NC, bool kAccumulate = false>
+template <int NC>
 __global__ void __launch_bounds__(kPassThreads, 1)
 em_pass_pair_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
                     const double *__restrict__ weights, const double *__restrict__ pi_a0,
@@ -1332,192 +505,9 @@ em_pass_pair_kernel(const double *__restrict__ lin, int64_t ld, int64_t n_rows,
     for (int k = 0; k < NC; ++k) {
         const int c = tid + k * kPassThreads;
         if (c < n_chunks) {
-            if (kAccumulate) {   // on top of what the launch before this one left (coded sessions)
-                const double2 qa = out_a[c], qb = out_b[c];
-                out_a[c] = make_double2(qa.x + ta[k].x, qa.y + ta[k].y);
-                out_b[c] = make_double2(qb.x + tb[k].x, qb.y + tb[k].y);
-            } else {
-                out_a[c] = ta[k];
-                out_b[c] = tb[k];
-            }
+            out_a[c] = ta[k];
+            out_b[c] = tb[k];
         }
-    }
-    if (bad) atomicOr(&st[(q4 & 1)].bad, 1);
-}
-
-// Two restarts per read of the chunk-coded records (em_pack_pairs_kernel, 512-thread layout):
-// em_pass_pair_kernel with the two values of a chunk looked up in the row's table, in both
-// sweeps over a staged row.  Writes the column sums; the fp64 pair pass over the dense rows
-// (em_pass_pair_kernel<NC, true>) adds its own afterwards.  Experimental, MXB_EM_CODED_PAIRS=1.
-template <int NC>
-__global__ void __launch_bounds__(kPassThreads, 1)
-em_pass_pair_coded_kernel(const unsigned char *__restrict__ rec, int64_t ld, int64_t n_rows,
-                    const double *__restrict__ weights, const double *__restrict__ pi_a0,
-                    const double *__restrict__ pi_a1, const double *__restrict__ pi_b0,
-                    const double *__restrict__ pi_b1, EmState *__restrict__ st,
-                    double *__restrict__ partials_a, double *__restrict__ partials_b,
-                    int n_stages) {
-    static_assert(kPassGroup == 2 && kPassWarps == 16, "reduction layout below");
-    pdl_launch_dependents();
-
-    MXB_DYN_SHARED __align__(128) unsigned char smem_raw[];
-    constexpr uint32_t row_bytes = (uint32_t)pair_rec_bytes(kPassThreads);
-    double *scratch = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * row_bytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 2 * kPassWarps * kPassGroup);
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int64_t r_begin = n_rows * (int64_t)blockIdx.x / gridDim.x;
-    const int64_t r_end = n_rows * (int64_t)(blockIdx.x + 1) / gridDim.x;
-    const int n_my = (int)(r_end - r_begin);
-    const unsigned char *my_rows = rec + (size_t)r_begin * row_bytes;
-    const double *my_w = weights + r_begin;
-    const uint32_t stages_u32 = smem_u32(smem_raw);
-    const uint32_t full_u32 = smem_u32(full);
-
-    if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
-        mbar_init_fence();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int q = 0; q < n_my && q < n_stages; ++q) {
-            mbar_expect_tx(&full[q], row_bytes);
-            bulk_load(smem_raw + (size_t)q * row_bytes, my_rows + (size_t)q * row_bytes, row_bytes,
-                      &full[q]);
-        }
-    }
-
-    pdl_wait();
-    const int done_a = st[0].done, done_b = st[1].done;
-    if (done_a && done_b) {
-        for (int q = 0; q < n_my && q < n_stages; ++q) mbar_wait_u32(full_u32 + 8u * (uint32_t)q, 0u);
-        return;
-    }
-    const double *__restrict__ pia = st[0].cur ? pi_a1 : pi_a0;
-    const double *__restrict__ pib = st[1].cur ? pi_b1 : pi_b0;
-
-    const int n_chunks = (int)(ld >> 1);
-    double2 pa[NC], pb[NC], ta[NC], tb[NC];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * kPassThreads;
-        const bool in = c < n_chunks;
-        pa[k] = in ? reinterpret_cast<const double2 *>(pia)[c] : make_double2(0.0, 0.0);
-        pb[k] = in ? reinterpret_cast<const double2 *>(pib)[c] : make_double2(0.0, 0.0);
-        ta[k] = make_double2(0.0, 0.0);
-        tb[k] = make_double2(0.0, 0.0);
-    }
-
-    int stage = 0;
-    uint32_t phase = 0;
-    int bad = 0;
-    // quarter q4 = lane >> 3 owns pair (row g = q4 >> 1, restart = q4 & 1) after the butterfly
-    const int q4 = lane >> 3;
-    const bool mine_done = (q4 & 1) ? done_b != 0 : done_a != 0;
-    for (int q0 = 0; q0 < n_my; q0 += kPassGroup) {
-        const int q_mine = q0 + (q4 >> 1);
-        const double w_mine = (q_mine < n_my) ? my_w[q_mine] : 0.0;
-        int s_of[kPassGroup];
-        double d[4];  // [row][restart]
-        int s = stage;
-        uint32_t ph = phase;
-#pragma unroll
-        for (int g = 0; g < kPassGroup; ++g) {
-            s_of[g] = s;
-            double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
-            if (q0 + g < n_my) {
-                mbar_wait_u32(full_u32 + 8u * (uint32_t)s, ph);
-                const uint32_t rec_u32 = stages_u32 + (uint32_t)s * row_bytes;
-                uint2 cw;   // this thread's chunk codes of the row
-                cw = lds_v2_u32(rec_u32 + (uint32_t)tid * 8u);
-                const uint32_t tab_u32 = rec_u32 + (uint32_t)(kPassThreads * 8);
-#pragma unroll
-                for (int k = 0; k < NC; ++k) {
-                    // a chunk past the end of the row has code 0 and proportions 0
-                    const unsigned word = (k < 4) ? cw.x : cw.y;
-                    const unsigned off = ((word >> (8 * (k & 3))) & 0xFFu) << 4;
-                    double2 l;
-                    l = lds_v2_f64(tab_u32 + off);
-                    ax = fma(l.x, pa[k].x, ax);
-                    ay = fma(l.y, pa[k].y, ay);
-                    bx = fma(l.x, pb[k].x, bx);
-                    by = fma(l.y, pb[k].y, by);
-                }
-            }
-            d[2 * g] = ax + ay;
-            d[2 * g + 1] = bx + by;
-            if (++s == n_stages) { s = 0; ph ^= 1u; }
-        }
-        // four sums in one butterfly: halves keep a row, quarters keep a restart
-        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
-        double e0 = (up16 ? d[2] : d[0]) + shfl_xor_f64(up16 ? d[0] : d[2], 16);
-        double e1 = (up16 ? d[3] : d[1]) + shfl_xor_f64(up16 ? d[1] : d[3], 16);
-        double v = (up8 ? e1 : e0) + shfl_xor_f64(up8 ? e0 : e1, 8);
-        v += shfl_xor_f64(v, 4);
-        v += shfl_xor_f64(v, 2);
-        v += shfl_xor_f64(v, 1);
-        // scratch[pair q4][warp]; the loop's second barrier separates consecutive groups
-        if ((lane & 7) == 0) scratch[q4 * kPassWarps + warp] = v;
-        __syncthreads();
-        // 16 warp totals per pair: lane reads two of them, 3-step butterfly inside its quarter
-        double t = scratch[q4 * kPassWarps + (lane & 7)] + scratch[q4 * kPassWarps + 8 + (lane & 7)];
-        t += shfl_xor_f64(t, 4);
-        t += shfl_xor_f64(t, 2);
-        t += shfl_xor_f64(t, 1);
-        double coef_mine = 0.0;
-        if (w_mine != 0.0) {
-            coef_mine = w_mine / t;
-            bad |= (t == 0.0 && !mine_done);
-        }
-        const double c0a = __shfl_sync(0xffffffffu, coef_mine, 0);
-        const double c0b = __shfl_sync(0xffffffffu, coef_mine, 8);
-        const double c1a = __shfl_sync(0xffffffffu, coef_mine, 16);
-        const double c1b = __shfl_sync(0xffffffffu, coef_mine, 24);
-#pragma unroll
-        for (int g = 0; g < kPassGroup; ++g) {
-            if (q0 + g < n_my) {
-                const double ca = g ? c1a : c0a, cb = g ? c1b : c0b;
-                const uint32_t rec_u32 = stages_u32 + (uint32_t)s_of[g] * row_bytes;
-                uint2 cw;
-                cw = lds_v2_u32(rec_u32 + (uint32_t)tid * 8u);
-                const uint32_t tab_u32 = rec_u32 + (uint32_t)(kPassThreads * 8);
-#pragma unroll
-                for (int k = 0; k < NC; ++k) {
-                    const unsigned word = (k < 4) ? cw.x : cw.y;
-                    const unsigned off = ((word >> (8 * (k & 3))) & 0xFFu) << 4;
-                    double2 l;
-                    l = lds_v2_f64(tab_u32 + off);
-                    ta[k].x = fma(ca, l.x, ta[k].x);
-                    ta[k].y = fma(ca, l.y, ta[k].y);
-                    tb[k].x = fma(cb, l.x, tb[k].x);
-                    tb[k].y = fma(cb, l.y, tb[k].y);
-                }
-            }
-        }
-        __syncthreads();  // both staged rows have been read twice: release them
-        if (tid == 0) {
-#pragma unroll
-            for (int g = 0; g < kPassGroup; ++g) {
-                const int q = q0 + g + n_stages;
-                if (q < n_my) {
-                    const uint32_t bar = full_u32 + 8u * (uint32_t)s_of[g];
-                    mbar_expect_tx_u32(bar, row_bytes);
-                    bulk_load_u32(stages_u32 + (uint32_t)s_of[g] * row_bytes,
-                                  my_rows + (size_t)q * row_bytes, row_bytes, bar);
-                }
-            }
-        }
-        stage = s;
-        phase = ph;
-    }
-
-    double2 *out_a = reinterpret_cast<double2 *>(partials_a + (size_t)blockIdx.x * ld);
-    double2 *out_b = reinterpret_cast<double2 *>(partials_b + (size_t)blockIdx.x * ld);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        const int c = tid + k * kPassThreads;
-        if (c < n_chunks) { out_a[c] = ta[k]; out_b[c] = tb[k]; }
     }
     if (bad) atomicOr(&st[(q4 & 1)].bad, 1);
 }
@@ -1645,7 +635,6 @@ em_update_kernel(const double *__restrict__ tsum, int64_t n_cols, int64_t ld,
     }
 }
 
-#ifndef MXB_CPU_EMUL   // thread-block clusters and peer mailboxes: not modelled on the host
 // ---- fused tail of an iteration (fast path) ------------------------------------
 // One launch replaces em_colreduce_kernel + em_update_kernel: a single cluster of
 // kFinCtas CTAs, one thread per column.  Each thread adds the per-CTA partial
@@ -1847,7 +836,6 @@ em_finish_kernel(const double *partials, int n_part, int64_t n_cols, int64_t ld,
 }
 
 // ln pi -> (ln pi, pi) device buffers, padding zeroed.
-#endif  // MXB_CPU_EMUL
 
 __global__ void em_set_props_kernel(const double *__restrict__ src, int64_t n_cols, int64_t ld,
                                     double *__restrict__ lnp, double *__restrict__ pi,
@@ -1917,20 +905,26 @@ read_mix_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols,
 }
 
 // Cross-rank fold helpers: m <- exp(m - mx) ; m <- mx + log(m) - sub_log.
-__global__ void fold_exp_kernel(double *__restrict__ m, const double *__restrict__ mx, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+// Restart fan-out (mxb_matrix_fold_ranks): `own` is this rank's shard of its own fold of read
+// matrices, recv[q] the same rows as folded by rank q.  numpy.logaddexp in rank order
+// (em.py:156), then - log(n_multi) (em.py:161).
+__global__ void fold_shards_kernel(double *__restrict__ own, const double *__restrict__ recv,
+                                   int64_t slot, int64_t cells, int world, int me, double sub_log) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const double a = mx[i];
-        m[i] = isinf(a) ? (a < 0 ? 0.0 : 1.0) : exp(m[i] - a);
+        double acc = 0.0;
+        for (int q = 0; q < world; ++q) {
+            const double v = q == me ? own[i] : recv[(int64_t)q * slot + i];
+            acc = q == 0 ? v : np_logaddexp(acc, v);
+        }
+        own[i] = acc - sub_log;
     }
 }
-__global__ void fold_log_kernel(double *__restrict__ m, const double *__restrict__ mx, int64_t n,
-                                double sub_log) {
+
+__global__ void fold_shift_kernel(double *__restrict__ m, int64_t n, double sub_log) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const double a = mx[i];
-        m[i] = (isinf(a) ? a : a + log(m[i])) - sub_log;
-    }
+         i += (int64_t)gridDim.x * blockDim.x)
+        m[i] -= sub_log;
 }
 
 }  // namespace mxb

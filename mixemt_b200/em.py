@@ -86,9 +86,6 @@ def run_em_device(dev_mat, weights, args, keep_device=False, want_host=True, ini
     wts = _lib.as_f64(numpy.asarray(weights).reshape(-1))
     if wts.shape[0] != n:
         raise ValueError("weights has %d entries for %d rows" % (wts.shape[0], n))
-    if inits is None:
-        inits = _draw_inits(n_multi, h, args.init_alpha)
-    inits = _lib.as_f64(inits)
     shard = getattr(args, "b200_shard", None)
     verbose = getattr(args, "verbose", False)
     flags = 0
@@ -101,11 +98,22 @@ def run_em_device(dev_mat, weights, args, keep_device=False, want_host=True, ini
         if ctx.world > 1:
             flags |= _lib.MXB_EM_RAW
             mine = sharding.restart_shard(n_multi, ctx.rank, ctx.world)
+    if inits is None:
+        if shard in ("rows", "restarts") and ctx.world > 1:
+            # every rank must start every restart from the same proportions (the fused tail
+            # takes one convergence decision for all ranks): rank 0 draws from its global
+            # numpy.random stream, as the reference would, and the draws are shared
+            inits = sharding.share_from_rank0(
+                lambda: _draw_inits(n_multi, h, args.init_alpha), (n_multi, h), ctx.rank,
+                ctx.allreduce_host)
+        else:
+            inits = _draw_inits(n_multi, h, args.init_alpha)
+    inits = _lib.as_f64(inits)
 
     props = numpy.zeros(h)
     iters = numpy.zeros(max(1, len(mine)), dtype=numpy.int64)
     conv = numpy.zeros(max(1, len(mine)), dtype=numpy.int32)
-    read_mix = numpy.empty((n, h)) if (want_host and not (flags & _lib.MXB_EM_RAW)) else None
+    read_mix = _lib.result_empty((n, h)) if (want_host and not (flags & _lib.MXB_EM_RAW)) else None
     mix_handle = ctypes.c_void_p()
     need_dev = keep_device or bool(flags & _lib.MXB_EM_RAW)
     if mine:

@@ -220,7 +220,7 @@ def build_matrix_from_csr(tables, csr, ctx=None, want_host=True, want_counts=Fal
     ctx = ctx or get_context()
     dev = tables.to_device(ctx)
     n, h = csr.n_rows, tables.n_hap
-    out = np.empty((n, h), dtype=np.float64) if want_host else None
+    out = _lib.result_empty((n, h)) if want_host else None
     counts = np.empty((n, h), dtype=np.int32) if want_counts else None
     handle = ctypes.c_void_p()
     ms = ctypes.c_float(0.0)

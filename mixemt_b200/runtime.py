@@ -129,7 +129,7 @@ class DeviceMatrix(object):
 
     def to_host(self, out=None):
         if out is None:
-            out = np.empty(self.shape, dtype=np.float64)
+            out = _lib.result_empty(self.shape)
         assert out.shape == self.shape and out.dtype == np.float64
         check(lib.mxb_matrix_download(self.ctx.handle, self.handle, ptr(out)))
         return out

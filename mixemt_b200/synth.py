@@ -22,8 +22,9 @@ class Mixture(object):
     """Unique signatures of a synthetic mixture.
 
     ``pos_idx`` indexes ``sorted(phylo.variants)``; ``base_ascii`` holds the
-    observed base letters; rows follow ``signatures`` (string-sorted) when
-    those were requested, generation order otherwise."""
+    observed base letters; rows follow ``signatures`` (string-sorted, the order
+    ``build_em_input`` hands them over in, preprocess.py:219) when those were
+    requested, and the same grouping by first position otherwise."""
 
     def __init__(self, row_ptr, pos_idx, base_ascii, weights, signatures, n_fragments):
         self.row_ptr = row_ptr
@@ -106,7 +107,12 @@ def make_mixture(phylo, refseq, mixture, n_fragments, frag_len=300, err=0.002, s
         keys = [keys[i] for i in order]
         signatures = [sigs[i] for i in order]
     else:
+        # no strings wanted: still the reference's grouping (rows that start at the same
+        # variant position are neighbours, positions ordered as decimal strings)
         signatures = None
+        rank = {p: r for r, p in enumerate(sorted(range(len(positions)),
+                                                  key=lambda i: "%d:" % positions[i]))}
+        keys.sort(key=lambda k: (rank[k[0]], k[1]))
 
     lens = np.fromiter((len(k[1]) for k in keys), dtype=np.int64, count=len(keys))
     row_ptr = np.zeros(len(keys) + 1, dtype=np.int64)
@@ -154,12 +160,14 @@ def synthetic_phylo(n_hap=512, n_pos=400, ref_len=4000, markers_per_hap=12, seed
     return PhyloTables(variants, hap_var, refseq), refseq
 
 
-def random_rows(phylo, refseq, mixture, n_rows, frag_len=300, err=0.002, seed=1):
+def random_rows(phylo, refseq, mixture, n_rows, frag_len=300, err=0.002, seed=1,
+                reference_order=True):
     """``n_rows`` fragment signatures drawn like :func:`make_mixture` draws
     fragments, fully vectorised and *without* the reduction to unique signatures
     (duplicates stay, every weight is 1).  For shard-sized workloads (millions of
     rows per GPU, BASELINE.json config 3) where the Python dedupe loop of
-    ``make_mixture`` would take minutes.  Rows are in generation order."""
+    ``make_mixture`` would take minutes.  Rows are grouped like the reference's string-sorted
+    signatures (``reference_order``) or left in generation order."""
     rs = np.random.RandomState(seed)
     positions = sorted(phylo.variants)
     pos_arr = np.asarray(positions, dtype=np.int64)
@@ -193,6 +201,21 @@ def random_rows(phylo, refseq, mixture, n_rows, frag_len=300, err=0.002, seed=1)
     lens = np.concatenate([c[0] for c in chunks])
     row_ptr = np.zeros(len(lens) + 1, dtype=np.int64)
     np.cumsum(lens, out=row_ptr[1:])
-    return Mixture(row_ptr, np.concatenate([c[1] for c in chunks]),
-                   np.concatenate([c[2] for c in chunks]),
-                   np.ones(len(lens), dtype=np.int64), None, len(lens))
+    pos_idx = np.concatenate([c[1] for c in chunks])
+    base = np.concatenate([c[2] for c in chunks])
+    if reference_order:
+        # build_em_input hands the rows over string-sorted (preprocess.py:219): rows that
+        # start at the same variant position are neighbours, and positions follow each other
+        # as the strings "pos:" ("1000:" < "1001:" < "100:" < "101:").  Same grouping here, without
+        # building ten million strings: order by the string rank of the first position, then
+        # by the window's end.
+        rank = np.empty(len(positions), dtype=np.int64)
+        rank[np.argsort(np.array(["%d:" % p for p in positions]))] = np.arange(len(positions))
+        first = pos_idx[row_ptr[:-1]]
+        order = np.lexsort((lens, rank[first]))
+        new_ptr = np.zeros_like(row_ptr)
+        np.cumsum(lens[order], out=new_ptr[1:])
+        take = (np.repeat(row_ptr[:-1][order] - new_ptr[:-1], lens[order])
+                + np.arange(new_ptr[-1]))
+        row_ptr, pos_idx, base = new_ptr, pos_idx[take], base[take]
+    return Mixture(row_ptr, pos_idx, base, np.ones(len(lens), dtype=np.int64), None, len(lens))

@@ -331,12 +331,14 @@ def test_batched_restarts_equal_sequential(n_multi):
     assert close_mix(m_b, o_m)
 
 
-@pytest.mark.parametrize("n_extra", [0, 37])
-def test_coded_rows_equal_fp64_rows(phylo17, n_extra):
-    """Rows with at most 256 distinct values are stored as one byte per cell plus a table
-    (em_pack_kernel) and looked up in shared memory by the pass kernel
-    (em_pass_coded_kernel); rows with more go through the fp64 pass.  The same numbers enter
-    the sums; only the order of the additions differs from the fp64 path (MXB_EM_NO_PACK=1)."""
+@pytest.mark.parametrize("n_extra,n_multi", [(0, 1), (37, 1), (150, 3)])
+def test_class_tiles_equal_fp64_rows(phylo17, n_extra, n_multi):
+    """A matrix built from string-sorted signatures runs over class tiles (em_tiles.cuh: per
+    128-row batch the bit-identical columns collapse into classes; tile_pi / tile_pass /
+    tile_gather kernels).  The same non-negative terms enter every sum, regrouped; results must
+    equal the fp64-row pass (MXB_EM_NO_PACK=1) to rounding with identical iteration counts,
+    and the oracle.  Noise rows in the middle make batches whose columns are all distinct
+    (the widest row teams: 16 warps per row)."""
     import ctypes
     import os
     from mixemt_b200._lib import lib, check, ptr
@@ -346,11 +348,7 @@ def test_coded_rows_equal_fp64_rows(phylo17, n_extra):
     tables = HapVarBaseMatrix(phylo17.refseq, phylo17, haps).pack()
     mat, _, _, _ = build_matrix_from_csr(tables, mix.csr(tables))
     wts = mix.weights.astype(np.float64)
-    distinct = np.array([len(np.unique(r)) for r in mat])
-    if n_extra == 0:
-        keep = distinct <= 256
-        mat, wts = np.ascontiguousarray(mat[keep]), wts[keep]
-    else:
+    if n_extra:
         rs = np.random.RandomState(3)
         noise = mat[:n_extra] - rs.gamma(2.0, 1.0, size=(n_extra, mat.shape[1]))
         mat = np.ascontiguousarray(np.vstack([mat[:1500], noise, mat[1500:]]))
@@ -359,27 +357,89 @@ def test_coded_rows_equal_fp64_rows(phylo17, n_extra):
     n, h = mat.shape
     ctx = get_context()
     dev = DeviceMatrix.from_host(ctx, mat)
-    # the session reports what its pass reads
+    # the session reports what its pass reads: tiles, far fewer bytes than the fp64 rows
     sess = ctypes.c_void_p()
     check(lib.mxb_em_create(ctx.handle, dev.handle, ptr(wts), 0, ctypes.byref(sess)))
-    nbytes, n_dense = ctypes.c_int64(), ctypes.c_int64()
-    check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nbytes), ctypes.byref(n_dense)))
+    nbytes, flag = ctypes.c_int64(), ctypes.c_int64()
+    check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nbytes), ctypes.byref(flag)))
     lib.mxb_em_destroy(sess)
-    expect_dense = int((np.array([len(np.unique(r)) for r in mat]) > 256).sum())
-    assert n_dense.value == expect_dense
-    assert nbytes.value == n * (h + 2048) + expect_dense * h * 8 < 0.5 * n * h * 8
+    assert flag.value == 0 and nbytes.value < 0.5 * n * h * 8
 
-    inits = np.log(np.random.RandomState(1).dirichlet([1.0] * h, size=1))
-    a = make_args(max_iter=400, tolerance=1e-5)
+    inits = np.log(np.random.RandomState(1).dirichlet([1.0] * h, size=n_multi))
+    a = make_args(max_iter=400, tolerance=1e-5, n_multi=n_multi)
     p_c, m_c, info_c, _ = em.run_em_device(dev, wts, a, inits=inits)
     os.environ["MXB_EM_NO_PACK"] = "1"
     try:
+        sess = ctypes.c_void_p()
+        check(lib.mxb_em_create(ctx.handle, dev.handle, ptr(wts), 0, ctypes.byref(sess)))
+        check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nbytes), ctypes.byref(flag)))
+        lib.mxb_em_destroy(sess)
+        assert flag.value == -1 and nbytes.value == n * ((h + 15) // 16 * 16) * 8
         p_f, m_f, info_f, _ = em.run_em_device(dev, wts, a, inits=inits)
     finally:
         del os.environ["MXB_EM_NO_PACK"]
-    assert info_c["iterations"] == info_f["iterations"] and info_c["iterations"][0] > 20
+    assert info_c["iterations"] == info_f["iterations"] and min(info_c["iterations"]) > 20
     assert np.abs(p_c - p_f).max() < 1e-13
     assert close_mix(m_c, m_f, 1e-10)
     o_p, o_m, o_it = oracle_c.run_em(mat, wts, inits, a.max_iter, a.tolerance)
     assert list(o_it) == info_c["iterations"]
     assert np.abs(p_c - o_p).max() < 1e-10
+    assert close_mix(m_c, o_m)
+
+
+def test_class_tiles_fall_back_on_unsorted_rows(phylo17):
+    """Rows in random order share no column classes within a batch: the session keeps the
+    fp64 rows (and still equals the oracle)."""
+    import ctypes
+    from mixemt_b200._lib import lib, check, ptr
+    haps = sorted(phylo17.hap_var)
+    mix = synth.make_mixture(phylo17, phylo17.refseq, [("H1", 0.6), ("L3e", 0.4)], 3000, seed=6)
+    tables = HapVarBaseMatrix(phylo17.refseq, phylo17, haps).pack()
+    mat, _, _, _ = build_matrix_from_csr(tables, mix.csr(tables))
+    perm = np.random.RandomState(2).permutation(mat.shape[0])
+    mat, wts = np.ascontiguousarray(mat[perm]), mix.weights[perm].astype(np.float64)
+    ctx = get_context()
+    dev = DeviceMatrix.from_host(ctx, mat)
+    sess = ctypes.c_void_p()
+    check(lib.mxb_em_create(ctx.handle, dev.handle, ptr(wts), 0, ctypes.byref(sess)))
+    nbytes, flag = ctypes.c_int64(), ctypes.c_int64()
+    check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nbytes), ctypes.byref(flag)))
+    lib.mxb_em_destroy(sess)
+    assert flag.value == -1
+    inits = np.log(np.random.RandomState(1).dirichlet([1.0] * mat.shape[1], size=1))
+    a = make_args(max_iter=60, tolerance=1e-9)
+    p, m, info, _ = em.run_em_device(dev, wts, a, inits=inits)
+    o_p, o_m, o_it = oracle_c.run_em(mat, wts, inits, a.max_iter, a.tolerance)
+    assert np.abs(p - o_p).max() < 1e-10 and close_mix(m, o_m)
+
+
+def test_config1_to_convergence_against_oracle(phylo17):
+    """BASELINE.json config 1 (H1 70 % + L3e 30 %, 10 000 fragments x 5408 Build-17
+    haplogroups) from a Dirichlet(1) start to convergence at the reference's default
+    tolerance: same iteration count as the CPU oracle, proportions within 1e-6 (north star),
+    identical argmax votes and identical read-to-contributor assignments
+    (assemble.py:267-334 restated in oracle_np)."""
+    haps = sorted(phylo17.hap_var)
+    mix = synth.make_mixture(phylo17, phylo17.refseq, [("H1", 0.7), ("L3e", 0.3)], 10000, seed=1)
+    tables = HapVarBaseMatrix(phylo17.refseq, phylo17, haps).pack()
+    mat, _, dmat, _ = build_matrix_from_csr(tables, mix.csr(tables), keep_device=True)
+    wts = mix.weights.astype(np.float64)
+    inits = np.log(np.random.RandomState(5).dirichlet([1.0] * len(haps), size=1))
+    a = make_args(max_iter=10000, tolerance=1e-4)
+    props, read_mix, info, _ = em.run_em_device(dmat, wts, a, inits=inits)
+    o_props, o_mix, o_iters = oracle_c.run_em(mat, wts, inits, a.max_iter, a.tolerance)
+    assert info["converged"] == [1] and info["iterations"] == list(o_iters)
+    assert info["iterations"][0] > 300
+    assert np.abs(props - o_props).max() < PROP_TOL
+    assert np.array_equal(np.argmax(read_mix, 1), np.argmax(o_mix, 1))
+    top = np.argsort(props)[::-1][:2]
+    assert [haps[i] for i in top] == ["H1", "L3e"]
+    contribs = [["hap%d" % (k + 1), haps[j], props[j]] for k, j in enumerate(top.tolist())]
+    got = oracle_np.assign_read_indexes(contribs, (props, read_mix), haps, len(wts), 2.0)
+    want = oracle_np.assign_read_indexes(contribs, (o_props, o_mix), haps, len(wts), 2.0)
+    assert got == want
+    from mixemt_b200 import consumers
+    dev_assign = consumers.assign_read_indexes(contribs, (props, read_mix), haps,
+                                               [[i] for i in range(len(wts))], 2.0)
+    assert {k: set(v) for k, v in dev_assign.items()} == want
+    dmat.free()
