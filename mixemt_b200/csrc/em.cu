@@ -77,12 +77,16 @@ struct mxb_em {
     // Class tiles (em_tiles.cuh): when `tiled` the pass reads `tile_v` instead of `lin`.
     bool tiled = false;
     int n_batches = 0, tile_hs = 0, tile_parts = 0, tile_grid = 0;
-    unsigned char *tile_block = nullptr;   // [perm][cmap][desc][order]
-    unsigned char *tile_vecs = nullptr;    // [pi_cls][u_cls]
-    unsigned short *tile_perm = nullptr, *tile_cmap = nullptr;
+    unsigned char *tile_block = nullptr;   // [perm][cmap][ckey][desc]
+    unsigned char *tile_vecs = nullptr;    // [pi_cls][u_sum][u shares][plan][slot_ptr][slot_items][items][p_off][done]
+    unsigned short *tile_perm = nullptr, *tile_cmap = nullptr, *tile_ckey = nullptr;
     TileDesc *tile_desc = nullptr;
-    int *tile_order = nullptr;
-    double *tile_pi = nullptr, *tile_u = nullptr;
+    TileItem *tile_items = nullptr;
+    TilePlan *tile_plan = nullptr;
+    int *tile_slot_ptr = nullptr, *tile_slot_items = nullptr;
+    double *tile_pi = nullptr, *tile_u = nullptr, *tile_usum = nullptr;
+    int64_t *tile_poff = nullptr;
+    int *tile_done = nullptr;
     double *tile_v = nullptr;
     int64_t tile_cells = 0;                // doubles in tile_v
     int64_t tile_bytes_per_pass = 0;
@@ -172,24 +176,32 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
         return MXB_OK;
     }
     if (em->tiled) {
-        MXB_CUDA(launch_pdl(tile_pi_kernel, dim3(std::min(em->n_batches, 3 * em->tile_grid)),
-                            dim3(kTileThreads), 0, s,
-                            (const unsigned short *)em->tile_perm,
-                            (const unsigned short *)em->tile_cmap, em->tile_hs, (int)em->n_cols,
-                            (const TileDesc *)em->tile_desc, em->n_batches,
-                            (const double *)em->pi[0], (const double *)em->pi[1],
-                            (const EmState *)em->state, em->tile_pi));
+        {
+            const int per = (int)ceil_div(em->n_cols, kTileThreads);
+            auto pi_fn = per <= 4 ? tile_pi_kernel<4> : per <= 8 ? tile_pi_kernel<8>
+                         : per <= 12 ? tile_pi_kernel<12> : tile_pi_kernel<16>;
+            MXB_CUDA(launch_pdl(pi_fn, dim3(std::min(em->n_batches, 2 * ctx->num_sms)),
+                                dim3(kTileThreads), (size_t)em->ld * sizeof(double), s,
+                                (const unsigned short *)em->tile_perm,
+                                (const unsigned short *)em->tile_ckey, em->tile_hs,
+                                (int)em->n_cols, (const TileDesc *)em->tile_desc, em->n_batches,
+                                (const double *)em->pi[0], (const double *)em->pi[1],
+                                (const EmState *)em->state, em->tile_pi));
+        }
         if (marks) MXB_CUDA(cudaEventRecord(marks[0], s));
         MXB_CUDA(launch_pdl(tile_pass_kernel, dim3(em->tile_grid), dim3(kTileThreads),
-                            kTileSmemBytes, s, (const TileDesc *)em->tile_desc,
-                            (const int *)em->tile_order, em->n_batches,
-                            (const double *)em->tile_v, (const double *)em->tile_pi,
-                            (const double *)em->weights, em->state, em->tile_u));
+                            kTilePassSmem, s, (const TileDesc *)em->tile_desc,
+                            (const TileItem *)em->tile_items,
+                            (const TilePlan *)em->tile_plan, (const int *)em->tile_slot_ptr,
+                            (const int *)em->tile_slot_items, (const double *)em->tile_v,
+                            (const double *)em->tile_pi, (const double *)em->weights, em->state,
+                            em->tile_u, em->tile_usum, em->tile_done));
         if (marks) MXB_CUDA(cudaEventRecord(marks[1], s));
-        MXB_CUDA(launch_pdl(tile_gather_kernel, dim3((unsigned)ceil_div(em->ld, 256), em->tile_parts),
-                            dim3(256), 0, s, (const unsigned short *)em->tile_cmap, em->tile_hs,
-                            (int)em->n_cols, em->ld, (const TileDesc *)em->tile_desc,
-                            em->n_batches, (const double *)em->tile_u,
+        MXB_CUDA(launch_pdl(tile_gather_kernel,
+                            dim3((unsigned)ceil_div(em->ld, kGatherThreads), em->tile_parts),
+                            dim3(kGatherThreads), 0, s, (const unsigned short *)em->tile_cmap,
+                            em->tile_hs, (int)em->n_cols, em->ld, (const int64_t *)em->tile_poff,
+                            em->n_batches, (const double *)em->tile_usum,
                             (const EmState *)em->state, em->partials));
         if (marks) MXB_CUDA(cudaEventRecord(marks[2], s));
         ctx->launches += 3;
@@ -318,7 +330,8 @@ __global__ void em_reset_state_kernel(EmState *st, long long max_iter, double to
 template <int ITEMS>
 static cudaError_t launch_tile_class(mxb_ctx *ctx, int grid, const unsigned long long *hash, int hs,
                                      int n_cols, int n_batches, unsigned short *perm,
-                                     unsigned short *cmap, unsigned short *rep, int *n_cls) {
+                                     unsigned short *ckey, unsigned short *cmap,
+                                     unsigned short *rep, int *n_cls) {
     using Sort = cub::BlockRadixSort<unsigned long long, kTileThreads, ITEMS, unsigned short>;
     using Scan = cub::BlockScan<int, kTileThreads>;
     const size_t smem = std::max(sizeof(typename Sort::TempStorage), sizeof(typename Scan::TempStorage));
@@ -326,13 +339,13 @@ static cudaError_t launch_tile_class(mxb_ctx *ctx, int grid, const unsigned long
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     tile_class_kernel<ITEMS><<<grid, kTileThreads, smem, ctx->stream>>>(hash, hs, n_cols, n_batches,
-                                                                        perm, cmap, rep, n_cls);
+                                                                        perm, ckey, cmap, rep, n_cls);
     return cudaGetLastError();
 }
 
 static int em_pack_tiles(mxb_em *em) {
     mxb_ctx *ctx = em->ctx;
-    if (!em->fast || !em->fused_tail || em->n_rows == 0 || em->n_cols > kTileMaxCols ||
+    if (!em->fast || em->n_rows == 0 || em->n_cols > kTileMaxCols ||
         getenv("MXB_EM_NO_PACK"))
         return MXB_OK;
     const int64_t n = em->n_rows, h = em->n_cols;
@@ -366,19 +379,18 @@ static int em_pack_tiles(mxb_em *em) {
     unsigned short *rep = reinterpret_cast<unsigned short *>(tmp + b_hash);
     int *d_ncls = reinterpret_cast<int *>(tmp + b_hash + b_map);
     int *d_bad = reinterpret_cast<int *>(tmp + b_hash + b_map + b_int);
-    // persistent: [perm][cmap][desc][order] first, class vectors appended once their size is known
+    // persistent: [perm][cmap][desc]; the class vectors and the plan of the pass follow in a
+    // second block once the class counts are known
     const size_t b_desc = up((size_t)nb * sizeof(TileDesc));
-    const size_t head_bytes = 2 * b_map + b_desc + b_int;
-    // (allocated with room for the class vectors of the widest possible layout only after the
-    // class counts are known; the maps are written into a first block and kept)
+    const size_t head_bytes = 3 * b_map + b_desc;
     unsigned char *maps = nullptr;
     e = dev_alloc(ctx, (void **)&maps, head_bytes);
     if (e != cudaSuccess) return give_up(false, "maps");
     block = maps;
     unsigned short *perm = reinterpret_cast<unsigned short *>(maps);
     unsigned short *cmap = reinterpret_cast<unsigned short *>(maps + b_map);
-    TileDesc *d_desc = reinterpret_cast<TileDesc *>(maps + 2 * b_map);
-    int *d_order = reinterpret_cast<int *>(maps + 2 * b_map + b_desc);
+    unsigned short *ckey = reinterpret_cast<unsigned short *>(maps + 2 * b_map);
+    TileDesc *d_desc = reinterpret_cast<TileDesc *>(maps + 3 * b_map);
 
     const int grid = std::min(nb, ctx->num_sms * 2);
     tile_hash_kernel<<<std::min(nb, ctx->num_sms * 4), kTileThreads, 0, ctx->stream>>>(
@@ -386,10 +398,10 @@ static int em_pack_tiles(mxb_em *em) {
     e = cudaGetLastError();
     if (e == cudaSuccess) {
         const int items = (int)ceil_div(h, kTileThreads);
-        if (items <= 4) e = launch_tile_class<4>(ctx, grid, hash, hs, (int)h, nb, perm, cmap, rep, d_ncls);
-        else if (items <= 8) e = launch_tile_class<8>(ctx, grid, hash, hs, (int)h, nb, perm, cmap, rep, d_ncls);
-        else if (items <= 12) e = launch_tile_class<12>(ctx, grid, hash, hs, (int)h, nb, perm, cmap, rep, d_ncls);
-        else e = launch_tile_class<16>(ctx, grid, hash, hs, (int)h, nb, perm, cmap, rep, d_ncls);
+        if (items <= 4) e = launch_tile_class<4>(ctx, grid, hash, hs, (int)h, nb, perm, ckey, cmap, rep, d_ncls);
+        else if (items <= 8) e = launch_tile_class<8>(ctx, grid, hash, hs, (int)h, nb, perm, ckey, cmap, rep, d_ncls);
+        else if (items <= 12) e = launch_tile_class<12>(ctx, grid, hash, hs, (int)h, nb, perm, ckey, cmap, rep, d_ncls);
+        else e = launch_tile_class<16>(ctx, grid, hash, hs, (int)h, nb, perm, ckey, cmap, rep, d_ncls);
     }
     ctx->launches += 2;
     std::vector<int> ncls((size_t)nb);
@@ -401,8 +413,8 @@ static int em_pack_tiles(mxb_em *em) {
 
     // layout: team width and chunk count per batch, tile and class-vector offsets
     std::vector<TileDesc> desc((size_t)nb);
-    std::vector<int> order((size_t)nb);
-    int64_t v_cells = 0, p_cells = 0;
+    int64_t v_cells = 0, p_cells = 0, u_cells = 0;
+    std::vector<TileItem> items;
     for (int b = 0; b < nb; ++b) {
         TileDesc &d = desc[(size_t)b];
         d.row0 = b * kTileRows;
@@ -413,21 +425,99 @@ static int em_pack_tiles(mxb_em *em) {
         d.tw = tw;
         d.nk = (int)std::max<int64_t>(1, ceil_div(d.n_cls, 64 * tw));
         d.c_pad = 64 * tw * d.nk;
+        // up to four work items of at least 16 rows: enough items to keep every team of every
+        // SM busy (a CTA holds 16 / tw teams), shares of U_b added again by the gather kernel
+        d.ng = (int)std::max<int64_t>(1, std::min<int64_t>(kTileItems, d.n_rows / 16));
+        d.pad = 0;
         d.v_off = v_cells;
         d.p_off = p_cells;
+        d.u_off = u_cells;
         v_cells += (int64_t)d.n_rows * d.c_pad;
         p_cells += d.c_pad;
-        order[(size_t)b] = b;
+        u_cells += (int64_t)d.ng * d.c_pad;
+        for (int g = 0; g < d.ng; ++g) {
+            TileItem it;
+            it.batch = b;
+            it.g = g;
+            it.r0 = (int)((int64_t)d.n_rows * g / d.ng);
+            it.r1 = (int)((int64_t)d.n_rows * (g + 1) / d.ng);
+            items.push_back(it);
+        }
     }
-    // a team handles its rows one after the other and a CTA holds 16 / tw teams: the time of a
-    // batch grows with tw (fewer rows at a time) and with the chunks per thread
-    auto batch_cost = [&](int b) {
-        const TileDesc &d = desc[(size_t)b];
-        return (int64_t)d.n_rows * d.tw * (48 + 8 * d.nk);
-    };
-    std::stable_sort(order.begin(), order.end(),
-                     [&](int a, int b) { return batch_cost(a) > batch_cost(b); });
-    const double tile_bytes = (double)v_cells * 8 + 3.0 * (double)nb * hs * 2 + 4.0 * (double)p_cells * 8;
+    const int n_items = (int)items.size();
+    // Static plan of the pass: every CTA works on batches of one team width, its 16 / tw teams
+    // on different batches.  CTAs are dealt to the widths in proportion to the work (a row
+    // costs a team about 40 + 10 nk issue slots per warp, a little more with the per-row
+    // barrier of wide teams), batches to team slots longest first onto the least loaded slot.
+    std::vector<TilePlan> plan;
+    std::vector<int> slot_ptr(1, 0), slot_items;   // items of every team slot
+    {
+        auto batch_cost = [&](int i) {     // of work item i
+            const TileDesc &d = desc[(size_t)items[(size_t)i].batch];
+            return (double)(items[(size_t)i].r1 - items[(size_t)i].r0) * (40.0 + 10.0 * d.nk) *
+                   (d.tw > 1 ? 1.3 : 1.0) + 200.0;
+        };
+        std::vector<int> of_width[5];
+        double demand[5] = {0, 0, 0, 0, 0}, demand_sum = 0.0;
+        for (int i = 0; i < n_items; ++i) {
+            const int tw = desc[(size_t)items[(size_t)i].batch].tw;
+            int k = 0;
+            while ((1 << k) < tw) ++k;
+            of_width[k].push_back(i);
+            demand[k] += batch_cost(i) * tw / kTileWarps;
+        }
+        for (int k = 0; k < 5; ++k) demand_sum += demand[k];
+        int n_cta[5], total = 0;
+        for (int k = 0; k < 5; ++k) {
+            n_cta[k] = 0;
+            if (of_width[k].empty()) continue;
+            const int teams = kTileWarps >> k;
+            const int cap = (int)ceil_div((int64_t)of_width[k].size(), teams);
+            n_cta[k] = std::max(1, std::min(cap, (int)(ctx->num_sms * demand[k] / demand_sum)));
+            total += n_cta[k];
+        }
+        // hand out what rounding left over to the widths with the most work per CTA
+        for (bool grew = true; total < ctx->num_sms && grew;) {
+            grew = false;
+            int best = -1;
+            double best_load = 0.0;
+            for (int k = 0; k < 5; ++k) {
+                if (of_width[k].empty()) continue;
+                const int cap = (int)ceil_div((int64_t)of_width[k].size(), kTileWarps >> k);
+                if (n_cta[k] >= cap) continue;
+                const double load = demand[k] / n_cta[k];
+                if (best < 0 || load > best_load) { best = k; best_load = load; }
+            }
+            if (best >= 0) { ++n_cta[best]; ++total; grew = true; }
+        }
+        for (int k = 0; k < 5; ++k) {
+            if (n_cta[k] == 0) continue;
+            const int teams = kTileWarps >> k, n_slots = n_cta[k] * teams;
+            std::vector<std::vector<int>> items((size_t)n_slots);
+            std::vector<double> load((size_t)n_slots, 0.0);
+            std::vector<int> &list = of_width[k];
+            std::stable_sort(list.begin(), list.end(),
+                             [&](int a, int b) { return batch_cost(a) > batch_cost(b); });
+            for (int b : list) {
+                const int sl = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+                items[(size_t)sl].push_back(b);
+                load[(size_t)sl] += batch_cost(b);
+            }
+            for (int c = 0; c < n_cta[k]; ++c) {
+                TilePlan pl;
+                pl.tw = 1 << k;
+                pl.slot0 = (int)slot_ptr.size() - 1;
+                plan.push_back(pl);
+                for (int t = 0; t < teams; ++t) {
+                    for (int b : items[(size_t)(c * teams + t)]) slot_items.push_back(b);
+                    slot_ptr.push_back((int)slot_items.size());
+                }
+            }
+        }
+    }
+    const int n_plan = (int)plan.size();
+    const double tile_bytes = (double)v_cells * 8 + 3.0 * (double)nb * hs * 2 +
+                              2.0 * (double)(p_cells + u_cells) * 8;
     const double fp64_bytes = (double)n * (double)em->ld * 8;
     if (verbose) {
         int64_t c_sum = 0, c_max = 0, wide = 0;
@@ -445,14 +535,42 @@ static int em_pack_tiles(mxb_em *em) {
 
     e = dev_alloc(ctx, (void **)&v, (size_t)v_cells * sizeof(double));
     unsigned char *vecs = nullptr;
-    if (e == cudaSuccess) e = dev_alloc(ctx, (void **)&vecs, 2 * up((size_t)p_cells * sizeof(double)));
+    const size_t b_vec = up((size_t)p_cells * sizeof(double));
+    const size_t b_u = up((size_t)u_cells * sizeof(double));
+    const size_t b_plan = up((size_t)n_plan * sizeof(TilePlan));
+    const size_t b_sptr = up(slot_ptr.size() * sizeof(int));
+    const size_t b_sitems = up((size_t)n_items * sizeof(int));
+    const size_t b_items = up((size_t)n_items * sizeof(TileItem));
+    const size_t b_poff = up((size_t)nb * sizeof(int64_t));
+    if (e == cudaSuccess)
+        e = dev_alloc(ctx, (void **)&vecs, 2 * b_vec + b_u + b_plan + b_sptr + b_sitems + b_items +
+                                            b_poff + b_int);
     if (e != cudaSuccess) { dev_free(ctx, vecs); return give_up(false, "tiles"); }
     double *pi_cls = reinterpret_cast<double *>(vecs);
-    double *u_cls = reinterpret_cast<double *>(vecs + up((size_t)p_cells * sizeof(double)));
+    double *u_sum = reinterpret_cast<double *>(vecs + b_vec);
+    double *u_cls = reinterpret_cast<double *>(vecs + 2 * b_vec);
+    unsigned char *tail = vecs + 2 * b_vec + b_u;
+    TilePlan *d_plan = reinterpret_cast<TilePlan *>(tail);
+    int *d_slot_ptr = reinterpret_cast<int *>(tail + b_plan);
+    int *d_slot_items = reinterpret_cast<int *>(tail + b_plan + b_sptr);
+    TileItem *d_items = reinterpret_cast<TileItem *>(tail + b_plan + b_sptr + b_sitems);
+    int64_t *d_poff = reinterpret_cast<int64_t *>(tail + b_plan + b_sptr + b_sitems + b_items);
+    int *d_done = reinterpret_cast<int *>(tail + b_plan + b_sptr + b_sitems + b_items + b_poff);
+    std::vector<int64_t> poff((size_t)nb);
+    for (int b = 0; b < nb; ++b) poff[(size_t)b] = desc[(size_t)b].p_off;
     e = cudaMemcpyAsync(d_desc, desc.data(), (size_t)nb * sizeof(TileDesc), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(d_order, order.data(), (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(vecs, 0, 2 * up((size_t)p_cells * sizeof(double)), ctx->stream);
+        e = cudaMemcpyAsync(d_plan, plan.data(), (size_t)n_plan * sizeof(TilePlan), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_slot_ptr, slot_ptr.data(), slot_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_slot_items, slot_items.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_items, items.data(), (size_t)n_items * sizeof(TileItem), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_poff, poff.data(), (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_done, 0, (size_t)nb * sizeof(int), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(vecs, 0, 2 * b_vec + b_u, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, (size_t)nb * sizeof(int), ctx->stream);
     if (e == cudaSuccess) {
         tile_fill_kernel<<<std::min(nb, ctx->num_sms * 4), kTileThreads, 0, ctx->stream>>>(
@@ -466,7 +584,13 @@ static int em_pack_tiles(mxb_em *em) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute((const void *)tile_pass_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTilePassSmem);
+    for (int v = 0; v < 4 && e == cudaSuccess; ++v) {
+        const void *fn = v == 0 ? (const void *)tile_pi_kernel<4> : v == 1 ? (const void *)tile_pi_kernel<8>
+                         : v == 2 ? (const void *)tile_pi_kernel<12> : (const void *)tile_pi_kernel<16>;
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kTileMaxCols * sizeof(double)));
+    }
     if (e != cudaSuccess) { dev_free(ctx, vecs); return give_up(true, "fill"); }
     bool any_bad = false;
     for (int b = 0; b < nb; ++b) any_bad |= bad[(size_t)b] != 0;
@@ -480,17 +604,24 @@ static int em_pack_tiles(mxb_em *em) {
     em->tile_vecs = vecs;
     em->tile_perm = perm;
     em->tile_cmap = cmap;
+    em->tile_ckey = ckey;
     em->tile_desc = d_desc;
-    em->tile_order = d_order;
+    em->tile_plan = d_plan;
+    em->tile_items = d_items;
+    em->tile_usum = u_sum;
+    em->tile_poff = d_poff;
+    em->tile_done = d_done;
+    em->tile_slot_ptr = d_slot_ptr;
+    em->tile_slot_items = d_slot_items;
     em->tile_pi = pi_cls;
     em->tile_u = u_cls;
     em->tile_v = v;
     em->tile_cells = v_cells;
-    em->tile_grid = std::min(nb, ctx->num_sms);
+    em->tile_grid = n_plan;
     em->tile_parts = std::max(1, std::min(32, nb / 8));
     em->n_part = em->tile_parts;
     // what an iteration reads: the tiles, perm + cmap (Pi), cmap (gather), the class vectors
-    em->tile_bytes_per_pass = v_cells * 8 + 3 * (int64_t)nb * hs * 2 + 4 * p_cells * 8 + n * 8;
+    em->tile_bytes_per_pass = v_cells * 8 + 3 * (int64_t)nb * hs * 2 + 2 * (p_cells + u_cells) * 8 + n * 8;
     return rc;
 }
 

@@ -43,16 +43,20 @@ constexpr int kTileThreads = 512;
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kTileMaxNK = 8;        // double2 per thread and row
 constexpr int kTileMaxCols = 8192;   // widest matrix (the fast path's limit on ld)
-constexpr int kTileUsDoubles = 8192; // staging of the per-team class sums: 16 teams x 512 ... 1 x 8192
-constexpr int kTileMaxRU = 4;        // rows in flight per team
-constexpr size_t kTileSmemBytes = (kTileUsDoubles + 2 * kTileMaxRU * kTileWarps) * sizeof(double);
+constexpr int kTileItems = 4;        // work items (row ranges) per batch, at most
 
-struct TileDesc {
+struct TileDesc {           // one batch
     int32_t row0, n_rows;
     int32_t n_cls, c_pad;   // classes; row stride of the batch's tile in doubles (= 64 tw nk)
     int32_t tw, nk;         // warps per row team (1, 2, 4, 8, 16), double2 per thread
+    int32_t ng, pad;        // work items (contiguous row ranges) of the batch
     int64_t v_off;          // tile offset in V (doubles)
-    int64_t p_off;          // offset of the batch's class vectors in Pi / U (doubles)
+    int64_t p_off;          // offset of the batch's class sums Pi_b (doubles)
+    int64_t u_off;          // offset of the batch's ng partial class vectors U_b (doubles)
+};
+
+struct TileItem {           // one work item of the pass: rows [r0, r1) of a batch
+    int32_t batch, r0, r1, g;
 };
 
 __device__ __forceinline__ uint64_t tile_mix(uint64_t h, uint64_t v) {
@@ -91,16 +95,18 @@ tile_hash_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols, i
 
 // Classes of one batch: sort (hash, column), number the runs of equal hashes.
 //   perm[b][e]  column at sorted position e (classes are contiguous, columns ascending inside)
+//   ckey[b][e]  class of that column (non-decreasing in e)
 //   cmap[b][j]  class of column j
 //   rep[b][c]   first (smallest) column of class c
 template <int ITEMS>
 __global__ void __launch_bounds__(kTileThreads)
 tile_class_kernel(const unsigned long long *__restrict__ hash, int hs, int n_cols, int n_batches,
-                  unsigned short *__restrict__ perm, unsigned short *__restrict__ cmap,
-                  unsigned short *__restrict__ rep, int *__restrict__ n_cls) {
+                  unsigned short *__restrict__ perm, unsigned short *__restrict__ ckey,
+                  unsigned short *__restrict__ cmap, unsigned short *__restrict__ rep,
+                  int *__restrict__ n_cls) {
     using Sort = cub::BlockRadixSort<unsigned long long, kTileThreads, ITEMS, unsigned short>;
     using Scan = cub::BlockScan<int, kTileThreads>;
-    extern __shared__ __align__(16) unsigned char tile_smem[];
+    extern __shared__ __align__(128) unsigned char tile_smem[];
     typename Sort::TempStorage &sort_tmp = *reinterpret_cast<typename Sort::TempStorage *>(tile_smem);
     typename Scan::TempStorage &scan_tmp = *reinterpret_cast<typename Scan::TempStorage *>(tile_smem);
     __shared__ unsigned long long last_key[kTileThreads];
@@ -139,6 +145,7 @@ tile_class_kernel(const unsigned long long *__restrict__ hash, int hs, int n_col
                     rep[(size_t)b * hs + cls] = vals[i];
                 }
                 perm[(size_t)b * hs + e] = vals[i];
+                ckey[(size_t)b * hs + e] = (unsigned short)cls;
                 cmap[(size_t)b * hs + vals[i]] = (unsigned short)cls;
             }
         }
@@ -177,8 +184,15 @@ tile_fill_kernel(const double *__restrict__ m, int64_t n_cols, const TileDesc *_
     }
 }
 
-// Pi_b[c] = sum of pi_j over the members of class c, members added in ascending column order
-// within a thread's chunk of `perm` and chunk totals combined by a segmented scan: fixed order.
+// Pi_b[c] = sum of pi_j over the members of class c.  `perm` lists the columns of a batch class
+// by class (ckey = class of every entry, non-decreasing), so a class is a run of entries and
+// the sums are a segmented reduction: every thread adds the entries of its chunk run by run
+// in order (branch-free: the run structure is data, not control flow), stores the runs that
+// begin and end inside the chunk, and the runs that cross chunk borders are completed by a
+// segmented scan over the threads (shuffles in the warp, one more shuffle scan over the 16
+// warp totals).  Fixed order of additions: deterministic.
+constexpr int kPiPer = 16;       // entries per thread, at most (512 x 16 = 8192 columns)
+
 struct SegItem {
     int flag;      // 1: a new class starts at (or inside) this item
     double val;    // sum of the trailing run
@@ -189,132 +203,162 @@ __device__ __forceinline__ SegItem seg_combine(const SegItem &a, const SegItem &
     r.val = b.flag ? b.val : a.val + b.val;
     return r;
 }
+__device__ __forceinline__ SegItem seg_shfl_up(const SegItem &v, int off) {
+    SegItem o;
+    o.flag = __shfl_up_sync(0xffffffffu, v.flag, off);
+    o.val = __shfl_up_sync(0xffffffffu, v.val, off);
+    return o;
+}
 
+template <int PER>
 __global__ void __launch_bounds__(kTileThreads)
-tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned short *__restrict__ cmap,
+tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned short *__restrict__ ckey,
                int hs, int n_cols, const TileDesc *__restrict__ desc, int n_batches,
                const double *__restrict__ pi0, const double *__restrict__ pi1,
                const EmState *__restrict__ st, double *__restrict__ pi_cls) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    double *pi = reinterpret_cast<double *>(tile_smem);     // [n_cols]: the gathers below are
+    // random 8-byte reads; from L1 they cost a tag lookup per distinct line (the kernel was
+    // bound by exactly that), from shared memory a couple of bank wavefronts per warp
     pdl_wait();
     pdl_launch_dependents();
     if (st->done) return;
-    const double *__restrict__ pi = st->cur ? pi1 : pi0;
-    __shared__ int s_key[kTileThreads + 1];      // key of a thread's first element
+    const double *__restrict__ pi_g = st->cur ? pi1 : pi0;
     __shared__ int s_flag[kTileWarps];
     __shared__ double s_val[kTileWarps];
+    __shared__ double s_carry[kTileWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n_cols + kTileThreads - 1) / kTileThreads;
+    for (int j = tid; j < n_cols; j += kTileThreads) pi[j] = pi_g[j];
+    __syncthreads();
+    const int e0 = min(n_cols, tid * PER), cnt = min(n_cols, e0 + PER) - e0;
     for (int b = blockIdx.x; b < n_batches; b += gridDim.x) {
-        const unsigned short *pm = perm + (size_t)b * hs;
-        const unsigned short *cm = cmap + (size_t)b * hs;
+        const unsigned short *pm = perm + (size_t)b * hs + e0;
+        const unsigned short *ck = ckey + (size_t)b * hs + e0;
         double *out = pi_cls + desc[b].p_off;
-        const int e0 = min(n_cols, tid * per), e1 = min(n_cols, e0 + per);
-        // head run (may continue the previous thread's), interior runs (complete: stored
-        // straight away), tail run (may continue into the next thread)
-        int head_key = -1, tail_key = -1, n_runs = 0;
-        double head_sum = 0.0, run_sum = 0.0;
-        for (int eb = e0; eb < e1; eb += 8) {
-            // eight elements at a time: the three dependent loads of each (position -> column
-            // -> class and proportion) are issued side by side
-            int key[8];
-            double pv[8];
+        int key[PER + 1];
+        double pv[PER];
+        const int prev_key = (cnt > 0 && e0 > 0) ? ck[-1] : -1;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int col = eb + q < e1 ? pm[eb + q] : 0;
-                key[q] = eb + q < e1 ? cm[col] : -3;
-                pv[q] = pi[col];
-            }
+        for (int q = 0; q < PER; ++q) {
+            const bool in = q < cnt;
+            key[q] = in ? ck[q] : -2;
+            pv[q] = in ? pi[pm[q]] : 0.0;
+        }
+        // class of the entry after the chunk (-2: none): tells whether the last run ends here
+        key[PER] = -2;
+        const int next_key = (cnt > 0 && e0 + cnt < n_cols) ? ck[cnt] : -2;
+        const bool live = cnt > 0;
+        const int f_head = live ? (key[0] != prev_key) : 1;
+        double s = 0.0, head_sum = 0.0;
+        int started = f_head;            // a run has begun at or inside this chunk
+        int head_open = 1;               // the first run has not ended yet
+        int head_key = key[0];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                if (key[q] == -3) break;
-                if (key[q] != tail_key) {
-                    if (n_runs == 1) head_sum = run_sum;
-                    else if (n_runs > 1) out[tail_key] = run_sum;
-                    if (n_runs == 0) head_key = key[q];
-                    tail_key = key[q];
-                    run_sum = pv[q];
-                    ++n_runs;
-                } else {
-                    run_sum += pv[q];
-                }
+        for (int q = 0; q < PER; ++q) {
+            if (q < cnt) {
+                const bool start = q == 0 ? true : key[q] != key[q - 1];
+                s = start ? pv[q] : s + pv[q];
+                const int after = q + 1 < cnt ? key[q + 1] : next_key;
+                const bool ends = after != key[q];
+                const bool interior_start = q > 0 && start;
+                started |= interior_start ? 1 : 0;
+                if (interior_start) head_open = 0;
+                // a run that ends here and did not come in from the previous thread is final
+                if (ends && (head_open == 0 || f_head)) out[key[q]] = s;
+                if (head_open && (ends || q + 1 == cnt)) head_sum = s;
+                if (ends) head_open = 0;
             }
         }
-        const bool live = n_runs > 0;
-        const bool single = n_runs == 1;
-        if (single) head_sum = run_sum;
-        __syncthreads();                       // s_key of the previous batch is no longer read
-        s_key[tid] = live ? head_key : -2;
-        if (tid == 0) s_key[kTileThreads] = -2;
-        __syncthreads();
-        // the last element before this chunk belongs to the previous live thread; chunks are
-        // contiguous, so that is thread tid - 1 whenever this thread is live
-        int prev_tail = -1;
-        if (live && tid > 0) prev_tail = cm[pm[e0 - 1]];
-        const int f_head = live ? (head_key != prev_tail) : 1;
-        // aggregate of this thread's items [head][tail]
+        // aggregate of the chunk: trailing-run sum, and whether a run began here
         SegItem agg;
-        agg.flag = f_head | (single ? 0 : 1);
-        agg.val = single ? head_sum : run_sum;
-        if (!live) { agg.flag = 1; agg.val = 0.0; }
-        // inclusive segmented scan over the threads (Kogge-Stone in the warp, then over warps)
+        agg.flag = live ? started : 1;
+        agg.val = live ? s : 0.0;
         SegItem inc = agg;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
-            SegItem o;
-            o.flag = __shfl_up_sync(0xffffffffu, inc.flag, off);
-            o.val = __shfl_up_sync(0xffffffffu, inc.val, off);
+            const SegItem o = seg_shfl_up(inc, off);
             if (lane >= off) inc = seg_combine(o, inc);
         }
+        __syncthreads();                       // the scratch of the previous batch has been read
         if (lane == 31) { s_flag[warp] = inc.flag; s_val[warp] = inc.val; }
         __syncthreads();
-        SegItem carry;                          // everything before this warp
-        carry.flag = 1; carry.val = 0.0;
-        for (int w = 0; w < warp; ++w) {
-            SegItem o;
-            o.flag = s_flag[w]; o.val = s_val[w];
-            carry = seg_combine(carry, o);
-        }
-        // exclusive value for this thread = carry (+) inclusive of lane - 1
-        SegItem exc;
-        exc.flag = __shfl_up_sync(0xffffffffu, inc.flag, 1);
-        exc.val = __shfl_up_sync(0xffffffffu, inc.val, 1);
-        if (lane == 0) exc = carry; else exc = seg_combine(carry, exc);
-        if (live) {
-            const double head_total = f_head ? head_sum : exc.val + head_sum;
-            const int next_key = s_key[tid + 1];          // -2: nothing follows
-            if (single) {
-                if (next_key != head_key) out[head_key] = head_total;
-            } else {
-                out[head_key] = head_total;               // the head run ended inside this chunk
-                if (next_key != tail_key) out[tail_key] = run_sum;
+        if (warp == 0) {
+            SegItem wv;
+            wv.flag = lane < kTileWarps ? s_flag[lane] : 1;
+            wv.val = lane < kTileWarps ? s_val[lane] : 0.0;
+#pragma unroll
+            for (int off = 1; off < kTileWarps; off <<= 1) {
+                const SegItem o = seg_shfl_up(wv, off);
+                if (lane >= off) wv = seg_combine(o, wv);
             }
+            // exclusive: what is open at the end of the warps before this one
+            const SegItem ex = seg_shfl_up(wv, 1);
+            if (lane < kTileWarps) s_carry[lane] = lane == 0 ? 0.0 : ex.val;
+        }
+        __syncthreads();
+        SegItem exc = seg_shfl_up(inc, 1);      // open run at the end of the previous thread
+        if (lane == 0) { exc.flag = 0; exc.val = s_carry[warp]; }
+        else if (!exc.flag) exc.val += s_carry[warp];
+        if (live && !f_head) {
+            // the first run came in from the previous thread(s): it is final here if it ended
+            // inside the chunk or if nothing of its class follows the chunk
+            const bool single = !started;
+            const double total = exc.val + head_sum;
+            if (!single || next_key != head_key) out[head_key] = total;
         }
     }
 }
 
 // ---- the pass ------------------------------------------------------------------------------
-// One batch at a time per CTA (batches in descending order of work, dealt round robin).  A row
-// is handled by a team of `tw` warps: thread tt of the team owns the double2 chunks tt + 32 tw k
-// (k < nk) of the class vectors -- Pi_b and its share of U_b live in registers for the whole
-// batch -- and the teams of a CTA take the rows of the batch in turn.  tw = 1 (at most 512
-// classes, the bulk of the batches) needs no block-level synchronisation per row at all: a row
-// costs a warp nk 16-byte loads, 4 nk DFMA, one shuffle butterfly and a division.  Wider teams
-// add one named barrier per row.  RU rows are in flight per team.
+// A work item is a contiguous range of rows of one batch (a batch is cut into up to four), handled
+// by a *team* of `tw` warps (tw = 1 for at most 512 classes -- the bulk --, 2, 4, 8 or 16 for the
+// wider ones); the 16 / tw teams of a CTA work on different items independently, CTAs and teams
+// are handed their items by a static, cost-balanced plan made when the tiles are built (em.cu).  Thread tt of a team owns the double2 chunks tt + 32 tw k (k < nk) of the
+// class vectors: Pi_b and the item's share of U_b live in registers for the whole item, the
+// share is stored straight from registers, and the item of a batch that finishes last adds
+// the shares in item order into U_b -- no block-level synchronisation anywhere.
+// The rows of the tile stream through a team-private shared-memory ring filled by 1-D bulk
+// async copies (cp.async.bulk + mbarrier complete_tx, one instruction per row, issued by the
+// team's first thread); a row costs a warp nk 16-byte shared loads, 4 nk DFMA, one shuffle
+// butterfly and a division (plus one named barrier per row for tw > 1).
+constexpr int kTileRingBytes = 192 * 1024;     // all teams of a CTA together
+constexpr int kTileMaxStages = 16;             // ring slots of a team
+constexpr size_t kTilePassSmem = kTileRingBytes + kTileWarps * kTileMaxStages * sizeof(uint64_t) +
+                                 2 * kTileWarps * sizeof(double) + kTileWarps * sizeof(int) + 128;
+
+struct TilePlan {          // one per CTA
+    int32_t tw;            // team width of this CTA
+    int32_t slot0;         // first team slot (slot_ptr index) of this CTA's teams
+};
+
 __device__ __forceinline__ void team_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int NKMAX, int RU>
-__device__ __forceinline__ void tile_batch(const TileDesc &d, const double *__restrict__ v,
+template <int NKMAX>
+__device__ __forceinline__ void tile_batch(const TileDesc &d, const TileItem &it, int tw, int team, int tt,
+                                           const double *__restrict__ v,
                                            const double *__restrict__ pi_cls,
                                            const double *__restrict__ w, double *__restrict__ u_out,
-                                           double *us, double *red, int &bad) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tw = d.tw, nk = d.nk;
+                                           double *__restrict__ u_sum, int *__restrict__ done,
+                                           uint32_t ring_u32, int ring_bytes, uint32_t bars_u32,
+                                           double *red, int *ired, uint32_t &phase_bits,
+                                           int &parity, int &bad) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nk = d.nk;
     const int tthreads = 32 * tw;
-    const int team = warp / tw, wit = warp - team * tw, n_teams = kTileWarps / tw;
-    const int tt = tid - team * tthreads;
-    const int c_pad = d.c_pad;
+    const uint32_t row_bytes = (uint32_t)d.c_pad * 8u;
+    const int ns = min(kTileMaxStages, ring_bytes / (int)row_bytes);
+    const bool producer = tt == 0;
+    const int n_rows = it.r1 - it.r0;
+    const double *tile = v + d.v_off + (size_t)it.r0 * d.c_pad;
+    if (producer) {
+        for (int q = 0; q < ns && q < n_rows; ++q) {
+            mbar_expect_tx_u32(bars_u32 + 8u * q, row_bytes);
+            bulk_load_u32(ring_u32 + (uint32_t)q * row_bytes, tile + (size_t)q * d.c_pad, row_bytes,
+                          bars_u32 + 8u * q);
+        }
+    }
     const double2 *pcls = reinterpret_cast<const double2 *>(pi_cls + d.p_off) + tt;
     double2 p[NKMAX], u[NKMAX];
 #pragma unroll
@@ -322,117 +366,157 @@ __device__ __forceinline__ void tile_batch(const TileDesc &d, const double *__re
         p[k] = k < nk ? pcls[k * tthreads] : make_double2(0.0, 0.0);
         u[k] = make_double2(0.0, 0.0);
     }
-    const double *wb = w + d.row0;
-    const double2 *vt = reinterpret_cast<const double2 *>(v + d.v_off) + tt;
-    const int row_d2 = c_pad >> 1;
-    int parity = 0;
-    for (int r0 = team; r0 < d.n_rows; r0 += n_teams * RU) {
-        double2 x[RU][NKMAX];
-        double dot[RU], wr[RU];
+    const double *wb = w + d.row0 + it.r0;
+    int q = 0;
+    for (int r = 0; r < n_rows; ++r) {
+        const double wr = wb[r];
+        mbar_wait_u32(bars_u32 + 8u * q, (phase_bits >> q) & 1u);
+        phase_bits ^= 1u << q;
+        const uint32_t src = ring_u32 + (uint32_t)q * row_bytes + (uint32_t)tt * 16u;
+        double2 x[NKMAX];
+        double dx = 0.0, dy = 0.0;
 #pragma unroll
-        for (int g = 0; g < RU; ++g) {
-            const int r = r0 + g * n_teams;
-            const bool have = r < d.n_rows;
-            wr[g] = have ? wb[r] : 0.0;
-#pragma unroll
-            for (int k = 0; k < NKMAX; ++k)
-                x[g][k] = (have && k < nk) ? __ldg(vt + (size_t)r * row_d2 + k * tthreads)
-                                           : make_double2(0.0, 0.0);
+        for (int k = 0; k < NKMAX; ++k) {
+            x[k] = k < nk ? lds_v2_f64(src + (uint32_t)(k * tthreads) * 16u) : make_double2(0.0, 0.0);
+            dx = fma(x[k].x, p[k].x, dx);
+            dy = fma(x[k].y, p[k].y, dy);
         }
-#pragma unroll
-        for (int g = 0; g < RU; ++g) {
-            double dx = 0.0, dy = 0.0;
-#pragma unroll
-            for (int k = 0; k < NKMAX; ++k) {
-                dx = fma(x[g][k].x, p[k].x, dx);
-                dy = fma(x[g][k].y, p[k].y, dy);
-            }
-            dot[g] = dx + dy;
-        }
-#pragma unroll
-        for (int g = 0; g < RU; ++g) dot[g] = warp_sum(dot[g]);
+        double dot = warp_sum(dx + dy);
         if (tw > 1) {
-            // warp totals -> red[parity][g][warp]; after the team barrier every thread adds the
-            // tw totals of its team in warp order (lanes < tw fetch, butterfly, broadcast)
-            if (lane == 0) {
-#pragma unroll
-                for (int g = 0; g < RU; ++g) red[(parity * RU + g) * kTileWarps + warp] = dot[g];
-            }
+            // warp totals -> red[parity][warp]; after the team barrier every thread adds the tw
+            // totals of its team in warp order (lanes < tw fetch, butterfly, broadcast)
+            if (lane == 0) red[parity * kTileWarps + warp] = dot;
             team_barrier(1 + team, tthreads);
-#pragma unroll
-            for (int g = 0; g < RU; ++g) {
-                double t = lane < tw ? red[(parity * RU + g) * kTileWarps + team * tw + lane] : 0.0;
-                for (int off = tw >> 1; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-                dot[g] = __shfl_sync(0xffffffffu, t, 0);
-            }
+            double t = lane < tw ? red[parity * kTileWarps + team * tw + lane] : 0.0;
+            for (int off = tw >> 1; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+            dot = __shfl_sync(0xffffffffu, t, 0);
             parity ^= 1;
         }
-#pragma unroll
-        for (int g = 0; g < RU; ++g) {
-            double coef = 0.0;
-            if (wr[g] != 0.0) {
-                coef = wr[g] / dot[g];
-                bad |= (dot[g] == 0.0);
-            }
-#pragma unroll
-            for (int k = 0; k < NKMAX; ++k) {
-                u[k].x = fma(coef, x[g][k].x, u[k].x);
-                u[k].y = fma(coef, x[g][k].y, u[k].y);
-            }
+        // every thread of the team holds its cells of the row in registers: refill the slot
+        if (producer && r + ns < n_rows) {
+            mbar_expect_tx_u32(bars_u32 + 8u * q, row_bytes);
+            bulk_load_u32(ring_u32 + (uint32_t)q * row_bytes, tile + (size_t)(r + ns) * d.c_pad,
+                          row_bytes, bars_u32 + 8u * q);
         }
+        double coef = 0.0;
+        if (wr != 0.0) {
+            coef = wr / dot;
+            bad |= (dot == 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < NKMAX; ++k) {
+            u[k].x = fma(coef, x[k].x, u[k].x);
+            u[k].y = fma(coef, x[k].y, u[k].y);
+        }
+        if (++q == ns) q = 0;
     }
-    // class sums of the teams, added in team order
-    double2 *us2 = reinterpret_cast<double2 *>(us);
-    __syncthreads();   // `us` of the previous batch has been read
+    if (d.ng == 1) {        // the item is the whole batch
+        double2 *uo = reinterpret_cast<double2 *>(u_sum + d.p_off) + tt;
+#pragma unroll
+        for (int k = 0; k < NKMAX; ++k)
+            if (k < nk) uo[k * tthreads] = u[k];
+        return;
+    }
+    // Store this item's share; the item of the batch that finishes last adds the ng shares in
+    // item order (so the sum does not depend on which one that is) into U_b.  `done` counts
+    // the finished items of the batch and is put back to zero by the last one.
+    double2 *uo = reinterpret_cast<double2 *>(u_out + d.u_off + (size_t)it.g * d.c_pad) + tt;
 #pragma unroll
     for (int k = 0; k < NKMAX; ++k)
-        if (k < nk) us2[team * row_d2 + tt + k * tthreads] = u[k];
-    __syncthreads();
-    double2 *uo = reinterpret_cast<double2 *>(u_out + d.p_off);
-    for (int c = tid; c < row_d2; c += kTileThreads) {
-        double2 t = us2[c];
-        for (int q = 1; q < n_teams; ++q) {
-            const double2 o = us2[q * row_d2 + c];
-            t.x += o.x;
-            t.y += o.y;
-        }
-        uo[c] = t;
+        if (k < nk) uo[k * tthreads] = u[k];
+    __threadfence();
+    int last = 0;
+    if (tw > 1) {
+        team_barrier(1 + team, tthreads);              // every warp's stores are fenced
+        if (tt == 0) ired[team] = atomicAdd(done + it.batch, 1) == d.ng - 1;
+        team_barrier(1 + team, tthreads);
+        last = ired[team];
+    } else {
+        if (lane == 0) last = atomicAdd(done + it.batch, 1) == d.ng - 1;
+        last = __shfl_sync(0xffffffffu, last, 0);
     }
+    if (!last) return;
+    __threadfence();
+    const double2 *sh = reinterpret_cast<const double2 *>(u_out + d.u_off) + tt;
+    double2 *us = reinterpret_cast<double2 *>(u_sum + d.p_off) + tt;
+    const int row_d2 = d.c_pad >> 1;
+#pragma unroll
+    for (int k = 0; k < NKMAX; ++k) {
+        if (k < nk) {
+            double2 acc = __ldcg(sh + k * tthreads);
+            for (int g = 1; g < d.ng; ++g) {
+                const double2 o = __ldcg(sh + (size_t)g * row_d2 + k * tthreads);
+                acc.x += o.x;
+                acc.y += o.y;
+            }
+            us[k * tthreads] = acc;
+        }
+    }
+    if (tt == 0) done[it.batch] = 0;
 }
 
-__global__ void __launch_bounds__(kTileThreads)
-tile_pass_kernel(const TileDesc *__restrict__ desc, const int *__restrict__ order, int n_work,
+__global__ void __launch_bounds__(kTileThreads, 1)
+tile_pass_kernel(const TileDesc *__restrict__ desc, const TileItem *__restrict__ items,
+                 const TilePlan *__restrict__ plan, const int *__restrict__ slot_ptr,
+                 const int *__restrict__ slot_items,
                  const double *__restrict__ v, const double *__restrict__ pi_cls,
                  const double *__restrict__ w, EmState *__restrict__ st,
-                 double *__restrict__ u_out) {
-    extern __shared__ __align__(16) unsigned char tile_smem[];
-    double *us = reinterpret_cast<double *>(tile_smem);                  // [kTileUsDoubles]
-    double *red = us + kTileUsDoubles;                                   // [2][4][16]
-    pdl_wait();               // Pi of this iteration is complete
+                 double *__restrict__ u_out, double *__restrict__ u_sum, int *__restrict__ done) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tile_smem + kTileRingBytes);   // [16][16]
+    double *red = reinterpret_cast<double *>(bars + kTileWarps * kTileMaxStages);  // [2][16]
+    int *ired = reinterpret_cast<int *>(red + 2 * kTileWarps);                     // [16]
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const TilePlan pl = plan[blockIdx.x];
+    const int tw = pl.tw;
+    const int team = warp / tw, tt = tid - team * 32 * tw;
+    const int ring_bytes = kTileRingBytes / (kTileWarps / tw);        // this team's share
+    const uint32_t ring_u32 = smem_u32(tile_smem) + (uint32_t)(team * ring_bytes);
+    const uint32_t bars_u32 = smem_u32(bars) + (uint32_t)(team * kTileMaxStages) * 8u;
+    if (tt == 0) {
+        for (int q = 0; q < kTileMaxStages; ++q) mbar_init(bars + team * kTileMaxStages + q, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    pdl_wait();               // the class sums of this iteration are complete
     pdl_launch_dependents();
     if (st->done) return;
-    int bad = 0;
-    for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-        const TileDesc d = desc[order[wi]];
-        if (d.nk <= 2) tile_batch<2, 4>(d, v, pi_cls, w, u_out, us, red, bad);
-        else if (d.nk <= 4) tile_batch<4, 2>(d, v, pi_cls, w, u_out, us, red, bad);
-        else tile_batch<8, 1>(d, v, pi_cls, w, u_out, us, red, bad);
+    int bad = 0, parity = 0;
+    uint32_t phase_bits = 0;
+    const int slot = pl.slot0 + team;
+    for (int i = slot_ptr[slot]; i < slot_ptr[slot + 1]; ++i) {
+        const TileItem it = items[slot_items[i]];
+        const TileDesc d = desc[it.batch];
+        if (d.nk <= 2)
+            tile_batch<2>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
+                          ring_bytes, bars_u32, red, ired, phase_bits, parity, bad);
+        else if (d.nk <= 4)
+            tile_batch<4>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
+                          ring_bytes, bars_u32, red, ired, phase_bits, parity, bad);
+        else
+            tile_batch<8>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
+                          ring_bytes, bars_u32, red, ired, phase_bits, parity, bad);
+        // the next batch may prime the ring at once: the team barrier of the last row (tw > 1)
+        // or the warp's own program order (tw == 1) came after every read of the ring
     }
-    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicAdd(&st->bad, 1);
+    if (__any_sync(0xffffffffu, bad) && (tid & 31) == 0) atomicAdd(&st->bad, 1);
 }
 
-// T_j = sum over batches of U_b[cmap_b[j]], batches in ascending order; the batches are
-// split into gridDim.y contiguous ranges whose partial sums the tail kernel adds in range
-// order (its `partials` input).  One thread per column.
-__global__ void __launch_bounds__(256)
+// T_j = sum over batches of U_b[cmap_b[j]], batches in ascending order; the batches are split
+// into gridDim.y contiguous ranges whose partial sums the tail kernel adds in range order (its
+// `partials` input).  One thread per column, eight batches in flight per thread.
+constexpr int kGatherThreads = 256;
+constexpr int kGatherUnroll = 8;
+
+__global__ void __launch_bounds__(kGatherThreads)
 tile_gather_kernel(const unsigned short *__restrict__ cmap, int hs, int n_cols, int64_t ld,
-                   const TileDesc *__restrict__ desc, int n_batches,
-                   const double *__restrict__ u_cls, const EmState *__restrict__ st,
+                   const int64_t *__restrict__ p_off, int n_batches,
+                   const double *__restrict__ u_sum, const EmState *__restrict__ st,
                    double *__restrict__ partials) {
     pdl_wait();
     pdl_launch_dependents();
     if (st->done) return;
-    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int j = blockIdx.x * kGatherThreads + threadIdx.x;
     if (j >= ld) return;
     const int part = blockIdx.y, n_part = gridDim.y;
     const int b0 = (int)((int64_t)n_batches * part / n_part);
@@ -440,15 +524,15 @@ tile_gather_kernel(const unsigned short *__restrict__ cmap, int hs, int n_cols, 
     double t = 0.0;
     if (j < n_cols) {
         int b = b0;
-        for (; b + 4 <= b1; b += 4) {
-            double x[4];
+        for (; b + kGatherUnroll <= b1; b += kGatherUnroll) {
+            double x[kGatherUnroll];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                x[q] = u_cls[desc[b + q].p_off + cmap[(size_t)(b + q) * hs + j]];
+            for (int q = 0; q < kGatherUnroll; ++q)
+                x[q] = u_sum[p_off[b + q] + cmap[(size_t)(b + q) * hs + j]];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) t += x[q];
+            for (int q = 0; q < kGatherUnroll; ++q) t += x[q];
         }
-        for (; b < b1; ++b) t += u_cls[desc[b].p_off + cmap[(size_t)b * hs + j]];
+        for (; b < b1; ++b) t += u_sum[p_off[b] + cmap[(size_t)b * hs + j]];
     }
     partials[(size_t)part * ld + j] = t;
 }

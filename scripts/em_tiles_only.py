@@ -39,6 +39,9 @@ def main():
     check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nb), ctypes.byref(nd)))
     print("EM %d x %d: %.4f ms per iteration, pass %.4f ms, %.3f GB per pass"
           % (n, h, el.value / iters, ps.value / iters, nb.value / 1e9))
+    ms = (ctypes.c_float * 4)()
+    check(lib.mxb_em_profile(sess, iters, ms))
+    print("per kernel (ms): class sums %.4f, pass %.4f, gather %.4f, tail %.4f" % tuple(ms))
     lib.mxb_em_destroy(sess)
 
 

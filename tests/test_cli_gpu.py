@@ -47,7 +47,7 @@ def _strip_argv_line(stderr):
     naming output files."""
     keep = []
     for line in stderr.splitlines():
-        if line.startswith("mixemt ") or "Wrote " in line or line.startswith("Read reference"):
+        if line.startswith("mixemt ") or "Wrote " in line or line.startswith("Read "):
             continue
         keep.append(line)
     return "\n".join(keep)
