@@ -7,26 +7,35 @@
 A *step* is one EM iteration (E-step + M-step + convergence test) over the
 resident read-signature x haplotype matrix of BASELINE.json config 2: a 3-way
 synthetic mixture (H1 50% / L3e 30% / U5a1 20%), 1M fragments of 300 bp reduced
-to unique signatures, against all 5408 Phylotree Build 17 haplotypes.  Under
+to unique signatures in the reference's row order (string-sorted,
+preprocess.py:219), against all 5408 Phylotree Build 17 haplotypes.  Under
 torchrun every rank builds its own 1M-fragment shard (weak scaling) and the H
 column sums are exchanged once per iteration by peer stores inside the tail
 kernel (ncclAllReduce when peer access is missing).
 
 One JSON line is printed by rank 0:
   value     matrix cells per second through EM iterations, inputs resident in HBM
-  e2e       same metric through the drop-in call mixemt_b200.run_em(host ndarray,
-            weights, args) run to convergence with the reference's default
-            options: host->device copy of the matrix, all iterations, read-matrix
-            materialisation and the device->host copy of the N x H result inside
-            the timed region (after one short untimed call)
-  roofline  the fused E/M pass against the measured HBM copy bandwidth, on the bytes the
-            pass reads (dictionary-coded rows); fp64_rows_equivalent_GBs is
-            the same time against the 8 bytes per cell of the plain fp64 layout
-  restart_sweep  4 restarts x 100 iterations per GPU (BASELINE.json config 4), two restarts
-            per read of the matrix and one at a time; under torchrun the matrix is
-            replicated and 4 N restarts are dealt over the N GPUs
+  e2e       same metric through the drop-in call mixemt_b200.run_em(pageable host
+            ndarray, weights, args) run to convergence with the reference's default
+            options: host->device copy of the matrix, class tiles, all iterations,
+            read-matrix kernel and the device->host copy of the N x H result inside
+            the timed region (after one short untimed call); e2e.breakdown_ms
+  roofline  the dominant kernel against the measured HBM copy bandwidth, two readings
+            (frac_contract: 8 B per matrix cell; frac_traffic: the bytes of
+            the kernel's own data layout), roofline.per_kernel for every kernel of an
+            iteration, the fp64-row pass of the same matrix and the build kernel
+  restart_sweep  BASELINE.json config 4: --restarts (100) random-init runs to
+            convergence on the config-2 matrix; under torchrun the matrix is
+            replicated and the restarts are dealt over the GPUs
+  parity    (N > 1) the multi-GPU path -- class tiles per shard + peer exchange --
+            against the CPU oracle on the whole matrix
+  strong_scaling  (N > 1) one config-2 matrix row-split over the N GPUs
+  config3   (N = 8, or --config3) BASELINE.json config 3: 5-way mixture, 1.25 M
+            signature rows per GPU (10 M rows x 5408 on eight)
   cpu_baseline  the CPU oracle port (C + OpenMP, all host threads) on a row sample
---rows N replaces the workload by N undeduplicated rows per GPU (config-3 shards).
+--impl reference times the UNMODIFIED reference's em_step (staged copy oracle/_ref,
+see oracle/stage_ref.py) on one core.  --rows N replaces the workload by N
+undeduplicated rows per GPU (config-3 shard sizes).
 """
 import argparse
 import json

@@ -77,9 +77,10 @@ struct mxb_em {
     // Class tiles (em_tiles.cuh): when `tiled` the pass reads `tile_v` instead of `lin`.
     bool tiled = false;
     int n_batches = 0, tile_hs = 0, tile_parts = 0, tile_grid = 0;
-    unsigned char *tile_block = nullptr;   // [perm][cmap][ckey][desc]
+    unsigned char *tile_block = nullptr;   // [perm][cmap][cword][desc]
     unsigned char *tile_vecs = nullptr;    // [pi_cls][u_sum][u shares][plan][slot_ptr][slot_items][items][p_off][done]
-    unsigned short *tile_perm = nullptr, *tile_cmap = nullptr, *tile_ckey = nullptr;
+    unsigned short *tile_perm = nullptr, *tile_cmap = nullptr;
+    unsigned int *tile_cword = nullptr;
     TileDesc *tile_desc = nullptr;
     TileItem *tile_items = nullptr;
     TilePlan *tile_plan = nullptr;
@@ -183,7 +184,7 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
             MXB_CUDA(launch_pdl(pi_fn, dim3(std::min(em->n_batches, 2 * ctx->num_sms)),
                                 dim3(kTileThreads), (size_t)em->ld * sizeof(double), s,
                                 (const unsigned short *)em->tile_perm,
-                                (const unsigned short *)em->tile_ckey, em->tile_hs,
+                                (const unsigned int *)em->tile_cword, em->tile_hs,
                                 (int)em->n_cols, (const TileDesc *)em->tile_desc, em->n_batches,
                                 (const double *)em->pi[0], (const double *)em->pi[1],
                                 (const EmState *)em->state, em->tile_pi));
@@ -330,7 +331,7 @@ __global__ void em_reset_state_kernel(EmState *st, long long max_iter, double to
 template <int ITEMS>
 static cudaError_t launch_tile_class(mxb_ctx *ctx, int grid, const unsigned long long *hash, int hs,
                                      int n_cols, int n_batches, unsigned short *perm,
-                                     unsigned short *ckey, unsigned short *cmap,
+                                     unsigned int *cword, unsigned short *cmap,
                                      unsigned short *rep, int *n_cls) {
     using Sort = cub::BlockRadixSort<unsigned long long, kTileThreads, ITEMS, unsigned short>;
     using Scan = cub::BlockScan<int, kTileThreads>;
@@ -339,7 +340,7 @@ static cudaError_t launch_tile_class(mxb_ctx *ctx, int grid, const unsigned long
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     tile_class_kernel<ITEMS><<<grid, kTileThreads, smem, ctx->stream>>>(hash, hs, n_cols, n_batches,
-                                                                        perm, ckey, cmap, rep, n_cls);
+                                                                        perm, cword, cmap, rep, n_cls);
     return cudaGetLastError();
 }
 
@@ -382,15 +383,16 @@ static int em_pack_tiles(mxb_em *em) {
     // persistent: [perm][cmap][desc]; the class vectors and the plan of the pass follow in a
     // second block once the class counts are known
     const size_t b_desc = up((size_t)nb * sizeof(TileDesc));
-    const size_t head_bytes = 3 * b_map + b_desc;
+    const size_t b_cword = up((size_t)nb * kTileThreads * sizeof(unsigned int));
+    const size_t head_bytes = 2 * b_map + b_cword + b_desc;
     unsigned char *maps = nullptr;
     e = dev_alloc(ctx, (void **)&maps, head_bytes);
     if (e != cudaSuccess) return give_up(false, "maps");
     block = maps;
     unsigned short *perm = reinterpret_cast<unsigned short *>(maps);
     unsigned short *cmap = reinterpret_cast<unsigned short *>(maps + b_map);
-    unsigned short *ckey = reinterpret_cast<unsigned short *>(maps + 2 * b_map);
-    TileDesc *d_desc = reinterpret_cast<TileDesc *>(maps + 3 * b_map);
+    unsigned int *cword = reinterpret_cast<unsigned int *>(maps + 2 * b_map);
+    TileDesc *d_desc = reinterpret_cast<TileDesc *>(maps + 2 * b_map + b_cword);
 
     const int grid = std::min(nb, ctx->num_sms * 2);
     tile_hash_kernel<<<std::min(nb, ctx->num_sms * 4), kTileThreads, 0, ctx->stream>>>(
@@ -398,10 +400,10 @@ static int em_pack_tiles(mxb_em *em) {
     e = cudaGetLastError();
     if (e == cudaSuccess) {
         const int items = (int)ceil_div(h, kTileThreads);
-        if (items <= 4) e = launch_tile_class<4>(ctx, grid, hash, hs, (int)h, nb, perm, ckey, cmap, rep, d_ncls);
-        else if (items <= 8) e = launch_tile_class<8>(ctx, grid, hash, hs, (int)h, nb, perm, ckey, cmap, rep, d_ncls);
-        else if (items <= 12) e = launch_tile_class<12>(ctx, grid, hash, hs, (int)h, nb, perm, ckey, cmap, rep, d_ncls);
-        else e = launch_tile_class<16>(ctx, grid, hash, hs, (int)h, nb, perm, ckey, cmap, rep, d_ncls);
+        if (items <= 4) e = launch_tile_class<4>(ctx, grid, hash, hs, (int)h, nb, perm, cword, cmap, rep, d_ncls);
+        else if (items <= 8) e = launch_tile_class<8>(ctx, grid, hash, hs, (int)h, nb, perm, cword, cmap, rep, d_ncls);
+        else if (items <= 12) e = launch_tile_class<12>(ctx, grid, hash, hs, (int)h, nb, perm, cword, cmap, rep, d_ncls);
+        else e = launch_tile_class<16>(ctx, grid, hash, hs, (int)h, nb, perm, cword, cmap, rep, d_ncls);
     }
     ctx->launches += 2;
     std::vector<int> ncls((size_t)nb);
@@ -604,7 +606,7 @@ static int em_pack_tiles(mxb_em *em) {
     em->tile_vecs = vecs;
     em->tile_perm = perm;
     em->tile_cmap = cmap;
-    em->tile_ckey = ckey;
+    em->tile_cword = cword;
     em->tile_desc = d_desc;
     em->tile_plan = d_plan;
     em->tile_items = d_items;
@@ -777,6 +779,48 @@ int mxb_em_pass_bytes(const mxb_em *em, int64_t *bytes_per_pass, int64_t *n_dens
     return MXB_OK;
 }
 
+// One iteration in log space on the session's current proportions (see em_logspace_*):
+// called when the tail flagged done = kDoneNeedsLogStep.  Leaves the control block as a normal
+// tail would (iters + 1, convergence / max_iter decision, buffers swapped).
+static int em_logspace_step(mxb_em *em, const EmState &seen) {
+    mxb_ctx *ctx = em->ctx;
+    cudaStream_t s = ctx->stream;
+    const int64_t n = em->n_rows, h = em->n_cols;
+    constexpr int kRowBlocks = 64;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_lse = up((size_t)n * sizeof(double)), b_col = up((size_t)h * sizeof(double));
+    const size_t b_part = up((size_t)kRowBlocks * h * sizeof(double));
+    unsigned char *tmp = nullptr;
+    if (dev_alloc(ctx, (void **)&tmp, b_lse + 2 * b_col + b_part) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("EM log-space step: out of device memory");
+        return MXB_ERR_NOMEM;
+    }
+    double *lse = (double *)tmp, *colmax = (double *)(tmp + b_lse);
+    double *colsum = (double *)(tmp + b_lse + b_col), *part = (double *)(tmp + b_lse + 2 * b_col);
+    const double *lnp = em->lnp[seen.cur];
+    const int col_blocks = (int)ceil_div(h, 256);
+    const int row_grid = (int)std::min<int64_t>(n, (int64_t)ctx->num_sms * 8);
+    em_logspace_rows_kernel<<<row_grid, 256, 0, s>>>(em->mat->data, n, h, lnp, lse);
+    em_logspace_cols_kernel<<<dim3(col_blocks, kRowBlocks), 256, 0, s>>>(
+        em->mat->data, n, h, lnp, lse, em->weights, nullptr, part);
+    em_logspace_colreduce_kernel<<<col_blocks, 256, 0, s>>>(part, kRowBlocks, h, 1, colmax);
+    em_logspace_cols_kernel<<<dim3(col_blocks, kRowBlocks), 256, 0, s>>>(
+        em->mat->data, n, h, lnp, lse, em->weights, colmax, part);
+    em_logspace_colreduce_kernel<<<col_blocks, 256, 0, s>>>(part, kRowBlocks, h, 0, colsum);
+    em_logspace_update_kernel<<<1, kUpdThreads, 0, s>>>(colmax, colsum, h, em->ld, em->lnp[0],
+                                                        em->lnp[1], em->pi[0], em->pi[1], em->state);
+    ctx->launches += 6;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    dev_free(ctx, tmp);
+    if (e != cudaSuccess) {
+        set_error("EM log-space step: %s", cudaGetErrorString(e));
+        return MXB_ERR_CUDA;
+    }
+    return MXB_OK;
+}
+
 int mxb_em_set_lnprops(mxb_em *em, const double *lnprops) {
     MXB_REQUIRE(em != nullptr && lnprops != nullptr, "NULL argument");
     mxb_ctx *ctx = em->ctx;
@@ -817,6 +861,7 @@ int mxb_em_iterate(mxb_em *em, int64_t max_iter, double tol, int64_t *iters_out,
     EmState fin;
     memset(&fin, 0, sizeof(fin));
     bool finished = false;
+    int64_t log_steps = 0;
     while (!finished) {
         if (enqueued < max_iter) {
             const int64_t n = std::min<int64_t>(kChunk, max_iter - enqueued);
@@ -834,7 +879,22 @@ int mxb_em_iterate(mxb_em *em, int64_t max_iter, double tol, int64_t *iters_out,
         if (must_wait) {
             MXB_CUDA(cudaEventSynchronize(em->poll_ev[wait_slot]));
             pending[wait_slot] = false;
-            if (em->host_state[wait_slot].done) {
+            if (em->host_state[wait_slot].done == kDoneNeedsLogStep) {
+                // everything queued behind the flagged iteration was a no-op: drain, redo
+                // that iteration in log space, go on from the state it leaves
+                MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+                pending[0] = pending[1] = false;
+                MXB_TRY(em_logspace_step(em, em->host_state[wait_slot]));
+                ++log_steps;
+                MXB_CUDA(cudaMemcpyAsync(&em->host_state[wait_slot], em->state, sizeof(EmState),
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+                MXB_CUDA(cudaStreamSynchronize(ctx->stream));
+                enqueued = em->host_state[wait_slot].iters;
+                if (em->host_state[wait_slot].done) {
+                    fin = em->host_state[wait_slot];
+                    finished = true;
+                }
+            } else if (em->host_state[wait_slot].done) {
                 fin = em->host_state[wait_slot];
                 finished = true;
             } else if (wait_slot == slot && enqueued >= max_iter) {

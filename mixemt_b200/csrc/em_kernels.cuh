@@ -16,8 +16,11 @@ namespace mxb {
 
 // Device-resident control block: lets every kernel of an iteration early-exit
 // once the run has converged, so iterations can be enqueued ahead of the host.
+constexpr int kDoneNeedsLogStep = 4;
+
 struct EmState {
-    int done;            // 0 running, 1 converged, 2 max_iter reached
+    int done;            // 0 running, 1 converged, 2 max_iter reached, 3 peer time-out,
+                         // 4 the current iteration must be redone in log space
     int cur;             // index of the current (input) proportions buffer
     int bad;             // rows whose mixture likelihood underflowed to 0
     int pad;
@@ -601,6 +604,10 @@ em_update_kernel(const double *__restrict__ tsum, int64_t n_cols, int64_t ld,
                  double *__restrict__ pi0, double *__restrict__ pi1,
                  EmState *__restrict__ st) {
     if (st->done) return;
+    if (st->bad) {               // a row's mixture likelihood underflowed: see em_logspace_*
+        if (threadIdx.x == 0) st->done = kDoneNeedsLogStep;
+        return;
+    }
     __shared__ double scratch[kUpdThreads / 32];
     const int cur = st->cur;
     const double *lnp_old = cur ? lnp1 : lnp0;
@@ -713,6 +720,15 @@ em_finish_kernel(const double *partials, int n_part, int64_t n_cols, int64_t ld,
         pi0 += slot * ld; pi1 += slot * ld;
     }
     if (st->done) return;  // same answer in every CTA: the block below is the only writer
+    if (!kP2P && st->bad) {
+        // A row's mixture likelihood underflowed in linear space: this iteration is redone in
+        // log space by the host (em_logspace_* kernels), the queued launches become no-ops.
+        // (st->bad was final before this launch began; the write below is seen by later
+        // launches only.)  Row-sharded runs keep reporting the condition as an error.
+        cooperative_groups::this_cluster().sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->done = kDoneNeedsLogStep;
+        return;
+    }
     __shared__ double wsum[2][kFinThreads / 32];
     __shared__ double slots[2][kFinCtas];
     __shared__ int s_timeout;
@@ -905,6 +921,108 @@ read_mix_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols,
 }
 
 // Cross-rank fold helpers: m <- exp(m - mx) ; m <- mx + log(m) - sub_log.
+// ---- one EM iteration in log space (rescue path) -------------------------------------
+// The linear-space pass needs s_i = sum_j L_ij pi_j > 0.  When every haplotype that still
+// has mass explains a row more than ~700 log units worse than the row's best one, s_i
+// underflows although the reference's log-space arithmetic (em.py:80-89, max-shifted
+// logsumexp) stays finite.  The iteration is then redone exactly as the reference states it:
+//   Z_ij = M_ij + ln pi_j - lse_i,  ln pi'_j = lse_i(Z_ij + ln w_i) - lse_j(...)
+// in three sweeps over M (row lse; column maxima; column sums).  Rare and slow by design.
+__global__ void __launch_bounds__(256)
+em_logspace_rows_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols,
+                        const double *__restrict__ lnp, double *__restrict__ lse) {
+    __shared__ double scratch[8];
+    for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const double *row = m + r * n_cols;
+        double mx = -INFINITY;
+        for (int64_t j = threadIdx.x; j < n_cols; j += 256) mx = fmax(mx, row[j] + lnp[j]);
+        mx = block_max<256>(mx, scratch);
+        double sum = 0.0;
+        if (mx > -INFINITY)
+            for (int64_t j = threadIdx.x; j < n_cols; j += 256) sum += exp(row[j] + lnp[j] - mx);
+        sum = block_sum<256>(sum, scratch);
+        if (threadIdx.x == 0) lse[r] = mx > -INFINITY ? mx + log(sum) : -INFINITY;
+    }
+}
+
+// partial column maxima / sums over a block of rows; thread = column, blockIdx.y = row block
+__global__ void __launch_bounds__(256)
+em_logspace_cols_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols,
+                        const double *__restrict__ lnp, const double *__restrict__ lse,
+                        const double *__restrict__ w, const double *__restrict__ colmax,
+                        double *__restrict__ part) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= n_cols) return;
+    const int64_t r0 = n_rows * blockIdx.y / gridDim.y, r1 = n_rows * (blockIdx.y + 1) / gridDim.y;
+    const double lp = lnp[j];
+    double acc = colmax ? 0.0 : -INFINITY;
+    const double cm = colmax ? colmax[j] : 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const double wr = w[r];
+        if (wr == 0.0) continue;                       // scipy: a = -inf where b == 0
+        const double z = (m[r * n_cols + j] + lp) - lse[r];
+        if (colmax) { if (cm > -INFINITY) acc += wr * exp(z - cm); }
+        else acc = fmax(acc, z);
+    }
+    part[(size_t)blockIdx.y * n_cols + j] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+em_logspace_colreduce_kernel(const double *__restrict__ part, int n_part, int64_t n_cols,
+                             int is_max, double *__restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= n_cols) return;
+    double acc = is_max ? -INFINITY : 0.0;
+    for (int b = 0; b < n_part; ++b) {
+        const double v = part[(size_t)b * n_cols + j];
+        acc = is_max ? fmax(acc, v) : acc + v;
+    }
+    out[j] = acc;
+}
+
+// ln pi' = colmax + log(colsum) - logsumexp(.), convergence test, control block (one CTA)
+__global__ void __launch_bounds__(kUpdThreads)
+em_logspace_update_kernel(const double *__restrict__ colmax, const double *__restrict__ colsum,
+                          int64_t n_cols, int64_t ld, double *__restrict__ lnp0,
+                          double *__restrict__ lnp1, double *__restrict__ pi0,
+                          double *__restrict__ pi1, EmState *__restrict__ st) {
+    __shared__ double scratch[kUpdThreads / 32];
+    const int cur = st->cur;
+    const double *pi_old = cur ? pi1 : pi0;
+    double *lnp_new = cur ? lnp0 : lnp1;
+    double *pi_new = cur ? pi0 : pi1;
+    double mx = -INFINITY;
+    for (int64_t j = threadIdx.x; j < n_cols; j += kUpdThreads) {
+        const double v = colmax[j] > -INFINITY ? colmax[j] + log(colsum[j]) : -INFINITY;
+        lnp_new[j] = v;
+        mx = fmax(mx, v);
+    }
+    mx = block_max<kUpdThreads>(mx, scratch);
+    double sum = 0.0;
+    for (int64_t j = threadIdx.x; j < n_cols; j += kUpdThreads) sum += exp(lnp_new[j] - mx);
+    sum = block_sum<kUpdThreads>(sum, scratch);
+    const double norm = mx + log(sum);
+    double dl = 0.0;
+    for (int64_t j = threadIdx.x; j < ld; j += kUpdThreads) {
+        const bool in = j < n_cols;
+        const double v = in ? lnp_new[j] - norm : -INFINITY;
+        const double p = in ? exp(v) : 0.0;
+        lnp_new[j] = v;
+        pi_new[j] = p;
+        if (in) dl += fabs(p - pi_old[j]);
+    }
+    const double delta = block_sum<kUpdThreads>(dl, scratch);
+    if (threadIdx.x == 0) {
+        st->delta = delta;
+        st->bad = 0;
+        const long long it = st->iters + 1;
+        st->iters = it;
+        if (delta < st->tol) st->done = 1;
+        else if (it >= st->max_iter) st->done = 2;
+        else { st->done = 0; st->cur = 1 - cur; }
+    }
+}
+
 // Restart fan-out (mxb_matrix_fold_ranks): `own` is this rank's shard of its own fold of read
 // matrices, recv[q] the same rows as folded by rank q.  numpy.logaddexp in rank order
 // (em.py:156), then - log(n_multi) (em.py:161).

@@ -95,13 +95,13 @@ tile_hash_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols, i
 
 // Classes of one batch: sort (hash, column), number the runs of equal hashes.
 //   perm[b][e]  column at sorted position e (classes are contiguous, columns ascending inside)
-//   ckey[b][e]  class of that column (non-decreasing in e)
+//   cword[b][t] run structure of entries [ITEMS t, ITEMS (t + 1)) for the class-sum kernel
 //   cmap[b][j]  class of column j
 //   rep[b][c]   first (smallest) column of class c
 template <int ITEMS>
 __global__ void __launch_bounds__(kTileThreads)
 tile_class_kernel(const unsigned long long *__restrict__ hash, int hs, int n_cols, int n_batches,
-                  unsigned short *__restrict__ perm, unsigned short *__restrict__ ckey,
+                  unsigned short *__restrict__ perm, unsigned int *__restrict__ cword,
                   unsigned short *__restrict__ cmap, unsigned short *__restrict__ rep,
                   int *__restrict__ n_cls) {
     using Sort = cub::BlockRadixSort<unsigned long long, kTileThreads, ITEMS, unsigned short>;
@@ -110,6 +110,7 @@ tile_class_kernel(const unsigned long long *__restrict__ hash, int hs, int n_col
     typename Sort::TempStorage &sort_tmp = *reinterpret_cast<typename Sort::TempStorage *>(tile_smem);
     typename Scan::TempStorage &scan_tmp = *reinterpret_cast<typename Scan::TempStorage *>(tile_smem);
     __shared__ unsigned long long last_key[kTileThreads];
+    __shared__ int first_start[kTileThreads + 1];
     const int tid = threadIdx.x;
     for (int b = blockIdx.x; b < n_batches; b += gridDim.x) {
         unsigned long long keys[ITEMS];
@@ -136,6 +137,7 @@ tile_class_kernel(const unsigned long long *__restrict__ hash, int hs, int n_col
         int before = 0, total = 0;
         Scan(scan_tmp).ExclusiveSum(heads, before, total);
         int cls = before - 1;
+        unsigned int starts = 0;             // bit i: a class begins at entry i of this chunk
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const int e = tid * ITEMS + i;
@@ -143,12 +145,22 @@ tile_class_kernel(const unsigned long long *__restrict__ hash, int hs, int n_col
                 if (head[i]) {
                     ++cls;
                     rep[(size_t)b * hs + cls] = vals[i];
+                    starts |= 1u << i;
                 }
                 perm[(size_t)b * hs + e] = vals[i];
-                ckey[(size_t)b * hs + e] = (unsigned short)cls;
                 cmap[(size_t)b * hs + vals[i]] = (unsigned short)cls;
+            } else {
+                starts |= 1u << i;           // past the last column: every run has ended
             }
         }
+        // chunk word of the class-sum kernel: bits 0..ITEMS = run starts (bit ITEMS: at the first
+        // entry of the next chunk), bits 17.. = class of the chunk's first entry
+        first_start[tid] = (int)(starts & 1u);
+        if (tid == 0) first_start[kTileThreads] = 1;
+        __syncthreads();
+        starts |= (unsigned int)first_start[tid + 1] << ITEMS;
+        const int first_cls = head[0] ? before : before - 1;
+        cword[(size_t)b * kTileThreads + tid] = starts | ((unsigned int)max(first_cls, 0) << 17);
         if (tid == 0) n_cls[b] = total;
         __syncthreads();   // temp storage and last_key are reused by the next batch
     }
@@ -212,14 +224,14 @@ __device__ __forceinline__ SegItem seg_shfl_up(const SegItem &v, int off) {
 
 template <int PER>
 __global__ void __launch_bounds__(kTileThreads)
-tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned short *__restrict__ ckey,
+tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned int *__restrict__ cword,
                int hs, int n_cols, const TileDesc *__restrict__ desc, int n_batches,
                const double *__restrict__ pi0, const double *__restrict__ pi1,
                const EmState *__restrict__ st, double *__restrict__ pi_cls) {
+    static_assert(PER % 4 == 0 && PER <= 16, "chunks are read as 8-byte words");
     extern __shared__ __align__(128) unsigned char tile_smem[];
     double *pi = reinterpret_cast<double *>(tile_smem);     // [n_cols]: the gathers below are
-    // random 8-byte reads; from L1 they cost a tag lookup per distinct line (the kernel was
-    // bound by exactly that), from shared memory a couple of bank wavefronts per warp
+    // random 8-byte reads, cheaper from shared memory than through L1 tags
     pdl_wait();
     pdl_launch_dependents();
     if (st->done) return;
@@ -231,44 +243,40 @@ tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned short *__
     for (int j = tid; j < n_cols; j += kTileThreads) pi[j] = pi_g[j];
     __syncthreads();
     const int e0 = min(n_cols, tid * PER), cnt = min(n_cols, e0 + PER) - e0;
+    const bool live = cnt > 0;
     for (int b = blockIdx.x; b < n_batches; b += gridDim.x) {
-        const unsigned short *pm = perm + (size_t)b * hs + e0;
-        const unsigned short *ck = ckey + (size_t)b * hs + e0;
         double *out = pi_cls + desc[b].p_off;
-        int key[PER + 1];
-        double pv[PER];
-        const int prev_key = (cnt > 0 && e0 > 0) ? ck[-1] : -1;
+        // the chunk's columns (PER 16-bit entries as 8-byte words) and its run structure
+        const uint2 *pm = reinterpret_cast<const uint2 *>(perm + (size_t)b * hs + (size_t)tid * PER);
+        uint2 words[PER / 4];
 #pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            const bool in = q < cnt;
-            key[q] = in ? ck[q] : -2;
-            pv[q] = in ? pi[pm[q]] : 0.0;
-        }
-        // class of the entry after the chunk (-2: none): tells whether the last run ends here
-        key[PER] = -2;
-        const int next_key = (cnt > 0 && e0 + cnt < n_cols) ? ck[cnt] : -2;
-        const bool live = cnt > 0;
-        const int f_head = live ? (key[0] != prev_key) : 1;
+        for (int i = 0; i < PER / 4; ++i) words[i] = live ? pm[i] : make_uint2(0u, 0u);
+        const unsigned int cw = cword[(size_t)b * kTileThreads + tid];
+        const unsigned int starts = cw & 0x1FFFFu;
+        int cls = (int)(cw >> 17);                  // class of the current run
+        const int f_head = live ? (int)(starts & 1u) : 1;
         double s = 0.0, head_sum = 0.0;
-        int started = f_head;            // a run has begun at or inside this chunk
-        int head_open = 1;               // the first run has not ended yet
-        int head_key = key[0];
+        int head_open = 1;                           // the chunk's first run has not ended yet
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
+            const unsigned int w = (q & 2) ? words[q >> 2].y : words[q >> 2].x;
+            const int col = q < cnt ? (int)((q & 1) ? (w >> 16) : (w & 0xFFFFu)) : 0;
+            const double v = pi[col];
+            const bool start = q > 0 && ((starts >> q) & 1u);
+            const bool ends = (starts >> (q + 1)) & 1u;
             if (q < cnt) {
-                const bool start = q == 0 ? true : key[q] != key[q - 1];
-                s = start ? pv[q] : s + pv[q];
-                const int after = q + 1 < cnt ? key[q + 1] : next_key;
-                const bool ends = after != key[q];
-                const bool interior_start = q > 0 && start;
-                started |= interior_start ? 1 : 0;
-                if (interior_start) head_open = 0;
+                cls += start ? 1 : 0;
+                s = (q == 0 || start) ? v : s + v;
+                if (start) head_open = 0;
                 // a run that ends here and did not come in from the previous thread is final
-                if (ends && (head_open == 0 || f_head)) out[key[q]] = s;
-                if (head_open && (ends || q + 1 == cnt)) head_sum = s;
+                if (ends && (!head_open || f_head)) out[cls] = s;
+                if (head_open && ends) head_sum = s;
                 if (ends) head_open = 0;
             }
         }
+        const int started = (starts & ((1u << PER) - 1u)) != 0;     // a run began in this chunk
+        const int head_cls = (int)(cw >> 17);
+        if (live && head_open) head_sum = s;          // one run fills the chunk and goes on
         // aggregate of the chunk: trailing-run sum, and whether a run began here
         SegItem agg;
         agg.flag = live ? started : 1;
@@ -301,10 +309,9 @@ tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned short *__
         else if (!exc.flag) exc.val += s_carry[warp];
         if (live && !f_head) {
             // the first run came in from the previous thread(s): it is final here if it ended
-            // inside the chunk or if nothing of its class follows the chunk
-            const bool single = !started;
-            const double total = exc.val + head_sum;
-            if (!single || next_key != head_key) out[head_key] = total;
+            // inside the chunk or at its very end
+            const bool ended = (starts >> 1) != 0;          // some later start bit, incl. bit PER
+            if (ended) out[head_cls] = exc.val + head_sum;
         }
     }
 }

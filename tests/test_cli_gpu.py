@@ -115,8 +115,12 @@ def test_cli_config1_against_reference_cpu_run():
         cli_sim.write_mixture_bam(bam, phy, refseq, cfg["mixture"], cfg["n_fragments"],
                                   frag_len=cfg["frag_len"], err=cfg["err"], seed=cfg["bam_seed"])
         prefix = os.path.join(tmp, "out")
+        import time
+        t0 = time.perf_counter()
         res = cli_sim.run_cli(cfg["argv"] + ["-o", prefix, "-t", prefix, "-b", prefix, bam],
                               gpu=True)
+        print("config-1 CLI run on the GPU core: %.1f s (the reference's CPU run of the same "
+              "command: %.0f s)" % (time.perf_counter() - t0, float(gold["seconds"])))
         files = cli_sim.read_outputs(prefix, res.contributors())
     assert res.rc == int(gold["rc"]) == 0
     assert res.stdout == str(gold["stdout"])

@@ -443,3 +443,31 @@ def test_config1_to_convergence_against_oracle(phylo17):
                                                [[i] for i in range(len(wts))], 2.0)
     assert {k: set(v) for k, v in dev_assign.items()} == want
     dmat.free()
+
+
+@pytest.mark.parametrize("h,layout", [(1100, "fp64"), (5408, "tiles")])
+def test_underflowing_rows_are_redone_in_log_space(h, layout):
+    """Rows whose mixture likelihood underflows in linear space (all the remaining mass sits
+    on haplotypes ~800 log units worse than the row's best one) used to abort the run with a
+    NumericRangeError; the reference's log-space arithmetic (em.py:80-89) stays finite.  The
+    flagged iteration is redone in log space on the device and the run continues; results
+    equal the oracle."""
+    rs = np.random.RandomState(5)
+    n = 300 if layout == "fp64" else 1280
+    if layout == "fp64":
+        mat = -rs.gamma(2.0, 3.0, size=(n, h))
+    else:   # column classes: blocks of 64 identical columns -> runs over class tiles
+        mat = np.repeat(-rs.gamma(2.0, 3.0, size=(n, h // 64 + 1)), 64, axis=1)[:, :h].copy()
+    mat[:, 0] = 0.0
+    mat[: n // 4, 1:] -= 800.0          # these rows only make sense under column 0 ...
+    init = np.full(h, 1.0)
+    init[0] = 1e-300                     # ... which starts with (almost) no mass
+    inits = np.log(init / init.sum()).reshape(1, h)
+    wts = rs.randint(1, 5, size=n).astype(np.float64)
+    a = make_args(max_iter=60, tolerance=1e-6)
+    dev = DeviceMatrix.from_host(get_context(), mat)
+    props, read_mix, info, _ = em.run_em_device(dev, wts, a, inits=inits)
+    o_props, o_mix, o_iters = oracle_c.run_em(mat, wts, inits, a.max_iter, a.tolerance)
+    assert info["iterations"] == list(o_iters)
+    assert np.abs(props - o_props).max() < 1e-9
+    assert close_mix(read_mix, o_mix, 1e-8)

@@ -17,6 +17,8 @@ def test_two_gpu_rows_and_restarts(exchange):
     if _lib.lib.mxb_device_count() < 2:
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ)
+    # torchrun pins OMP_NUM_THREADS to 1; the CPU oracle inside the check wants the cores
+    env["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 2) // 2))
     if exchange == "nccl":
         env["MXB_NO_P2P"] = "1"
     else:
