@@ -84,7 +84,7 @@ struct mxb_em {
     TileDesc *tile_desc = nullptr;
     TileItem *tile_items = nullptr;
     TilePlan *tile_plan = nullptr;
-    int *tile_slot_ptr = nullptr, *tile_slot_items = nullptr;
+    int *tile_class_ptr = nullptr, *tile_class_items = nullptr, *tile_next = nullptr;
     double *tile_pi = nullptr, *tile_u = nullptr, *tile_usum = nullptr;
     int64_t *tile_poff = nullptr;
     int *tile_done = nullptr;
@@ -187,14 +187,15 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
                                 (const unsigned int *)em->tile_cword, em->tile_hs,
                                 (int)em->n_cols, (const TileDesc *)em->tile_desc, em->n_batches,
                                 (const double *)em->pi[0], (const double *)em->pi[1],
-                                (const EmState *)em->state, em->tile_pi));
+                                (const EmState *)em->state, em->tile_pi, em->tile_next));
         }
         if (marks) MXB_CUDA(cudaEventRecord(marks[0], s));
         MXB_CUDA(launch_pdl(tile_pass_kernel, dim3(em->tile_grid), dim3(kTileThreads),
                             kTilePassSmem, s, (const TileDesc *)em->tile_desc,
                             (const TileItem *)em->tile_items,
-                            (const TilePlan *)em->tile_plan, (const int *)em->tile_slot_ptr,
-                            (const int *)em->tile_slot_items, (const double *)em->tile_v,
+                            (const TilePlan *)em->tile_plan, (const int *)em->tile_class_ptr,
+                            (const int *)em->tile_class_items, em->tile_next,
+                            (const double *)em->tile_v,
                             (const double *)em->tile_pi, (const double *)em->weights, em->state,
                             em->tile_u, em->tile_usum, em->tile_done));
         if (marks) MXB_CUDA(cudaEventRecord(marks[1], s));
@@ -430,6 +431,7 @@ static int em_pack_tiles(mxb_em *em) {
         // up to four work items of at least 16 rows: enough items to keep every team of every
         // SM busy (a CTA holds 16 / tw teams), shares of U_b added again by the gather kernel
         d.ng = (int)std::max<int64_t>(1, std::min<int64_t>(kTileItems, d.n_rows / 16));
+        static_assert(kTileRows <= 32 * kTileItems, "an item must not exceed 32 rows (tile_batch)");
         d.pad = 0;
         d.v_off = v_cells;
         d.p_off = p_cells;
@@ -447,12 +449,12 @@ static int em_pack_tiles(mxb_em *em) {
         }
     }
     const int n_items = (int)items.size();
-    // Static plan of the pass: every CTA works on batches of one team width, its 16 / tw teams
-    // on different batches.  CTAs are dealt to the widths in proportion to the work (a row
-    // costs a team about 40 + 10 nk issue slots per warp, a little more with the per-row
-    // barrier of wide teams), batches to team slots longest first onto the least loaded slot.
+    // Plan of the pass: every CTA works on items of one team width, its 16 / tw teams on
+    // different items.  CTAs are dealt to the widths in proportion to the work (a row costs a
+    // team about 40 + 10 nk issue slots per warp, a little more with the per-row barrier of
+    // wide teams); within a width the teams draw items longest first from a device queue.
     std::vector<TilePlan> plan;
-    std::vector<int> slot_ptr(1, 0), slot_items;   // items of every team slot
+    std::vector<int> slot_ptr(1, 0), slot_items;   // work items by width class, longest first
     {
         auto batch_cost = [&](int i) {     // of work item i
             const TileDesc &d = desc[(size_t)items[(size_t)i].batch];
@@ -493,27 +495,16 @@ static int em_pack_tiles(mxb_em *em) {
             if (best >= 0) { ++n_cta[best]; ++total; grew = true; }
         }
         for (int k = 0; k < 5; ++k) {
-            if (n_cta[k] == 0) continue;
-            const int teams = kTileWarps >> k, n_slots = n_cta[k] * teams;
-            std::vector<std::vector<int>> items((size_t)n_slots);
-            std::vector<double> load((size_t)n_slots, 0.0);
             std::vector<int> &list = of_width[k];
             std::stable_sort(list.begin(), list.end(),
                              [&](int a, int b) { return batch_cost(a) > batch_cost(b); });
-            for (int b : list) {
-                const int sl = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-                items[(size_t)sl].push_back(b);
-                load[(size_t)sl] += batch_cost(b);
-            }
+            for (int i : list) slot_items.push_back(i);
+            slot_ptr.push_back((int)slot_items.size());
             for (int c = 0; c < n_cta[k]; ++c) {
                 TilePlan pl;
                 pl.tw = 1 << k;
-                pl.slot0 = (int)slot_ptr.size() - 1;
+                pl.klass = k;
                 plan.push_back(pl);
-                for (int t = 0; t < teams; ++t) {
-                    for (int b : items[(size_t)(c * teams + t)]) slot_items.push_back(b);
-                    slot_ptr.push_back((int)slot_items.size());
-                }
             }
         }
     }
@@ -543,7 +534,7 @@ static int em_pack_tiles(mxb_em *em) {
     const size_t b_sptr = up(slot_ptr.size() * sizeof(int));
     const size_t b_sitems = up((size_t)n_items * sizeof(int));
     const size_t b_items = up((size_t)n_items * sizeof(TileItem));
-    const size_t b_poff = up((size_t)nb * sizeof(int64_t));
+    const size_t b_poff = up((size_t)nb * sizeof(int64_t)) + 256;   // + the pass's queue counters
     if (e == cudaSuccess)
         e = dev_alloc(ctx, (void **)&vecs, 2 * b_vec + b_u + b_plan + b_sptr + b_sitems + b_items +
                                             b_poff + b_int);
@@ -557,6 +548,7 @@ static int em_pack_tiles(mxb_em *em) {
     int *d_slot_items = reinterpret_cast<int *>(tail + b_plan + b_sptr);
     TileItem *d_items = reinterpret_cast<TileItem *>(tail + b_plan + b_sptr + b_sitems);
     int64_t *d_poff = reinterpret_cast<int64_t *>(tail + b_plan + b_sptr + b_sitems + b_items);
+    int *d_next = reinterpret_cast<int *>(tail + b_plan + b_sptr + b_sitems + b_items + b_poff - 256);
     int *d_done = reinterpret_cast<int *>(tail + b_plan + b_sptr + b_sitems + b_items + b_poff);
     std::vector<int64_t> poff((size_t)nb);
     for (int b = 0; b < nb; ++b) poff[(size_t)b] = desc[(size_t)b].p_off;
@@ -572,6 +564,7 @@ static int em_pack_tiles(mxb_em *em) {
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(d_poff, poff.data(), (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_done, 0, (size_t)nb * sizeof(int), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_next, 0, 256, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(vecs, 0, 2 * b_vec + b_u, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, (size_t)nb * sizeof(int), ctx->stream);
     if (e == cudaSuccess) {
@@ -613,8 +606,9 @@ static int em_pack_tiles(mxb_em *em) {
     em->tile_usum = u_sum;
     em->tile_poff = d_poff;
     em->tile_done = d_done;
-    em->tile_slot_ptr = d_slot_ptr;
-    em->tile_slot_items = d_slot_items;
+    em->tile_class_ptr = d_slot_ptr;
+    em->tile_class_items = d_slot_items;
+    em->tile_next = d_next;
     em->tile_pi = pi_cls;
     em->tile_u = u_cls;
     em->tile_v = v;

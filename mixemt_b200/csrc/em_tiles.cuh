@@ -44,6 +44,7 @@ constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kTileMaxNK = 8;        // double2 per thread and row
 constexpr int kTileMaxCols = 8192;   // widest matrix (the fast path's limit on ld)
 constexpr int kTileItems = 4;        // work items (row ranges) per batch, at most
+constexpr int kTileClasses = 5;      // team widths 1, 2, 4, 8, 16
 
 struct TileDesc {           // one batch
     int32_t row0, n_rows;
@@ -227,7 +228,8 @@ __global__ void __launch_bounds__(kTileThreads)
 tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned int *__restrict__ cword,
                int hs, int n_cols, const TileDesc *__restrict__ desc, int n_batches,
                const double *__restrict__ pi0, const double *__restrict__ pi1,
-               const EmState *__restrict__ st, double *__restrict__ pi_cls) {
+               const EmState *__restrict__ st, double *__restrict__ pi_cls,
+               int *__restrict__ next_item) {
     static_assert(PER % 4 == 0 && PER <= 16, "chunks are read as 8-byte words");
     extern __shared__ __align__(128) unsigned char tile_smem[];
     double *pi = reinterpret_cast<double *>(tile_smem);     // [n_cols]: the gathers below are
@@ -235,6 +237,7 @@ tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned int *__re
     pdl_wait();
     pdl_launch_dependents();
     if (st->done) return;
+    if (blockIdx.x == 0 && threadIdx.x < kTileClasses) next_item[threadIdx.x] = 0;  // the pass's queues
     const double *__restrict__ pi_g = st->cur ? pi1 : pi0;
     __shared__ int s_flag[kTileWarps];
     __shared__ double s_val[kTileWarps];
@@ -319,8 +322,9 @@ tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned int *__re
 // ---- the pass ------------------------------------------------------------------------------
 // A work item is a contiguous range of rows of one batch (a batch is cut into up to four), handled
 // by a *team* of `tw` warps (tw = 1 for at most 512 classes -- the bulk --, 2, 4, 8 or 16 for the
-// wider ones); the 16 / tw teams of a CTA work on different items independently, CTAs and teams
-// are handed their items by a static, cost-balanced plan made when the tiles are built (em.cu).  Thread tt of a team owns the double2 chunks tt + 32 tw k (k < nk) of the
+// wider ones); the 16 / tw teams of a CTA work on different items independently.  Every CTA is
+// given a width when the tiles are built (CTAs in proportion to the work of each width, em.cu);
+// its teams draw items of that width, longest first, from a device-wide queue.  Thread tt of a team owns the double2 chunks tt + 32 tw k (k < nk) of the
 // class vectors: Pi_b and the item's share of U_b live in registers for the whole item, the
 // share is stored straight from registers, and the item of a batch that finishes last adds
 // the shares in item order into U_b -- no block-level synchronisation anywhere.
@@ -335,7 +339,7 @@ constexpr size_t kTilePassSmem = kTileRingBytes + kTileWarps * kTileMaxStages * 
 
 struct TilePlan {          // one per CTA
     int32_t tw;            // team width of this CTA
-    int32_t slot0;         // first team slot (slot_ptr index) of this CTA's teams
+    int32_t klass;         // log2(tw): its teams take the work items of this width class
 };
 
 __device__ __forceinline__ void team_barrier(int id, int threads) {
@@ -373,10 +377,12 @@ __device__ __forceinline__ void tile_batch(const TileDesc &d, const TileItem &it
         p[k] = k < nk ? pcls[k * tthreads] : make_double2(0.0, 0.0);
         u[k] = make_double2(0.0, 0.0);
     }
-    const double *wb = w + d.row0 + it.r0;
+    // an item holds at most 32 rows (128-row batches, up to four items of at least 16 rows):
+    // lane l keeps the weight of row l, so the row loop has no global load of its own
+    const double w_lane = lane < n_rows ? w[d.row0 + it.r0 + lane] : 0.0;
     int q = 0;
     for (int r = 0; r < n_rows; ++r) {
-        const double wr = wb[r];
+        const double wr = __shfl_sync(0xffffffffu, w_lane, r);
         mbar_wait_u32(bars_u32 + 8u * q, (phase_bits >> q) & 1u);
         phase_bits ^= 1u << q;
         const uint32_t src = ring_u32 + (uint32_t)q * row_bytes + (uint32_t)tt * 16u;
@@ -464,8 +470,8 @@ __device__ __forceinline__ void tile_batch(const TileDesc &d, const TileItem &it
 
 __global__ void __launch_bounds__(kTileThreads, 1)
 tile_pass_kernel(const TileDesc *__restrict__ desc, const TileItem *__restrict__ items,
-                 const TilePlan *__restrict__ plan, const int *__restrict__ slot_ptr,
-                 const int *__restrict__ slot_items,
+                 const TilePlan *__restrict__ plan, const int *__restrict__ class_ptr,
+                 const int *__restrict__ class_items, int *__restrict__ next_item,
                  const double *__restrict__ v, const double *__restrict__ pi_cls,
                  const double *__restrict__ w, EmState *__restrict__ st,
                  double *__restrict__ u_out, double *__restrict__ u_sum, int *__restrict__ done) {
@@ -490,9 +496,25 @@ tile_pass_kernel(const TileDesc *__restrict__ desc, const TileItem *__restrict__
     if (st->done) return;
     int bad = 0, parity = 0;
     uint32_t phase_bits = 0;
-    const int slot = pl.slot0 + team;
-    for (int i = slot_ptr[slot]; i < slot_ptr[slot + 1]; ++i) {
-        const TileItem it = items[slot_items[i]];
+    // The teams of all CTAs of a width class draw their items from one list (longest first)
+    // through a counter that tile_pi_kernel put back to zero: which team handles an item does
+    // not change any result, so this costs no determinism and evens out the load.
+    const int k = pl.klass;
+    const int list0 = class_ptr[k], list1 = class_ptr[k + 1];
+    const int lane = tid & 31;
+    for (;;) {
+        int i = 0;
+        if (tw > 1) {
+            if (tt == 0) ired[team] = atomicAdd(next_item + k, 1);
+            team_barrier(1 + team, 32 * tw);
+            i = ired[team];
+            team_barrier(1 + team, 32 * tw);
+        } else {
+            if (lane == 0) i = atomicAdd(next_item + k, 1);
+            i = __shfl_sync(0xffffffffu, i, 0);
+        }
+        if (list0 + i >= list1) break;
+        const TileItem it = items[class_items[list0 + i]];
         const TileDesc d = desc[it.batch];
         if (d.nk <= 2)
             tile_batch<2>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,

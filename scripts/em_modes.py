@@ -20,8 +20,6 @@ from mixemt_b200.preprocess import HapVarBaseMatrix, build_matrix_from_csr  # no
 from mixemt_b200.runtime import get_context  # noqa: E402
 
 MODES = [("class tiles", {}), ("fp64 rows", {"MXB_EM_NO_PACK": "1"})]
-if os.environ.get("EM_MODES_CODED"):
-    MODES.insert(1, ("cell-coded rows", {"MXB_EM_NO_TILES": "1"}))
 
 
 def main():
@@ -37,8 +35,7 @@ def main():
     lnp0 = np.log(np.random.RandomState(1).dirichlet([1.0] * h))
     ref = None
     for name, env in MODES:
-        for k in ("MXB_EM_NO_PACK", "MXB_EM_NO_TILES"):
-            os.environ.pop(k, None)
+        os.environ.pop("MXB_EM_NO_PACK", None)
         os.environ.update(env)
         sess = ctypes.c_void_p()
         ctx.synchronize()

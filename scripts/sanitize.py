@@ -42,6 +42,22 @@ def main():
         props, read_mix, info, _ = em.run_em_device(dev, wts, a, inits=inits)
         assert np.isfinite(props).all() and np.isfinite(read_mix).all(), (n, h)
         dev.free()
+    # kernel 2 over class tiles: blocks of identical columns (narrow teams), a block of noise
+    # rows in the middle (all columns distinct: 16 warps per row), several work items per batch,
+    # and a row that underflows in linear space (log-space rescue step)
+    n, h = 420, 5408
+    mat = np.repeat(-rs.gamma(2.0, 3.0, size=(n, h // 64 + 1)), 64, axis=1)[:, :h].copy()
+    mat[130:170] -= rs.gamma(2.0, 1.0, size=(40, h))
+    mat[:, 0] = 0.0
+    mat[:8, 1:] -= 800.0
+    init = np.full(h, 1.0)
+    init[0] = 1e-300
+    dev = DeviceMatrix.from_host(ctx, mat)
+    a = make_args(n_multi=2, max_iter=6, tolerance=1e-9)
+    inits = np.log(np.stack([init / init.sum(), rs.dirichlet([1.0] * h)]))
+    props, read_mix, info, _ = em.run_em_device(dev, rs.randint(1, 9, size=n), a, inits=inits)
+    assert np.isfinite(props).all() and np.isfinite(read_mix).all()
+    dev.free()
     p, m = em.run_em(dmat, mix.weights, make_args(max_iter=10))
     # consumers
     votes, best = consumers.vote_count(m, mix.weights)
