@@ -331,11 +331,12 @@ tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned int *__re
 // The rows of the tile stream through a team-private shared-memory ring filled by 1-D bulk
 // async copies (cp.async.bulk + mbarrier complete_tx, one instruction per row, issued by the
 // team's first thread); a row costs a warp nk 16-byte shared loads, 4 nk DFMA, one shuffle
-// butterfly and a division (plus one named barrier per row for tw > 1).
+// butterfly and a division (plus one named barrier per row step for tw > 1); two rows are in
+// flight per team where the registers allow it (nk <= 4).
 constexpr int kTileRingBytes = 192 * 1024;     // all teams of a CTA together
 constexpr int kTileMaxStages = 16;             // ring slots of a team
 constexpr size_t kTilePassSmem = kTileRingBytes + kTileWarps * kTileMaxStages * sizeof(uint64_t) +
-                                 2 * kTileWarps * sizeof(double) + kTileWarps * sizeof(int) + 128;
+                                 4 * kTileWarps * sizeof(double) + kTileWarps * sizeof(int) + 128;
 
 struct TilePlan {          // one per CTA
     int32_t tw;            // team width of this CTA
@@ -346,7 +347,7 @@ __device__ __forceinline__ void team_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int NKMAX>
+template <int NKMAX, int RU>
 __device__ __forceinline__ void tile_batch(const TileDesc &d, const TileItem &it, int tw, int team, int tt,
                                            const double *__restrict__ v,
                                            const double *__restrict__ pi_cls,
@@ -381,47 +382,80 @@ __device__ __forceinline__ void tile_batch(const TileDesc &d, const TileItem &it
     // lane l keeps the weight of row l, so the row loop has no global load of its own
     const double w_lane = lane < n_rows ? w[d.row0 + it.r0 + lane] : 0.0;
     int q = 0;
-    for (int r = 0; r < n_rows; ++r) {
-        const double wr = __shfl_sync(0xffffffffu, w_lane, r);
-        mbar_wait_u32(bars_u32 + 8u * q, (phase_bits >> q) & 1u);
-        phase_bits ^= 1u << q;
-        const uint32_t src = ring_u32 + (uint32_t)q * row_bytes + (uint32_t)tt * 16u;
-        double2 x[NKMAX];
-        double dx = 0.0, dy = 0.0;
+    for (int r = 0; r < n_rows; r += RU) {
+        // RU rows per step: their dependency chains (shared loads -> dot product -> butterfly ->
+        // division -> column-sum update) overlap; the sums are formed in row order as before
+        double2 x[RU][NKMAX];
+        double dot[RU], wr[RU];
+        int qs[RU];
+        bool have[RU];
 #pragma unroll
-        for (int k = 0; k < NKMAX; ++k) {
-            x[k] = k < nk ? lds_v2_f64(src + (uint32_t)(k * tthreads) * 16u) : make_double2(0.0, 0.0);
-            dx = fma(x[k].x, p[k].x, dx);
-            dy = fma(x[k].y, p[k].y, dy);
+        for (int g = 0; g < RU; ++g) {
+            have[g] = r + g < n_rows;
+            wr[g] = have[g] ? __shfl_sync(0xffffffffu, w_lane, (r + g) & 31) : 0.0;
+            qs[g] = q;
+            if (have[g]) {
+                mbar_wait_u32(bars_u32 + 8u * q, (phase_bits >> q) & 1u);
+                phase_bits ^= 1u << q;
+                if (++q == ns) q = 0;
+            }
         }
-        double dot = warp_sum(dx + dy);
+#pragma unroll
+        for (int g = 0; g < RU; ++g) {
+            const uint32_t src = ring_u32 + (uint32_t)qs[g] * row_bytes + (uint32_t)tt * 16u;
+            double dx = 0.0, dy = 0.0;
+#pragma unroll
+            for (int k = 0; k < NKMAX; ++k) {
+                x[g][k] = (have[g] && k < nk) ? lds_v2_f64(src + (uint32_t)(k * tthreads) * 16u)
+                                              : make_double2(0.0, 0.0);
+                dx = fma(x[g][k].x, p[k].x, dx);
+                dy = fma(x[g][k].y, p[k].y, dy);
+            }
+            dot[g] = dx + dy;
+        }
+#pragma unroll
+        for (int g = 0; g < RU; ++g) dot[g] = warp_sum(dot[g]);
         if (tw > 1) {
-            // warp totals -> red[parity][warp]; after the team barrier every thread adds the tw
-            // totals of its team in warp order (lanes < tw fetch, butterfly, broadcast)
-            if (lane == 0) red[parity * kTileWarps + warp] = dot;
+            // warp totals -> red[parity][g][warp]; after the team barrier every thread adds the
+            // tw totals of its team in warp order (lanes < tw fetch, butterfly, broadcast)
+            if (lane == 0) {
+#pragma unroll
+                for (int g = 0; g < RU; ++g) red[(parity * RU + g) * kTileWarps + warp] = dot[g];
+            }
             team_barrier(1 + team, tthreads);
-            double t = lane < tw ? red[parity * kTileWarps + team * tw + lane] : 0.0;
-            for (int off = tw >> 1; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-            dot = __shfl_sync(0xffffffffu, t, 0);
+#pragma unroll
+            for (int g = 0; g < RU; ++g) {
+                double t = lane < tw ? red[(parity * RU + g) * kTileWarps + team * tw + lane] : 0.0;
+                for (int off = tw >> 1; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                dot[g] = __shfl_sync(0xffffffffu, t, 0);
+            }
             parity ^= 1;
         }
-        // every thread of the team holds its cells of the row in registers: refill the slot
-        if (producer && r + ns < n_rows) {
-            mbar_expect_tx_u32(bars_u32 + 8u * q, row_bytes);
-            bulk_load_u32(ring_u32 + (uint32_t)q * row_bytes, tile + (size_t)(r + ns) * d.c_pad,
-                          row_bytes, bars_u32 + 8u * q);
-        }
-        double coef = 0.0;
-        if (wr != 0.0) {
-            coef = wr / dot;
-            bad |= (dot == 0.0);
+        // every thread of the team holds its cells of these rows in registers: refill the slots
+        if (producer) {
+#pragma unroll
+            for (int g = 0; g < RU; ++g) {
+                if (have[g] && r + g + ns < n_rows) {
+                    mbar_expect_tx_u32(bars_u32 + 8u * qs[g], row_bytes);
+                    bulk_load_u32(ring_u32 + (uint32_t)qs[g] * row_bytes,
+                                  tile + (size_t)(r + g + ns) * d.c_pad, row_bytes,
+                                  bars_u32 + 8u * qs[g]);
+                }
+            }
         }
 #pragma unroll
-        for (int k = 0; k < NKMAX; ++k) {
-            u[k].x = fma(coef, x[k].x, u[k].x);
-            u[k].y = fma(coef, x[k].y, u[k].y);
+        for (int g = 0; g < RU; ++g) {
+            double coef = 0.0;
+            if (wr[g] != 0.0) {
+                coef = wr[g] / dot[g];
+                bad |= (dot[g] == 0.0);
+            }
+#pragma unroll
+            for (int k = 0; k < NKMAX; ++k) {
+                u[k].x = fma(coef, x[g][k].x, u[k].x);
+                u[k].y = fma(coef, x[g][k].y, u[k].y);
+            }
         }
-        if (++q == ns) q = 0;
     }
     if (d.ng == 1) {        // the item is the whole batch
         double2 *uo = reinterpret_cast<double2 *>(u_sum + d.p_off) + tt;
@@ -477,8 +511,8 @@ tile_pass_kernel(const TileDesc *__restrict__ desc, const TileItem *__restrict__
                  double *__restrict__ u_out, double *__restrict__ u_sum, int *__restrict__ done) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(tile_smem + kTileRingBytes);   // [16][16]
-    double *red = reinterpret_cast<double *>(bars + kTileWarps * kTileMaxStages);  // [2][16]
-    int *ired = reinterpret_cast<int *>(red + 2 * kTileWarps);                     // [16]
+    double *red = reinterpret_cast<double *>(bars + kTileWarps * kTileMaxStages);  // [2][2][16]
+    int *ired = reinterpret_cast<int *>(red + 4 * kTileWarps);                     // [16]
     const int tid = threadIdx.x, warp = tid >> 5;
     const TilePlan pl = plan[blockIdx.x];
     const int tw = pl.tw;
@@ -517,13 +551,13 @@ tile_pass_kernel(const TileDesc *__restrict__ desc, const TileItem *__restrict__
         const TileItem it = items[class_items[list0 + i]];
         const TileDesc d = desc[it.batch];
         if (d.nk <= 2)
-            tile_batch<2>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
+            tile_batch<2, 2>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
                           ring_bytes, bars_u32, red, ired, phase_bits, parity, bad);
         else if (d.nk <= 4)
-            tile_batch<4>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
+            tile_batch<4, 2>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
                           ring_bytes, bars_u32, red, ired, phase_bits, parity, bad);
         else
-            tile_batch<8>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
+            tile_batch<8, 1>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
                           ring_bytes, bars_u32, red, ired, phase_bits, parity, bad);
         // the next batch may prime the ring at once: the team barrier of the last row (tw > 1)
         // or the warp's own program order (tw == 1) came after every read of the ring

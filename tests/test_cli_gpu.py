@@ -96,6 +96,42 @@ def test_cli_identical_reports_and_assignments(tmp_path, with_consumers):
 
 @needs_ref
 @pytest.mark.gpu
+def test_cli_config5_options_identical(tmp_path):
+    """BASELINE.json config 5 through the CLI: --unstable filtering, --exclude_pos (which doubles
+    the mutation counts) and a custom --haps file, CPU reference against GPU core."""
+    from oracle import cli_sim
+    tmp = str(tmp_path)
+    phylotree, _, _ = refload.load()
+    csv = cli_sim.truncated_phylotree_csv(os.path.join(tmp, "tree.csv"), 400)
+    refseq = refload.read_fasta(refload.build17_paths()[1])
+    with open(csv) as handle:
+        phy = phylotree.Phylotree(handle, refseq=refseq, rm_unstable=True)
+    phy.ignore_sites("303-315,16180-16193")
+    haps = sorted(phy.hap_var)
+    base_a, base_b = haps[90], haps[280]
+    custom = os.path.join(tmp, "custom.tab")
+    with open(custom, "w") as handle:
+        handle.write("custom_hap1\t%s\n" % ",".join(list(phy.hap_var[base_a]) + ["G3010A", "A10005G"]))
+    phy.add_custom_hap("custom_hap1", list(phy.hap_var[base_a]) + ["G3010A", "A10005G"])
+    bam = os.path.join(tmp, "mix.bam")
+    cli_sim.write_mixture_bam(bam, phy, refseq, [("custom_hap1", 0.6), (base_b, 0.4)], 1500, seed=8)
+    out = {}
+    for arm, gpu in (("cpu", False), ("gpu", True)):
+        prefix = os.path.join(tmp, arm)
+        argv = ["-v", "--phy", csv, "-U", "-e", "303-315,16180-16193", "-H", custom, "-S", "9",
+                "-t", prefix, bam]
+        res = cli_sim.run_cli(argv, gpu=gpu)
+        assert res.rc == 0, res.stderr[-2000:]
+        out[arm] = (res, cli_sim.read_outputs(prefix, res.contributors()))
+    assert out["gpu"][0].stdout == out["cpu"][0].stdout
+    assert _strip_argv_line(out["gpu"][0].stderr) == _strip_argv_line(out["cpu"][0].stderr)
+    assert "custom_hap1" in out["cpu"][0].stdout
+    for name, text in out["cpu"][1].items():
+        assert out["gpu"][1]["gpu" + name[3:]] == text, name
+
+
+@needs_ref
+@pytest.mark.gpu
 def test_cli_config1_against_reference_cpu_run():
     """BASELINE.json config 1 (H1 70 % + L3e 30 %, 10 000 fragments, Build 17)
     through the unmodified CLI on the GPU core, against what the reference's own

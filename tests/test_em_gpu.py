@@ -471,3 +471,49 @@ def test_underflowing_rows_are_redone_in_log_space(h, layout):
     assert info["iterations"] == list(o_iters)
     assert np.abs(props - o_props).max() < 1e-9
     assert close_mix(read_mix, o_mix, 1e-8)
+
+
+def test_pinned_result_pool_and_stage_times():
+    """Results of the drop-in calls can live in pooled pinned host memory (mxb_host_alloc):
+    same values as with pageable results, ordinary writable arrays, blocks reused after the
+    arrays die; the stage timer reports where a call spent its time (bench e2e.breakdown_ms)."""
+    import ctypes
+    import gc
+    import os
+    from mixemt_b200 import _lib
+    from mixemt_b200._lib import lib, check
+    rs = np.random.RandomState(2)
+    n, h = 4000, 1200
+    mat = -rs.gamma(2.0, 5.0, size=(n, h))
+    wts = rs.randint(1, 9, size=n)
+    a = make_args(max_iter=15, tolerance=1e-9)
+    np.random.seed(5)
+    p0, m0 = em.run_em(mat, wts, a)
+    assert _lib.pinned_mode() == "auto"
+    _lib.reserve_pinned(m0.nbytes, 1)
+    check(lib.mxb_stage_timing(1))
+    np.random.seed(5)
+    p1, m1 = em.run_em(mat, wts, a)
+    stage = (ctypes.c_double * 6)()
+    check(lib.mxb_stage_times(stage, 6))
+    check(lib.mxb_stage_timing(0))
+    assert np.array_equal(p0, p1) and np.array_equal(m0, m1)
+    assert m1.flags.writeable and m1.flags.c_contiguous
+    # the pooled block is handed out again once the array is gone
+    addr = m1.ctypes.data
+    del m1
+    gc.collect()
+    np.random.seed(5)
+    _, m2 = em.run_em(mat, wts, a)
+    assert m2.ctypes.data == addr and np.array_equal(m0, m2)
+    assert stage[0] > 0 and stage[2] > 0 and stage[4] > 0      # h2d, iterations, d2h
+    os.environ["MIXEMT_B200_PINNED"] = "0"
+    try:
+        np.random.seed(5)
+        _, m3 = em.run_em(mat, wts, a)
+    finally:
+        del os.environ["MIXEMT_B200_PINNED"]
+    assert m3.ctypes.data != addr and np.array_equal(m0, m3)
+    del m2
+    gc.collect()
+    _lib.trim_pinned()
