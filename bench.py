@@ -593,8 +593,8 @@ def run_b200(opts):
                "call": "mixemt_b200.run_em(pageable host ndarray, weights, args) to convergence "
                        "(tolerance 1e-4, Dirichlet(1) start, seed %d)" % opts.seed,
                "input_memory": "pageable numpy array",
-               "result_memory": "pageable numpy array" if opts.pageable_result
-               else "pooled pinned block (reserved before the warm-up call)",
+               "result_memory": ("pooled pinned block (reserved before the warm-up call)"
+                                 if read_mix.base is not None else "pageable numpy array"),
                "iterations": iters, "seconds": e2e_s,
                "breakdown_ms": {"h2d": stage[0], "setup_tiles": stage[1], "iterate": stage[2],
                                 "read_mix": stage[3], "d2h": stage[4], "release": stage[5],
@@ -618,6 +618,8 @@ def run_b200(opts):
         barrier()
         dt = time.perf_counter() - t0
         build_e2e = {"seconds": dt, "cells_per_s": mat.size / dt, "d2h_bytes": mat.nbytes,
+                     "result_memory": "pooled pinned block" if mat.base is not None
+                     else "pageable numpy array",
                      "call": "mixemt_b200.build_em_matrix(refseq, phylo, %d signature strings, "
                              "%d haplogroups, args) -> host ndarray: table packing, string "
                              "parsing, kernel 1 and the %.2f GB device->host copy inside"

@@ -517,3 +517,38 @@ def test_pinned_result_pool_and_stage_times():
     del m2
     gc.collect()
     _lib.trim_pinned()
+
+
+@pytest.mark.parametrize("h", [1040, 1500, 3000, 4961, 8000, 8192])
+def test_class_tiles_other_widths(h):
+    """Class tiles at widths other than Build 17's 5408: the class-sum kernel reads its chunks
+    as 4, 8, 12 or 16 entries per thread depending on H, the sort uses as many items; -U gives
+    H = 4961.  Columns come in blocks of equal columns of varying width (1..200), rows 300-330
+    are noise (every column its own class)."""
+    import ctypes
+    from mixemt_b200._lib import lib, check, ptr
+    rs = np.random.RandomState(h)
+    n = 700
+    widths = []
+    while sum(widths) < h:
+        widths.append(int(rs.randint(1, 200)))
+    base = -rs.gamma(2.0, 3.0, size=(n, len(widths)))
+    mat = np.repeat(base, widths, axis=1)[:, :h].copy()
+    mat = mat[:, rs.permutation(h)]                      # classes are not contiguous columns
+    mat[300:330] -= rs.gamma(2.0, 1.0, size=(30, h))
+    wts = rs.randint(0, 6, size=n).astype(np.float64)   # some zero weights
+    ctx = get_context()
+    dev = DeviceMatrix.from_host(ctx, mat)
+    sess = ctypes.c_void_p()
+    check(lib.mxb_em_create(ctx.handle, dev.handle, ptr(wts), 0, ctypes.byref(sess)))
+    nbytes, flag = ctypes.c_int64(), ctypes.c_int64()
+    check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nbytes), ctypes.byref(flag)))
+    lib.mxb_em_destroy(sess)
+    assert flag.value == 0, "expected class tiles"
+    inits = np.log(rs.dirichlet([1.0] * h, size=1))
+    a = make_args(max_iter=80, tolerance=1e-7)
+    props, read_mix, info, _ = em.run_em_device(dev, wts, a, inits=inits)
+    o_props, o_mix, o_iters = oracle_c.run_em(mat, wts, inits, a.max_iter, a.tolerance)
+    assert info["iterations"] == list(o_iters)
+    assert np.abs(props - o_props).max() < 1e-10
+    assert close_mix(read_mix, o_mix)
