@@ -57,6 +57,13 @@ def _worker(rank, world, port, mode, out):
                 s = np.exp(ln) * t
                 ln = np.log(s / s.sum())
             out[rank] = ln
+        elif mode == "inits":
+            # every rank has its own numpy.random state; rank 0's Dirichlet draws must reach all
+            np.random.seed(100 + rank)
+            h = mat.shape[1]
+            got = sharding.share_from_rank0(
+                lambda: np.log(np.random.dirichlet([1.0] * h, size=3)), (3, h), rank, gloo_allreduce)
+            out[rank] = got
         else:
             mine = sharding.restart_shard(len(inits), rank, world)
             acc = np.zeros(mat.shape[1])
@@ -118,3 +125,20 @@ def test_fold_handles_ranks_without_restarts():
     x = np.array([[0.0, -np.inf], [-3.0, -700.0]])
     assert np.allclose(sharding.fold_read_mix(x, 1, ident), x)
     assert np.allclose(sharding.fold_read_mix(x, 4, ident)[1], x[1] - np.log(4))
+
+
+def test_default_inits_are_drawn_on_rank0_and_shared():
+    """in both sharding modes every rank must start from the same proportions; the
+    reference draws from the global numpy.random stream (em.py:36), here rank 0's."""
+    res = run_world("inits")
+    np.random.seed(100)
+    want = np.log(np.random.dirichlet([1.0] * problem()[0].shape[1], size=3))
+    assert np.array_equal(res[0], want) and np.array_equal(res[1], want)
+
+
+def test_restart_blocks_are_contiguous_and_ordered():
+    for n_multi, world in ((100, 8), (5, 2), (3, 8)):
+        blocks = [sharding.restart_shard(n_multi, r, world) for r in range(world)]
+        flat = sum(blocks, [])
+        assert flat == list(range(n_multi))                    # rank order == restart order
+        assert max(map(len, blocks)) - min(map(len, blocks)) <= 1
