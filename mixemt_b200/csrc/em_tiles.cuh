@@ -336,7 +336,7 @@ tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned int *__re
 constexpr int kTileRingBytes = 192 * 1024;     // all teams of a CTA together
 constexpr int kTileMaxStages = 16;             // ring slots of a team
 constexpr size_t kTilePassSmem = kTileRingBytes + kTileWarps * kTileMaxStages * sizeof(uint64_t) +
-                                 4 * kTileWarps * sizeof(double) + kTileWarps * sizeof(int) + 128;
+                                 4 * kTileWarps * sizeof(double) + 2 * kTileWarps * sizeof(int) + 128;
 
 struct TilePlan {          // one per CTA
     int32_t tw;            // team width of this CTA
@@ -432,6 +432,9 @@ __device__ __forceinline__ void tile_batch(const TileDesc &d, const TileItem &it
             parity ^= 1;
         }
         // every thread of the team holds its cells of these rows in registers: refill the slots
+        // (tw > 1: the team barrier above orders the reads before the refill; one warp: its
+        // lanes have converged in the butterfly, the explicit __syncwarp says so)
+        if (tw == 1) __syncwarp();
         if (producer) {
 #pragma unroll
             for (int g = 0; g < RU; ++g) {
@@ -475,9 +478,11 @@ __device__ __forceinline__ void tile_batch(const TileDesc &d, const TileItem &it
     int last = 0;
     if (tw > 1) {
         team_barrier(1 + team, tthreads);              // every warp's stores are fenced
-        if (tt == 0) ired[team] = atomicAdd(done + it.batch, 1) == d.ng - 1;
+        // (a slot of its own: the team's next queue index goes through ired[team] with no
+        // barrier between this read and that write)
+        if (tt == 0) ired[kTileWarps + team] = atomicAdd(done + it.batch, 1) == d.ng - 1;
         team_barrier(1 + team, tthreads);
-        last = ired[team];
+        last = ired[kTileWarps + team];
     } else {
         if (lane == 0) last = atomicAdd(done + it.batch, 1) == d.ng - 1;
         last = __shfl_sync(0xffffffffu, last, 0);
@@ -512,7 +517,7 @@ tile_pass_kernel(const TileDesc *__restrict__ desc, const TileItem *__restrict__
     extern __shared__ __align__(128) unsigned char tile_smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(tile_smem + kTileRingBytes);   // [16][16]
     double *red = reinterpret_cast<double *>(bars + kTileWarps * kTileMaxStages);  // [2][2][16]
-    int *ired = reinterpret_cast<int *>(red + 4 * kTileWarps);                     // [16]
+    int *ired = reinterpret_cast<int *>(red + 4 * kTileWarps);                     // [2][16]
     const int tid = threadIdx.x, warp = tid >> 5;
     const TilePlan pl = plan[blockIdx.x];
     const int tw = pl.tw;
