@@ -199,8 +199,11 @@ int mxb_matrix_upload_rows(mxb_ctx *ctx, mxb_matrix *m, int64_t row0, int64_t n_
 /* ---- kernel 2: EM (replaces em_step / run_em, em.py:57-165) ---------------- */
 /* Session over one matrix shard.  weights[n_rows] (fp64).  sharded != 0 and a
  * comm on ctx: rows are a shard, column sums are all-reduced every iteration.
- * The session keeps L = exp(M - rowmax); rows with at most 256 distinct values are
- * stored as one byte per cell plus a table (lossless, see mxb_em_pass_bytes). */
+ * The session keeps L = exp(M - rowmax) either as class tiles (per 128-row batch the
+ * bit-identical columns collapse into classes: exact, several times fewer bytes and FMAs;
+ * needs rows in the reference's order, preprocess.py:219, to pay off) or, when the matrix does
+ * not compress, as fp64 rows (see mxb_em_pass_bytes).  In a sharded session the call is
+ * collective: every rank zeroes its peer mailboxes behind a barrier. */
 int mxb_em_create(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
                   int sharded, mxb_em **out);
 int mxb_em_destroy(mxb_em *em);
@@ -210,17 +213,17 @@ int mxb_em_set_lnprops(mxb_em *em, const double *lnprops);
  * max_iter.  iters_out = iterations run; converged_out = 1/0. */
 int mxb_em_iterate(mxb_em *em, int64_t max_iter, double tol,
                    int64_t *iters_out, int32_t *converged_out);
-/* Bytes the pass kernel(s) of one EM iteration read from HBM, and how the rows are stored:
- * *n_dense_rows = -1 when the session keeps L as fp64 rows (N x ld x 8 bytes per pass), else
- * the number of rows kept as fp64 next to the dictionary-coded records of all rows
- * (ld + 2048 bytes each; csrc/em.cu: em_pack_kernel).  Measurement aid of bench.py; no
- * counterpart in the reference (em.py:57-91 re-reads the whole matrix several times). */
-int mxb_em_pass_bytes(const mxb_em *em, int64_t *bytes_per_pass, int64_t *n_dense_rows);
+/* Bytes the kernels of one EM iteration read from HBM, and how the rows are stored:
+ * *layout = -1 when the session keeps L as fp64 rows (N x ld x 8 bytes per pass), 0 when it
+ * runs over class tiles (csrc/em_tiles.cuh: tiles + class maps + class vectors).
+ * Measurement aid of bench.py; no counterpart in the reference (em.py:57-91 re-reads the
+ * whole matrix several times). */
+int mxb_em_pass_bytes(const mxb_em *em, int64_t *bytes_per_pass, int64_t *layout);
 
 /* Exactly n_iter iterations without convergence test or host sync (bench);
  * elapsed_ms (nullable) = device time between first and last launch,
- * pass_ms (nullable) = summed device time of the fused E/M pass kernel only
- * (adds an event pair per iteration). */
+ * pass_ms (nullable) = summed device time from the first pass kernel of an iteration to
+ * its tail kernel (class sums + pass + gather for tiles; adds an event pair per iteration). */
 int mxb_em_iterate_fixed(mxb_em *em, int64_t n_iter, float *elapsed_ms,
                          float *pass_ms);
 /* Per-kernel attribution of an iteration (bench instrumentation): n_iter iterations with an
@@ -259,8 +262,9 @@ int mxb_run_em_dev(mxb_ctx *ctx, const mxb_matrix *m, const double *weights,
                    double *props_out, double *read_mix_out,
                    mxb_matrix **read_mix_dev,
                    int64_t *iters_out, int32_t *converged_out);
-/* Cross-rank fold of per-rank read matrices (restart fan-out):
- * m = log(sum over ranks of exp(m)) - sub_log, in place, over the ctx comm. */
+/* Cross-rank fold of per-rank read matrices (restart fan-out, em.py:156 and :161 across
+ * ranks): m = logaddexp over ranks (in rank order) of m - sub_log, in place on every rank.
+ * All-to-all of row shards (ncclSend/ncclRecv), local fold, shards broadcast back. */
 int mxb_matrix_fold_ranks(mxb_ctx *ctx, mxb_matrix *m, double sub_log);
 /* em.em_step (em.py:57-91): one E+M step, read_mix_out written in full. */
 int mxb_em_step(mxb_ctx *ctx, const double *read_hap_mat, const double *weights,
