@@ -78,16 +78,17 @@ struct mxb_em {
     bool tiled = false;
     int n_batches = 0, tile_hs = 0, tile_parts = 0, tile_grid = 0;
     unsigned char *tile_block = nullptr;   // [perm][cmap][cword][desc]
-    unsigned char *tile_vecs = nullptr;    // [pi_cls][u_sum][u shares][plan][slot_ptr][slot_items][items][p_off][done]
+    unsigned char *tile_vecs = nullptr;    // [pi_cls][u_sum][ctas][segs][copies][gather entries]
     unsigned short *tile_perm = nullptr, *tile_cmap = nullptr;
     unsigned int *tile_cword = nullptr;
     TileDesc *tile_desc = nullptr;
-    TileItem *tile_items = nullptr;
-    TilePlan *tile_plan = nullptr;
-    int *tile_class_ptr = nullptr, *tile_class_items = nullptr, *tile_next = nullptr;
-    double *tile_pi = nullptr, *tile_u = nullptr, *tile_usum = nullptr;
-    int64_t *tile_poff = nullptr;
-    int *tile_done = nullptr;
+    TileCta *tile_ctas = nullptr;           // plan of the pass (em_tiles.cuh)
+    TileSeg *tile_segs = nullptr;
+    int *tile_ent_batch = nullptr;          // gather entries: batch and offset of every U vector
+    int64_t *tile_ent_off = nullptr;
+    int tile_n_ent = 0, tile_n_slots = 0;
+    uint32_t tile_slot_bytes = 0;
+    double *tile_pi = nullptr, *tile_usum = nullptr;
     double *tile_v = nullptr;
     int64_t tile_cells = 0;                // doubles in tile_v
     int64_t tile_bytes_per_pass = 0;
@@ -133,10 +134,14 @@ constexpr int kMaxSlots = 2;
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait): the kernel may
 // be scheduled before its predecessor in the stream has finished.  MXB_EM_NO_PDL=1 turns the
 // attribute off (plain stream order).
+// (set before a call to launch that kernel in plain stream order)
+static thread_local bool g_plain_launch = false;
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
                               cudaStream_t s, Args... args) {
-    static const bool use_pdl = getenv("MXB_EM_NO_PDL") == nullptr;
+    static const bool pdl_on = getenv("MXB_EM_NO_PDL") == nullptr;
+    const bool use_pdl = pdl_on && !g_plain_launch;
+    g_plain_launch = false;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -187,24 +192,24 @@ static int enqueue_iteration(mxb_em *em, cudaEvent_t pass_begin = nullptr,
                                 (const unsigned int *)em->tile_cword, em->tile_hs,
                                 (int)em->n_cols, (const TileDesc *)em->tile_desc, em->n_batches,
                                 (const double *)em->pi[0], (const double *)em->pi[1],
-                                (const EmState *)em->state, em->tile_pi, em->tile_next));
+                                (const EmState *)em->state, em->tile_pi));
         }
         if (marks) MXB_CUDA(cudaEventRecord(marks[0], s));
-        MXB_CUDA(launch_pdl(tile_pass_kernel, dim3(em->tile_grid), dim3(kTileThreads),
-                            kTilePassSmem, s, (const TileDesc *)em->tile_desc,
-                            (const TileItem *)em->tile_items,
-                            (const TilePlan *)em->tile_plan, (const int *)em->tile_class_ptr,
-                            (const int *)em->tile_class_items, em->tile_next,
-                            (const double *)em->tile_v,
-                            (const double *)em->tile_pi, (const double *)em->weights, em->state,
-                            em->tile_u, em->tile_usum, em->tile_done));
+        MXB_CUDA(launch_pdl(tile_pass_kernel, dim3(em->tile_grid), dim3(kTilePassThreads),
+                            kTilePassSmem, s, (const TileCta *)em->tile_ctas,
+                            (const TileSeg *)em->tile_segs, (const double *)em->tile_v, (const double *)em->tile_pi, em->state,
+                            em->tile_usum, em->tile_slot_bytes, em->tile_n_slots));
         if (marks) MXB_CUDA(cudaEventRecord(marks[1], s));
+        // The gather waits in plain stream order: launched early it would sit on the SMs the
+        // first CTAs of the pass leave and keep them from nothing, but measured it costs 27 us
+        // per iteration (B200, config 2), while the other three launches gain from the overlap.
+        g_plain_launch = true;
         MXB_CUDA(launch_pdl(tile_gather_kernel,
                             dim3((unsigned)ceil_div(em->ld, kGatherThreads), em->tile_parts),
                             dim3(kGatherThreads), 0, s, (const unsigned short *)em->tile_cmap,
-                            em->tile_hs, (int)em->n_cols, em->ld, (const int64_t *)em->tile_poff,
-                            em->n_batches, (const double *)em->tile_usum,
-                            (const EmState *)em->state, em->partials));
+                            em->tile_hs, (int)em->n_cols, em->ld, (const int *)em->tile_ent_batch,
+                            (const int64_t *)em->tile_ent_off, em->tile_n_ent,
+                            (const double *)em->tile_usum, (const EmState *)em->state, em->partials));
         if (marks) MXB_CUDA(cudaEventRecord(marks[2], s));
         ctx->launches += 3;
     } else if (em->fast) {
@@ -414,162 +419,182 @@ static int em_pack_tiles(mxb_em *em) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return give_up(true, "classes");
 
-    // layout: team width and chunk count per batch, tile and class-vector offsets
+    // layout: threads per row, tile and class-vector offsets
     std::vector<TileDesc> desc((size_t)nb);
-    int64_t v_cells = 0, p_cells = 0, u_cells = 0;
-    std::vector<TileItem> items;
+    int64_t v_cells = 0, p_cells = 0;
+    int max_r_pad = 4;
     for (int b = 0; b < nb; ++b) {
         TileDesc &d = desc[(size_t)b];
         d.row0 = b * kTileRows;
         d.n_rows = (int)std::min<int64_t>(kTileRows, n - (int64_t)b * kTileRows);
         d.n_cls = ncls[(size_t)b];
-        int tw = 1;
-        while (tw < kTileWarps && d.n_cls > 512 * tw) tw *= 2;
-        d.tw = tw;
-        d.nk = (int)std::max<int64_t>(1, ceil_div(d.n_cls, 64 * tw));
-        d.c_pad = 64 * tw * d.nk;
-        // up to four work items of at least 16 rows: enough items to keep every team of every
-        // SM busy (a CTA holds 16 / tw teams), shares of U_b added again by the gather kernel
-        d.ng = (int)std::max<int64_t>(1, std::min<int64_t>(kTileItems, d.n_rows / 16));
-        static_assert(kTileRows <= 32 * kTileItems, "an item must not exceed 32 rows (tile_batch)");
-        d.pad = 0;
+        d.r_pad = (int)round_up(d.n_cls + 1, 4);      // + the weight column
+        // a row is handled by 2^lg threads, each with at most 8 double2 chunks of its class
+        // values (the weight behind them is read apart): up to 8192 classes with 16 warps
+        d.lg = 3;
+        while (((d.n_cls + 1) >> 1) > (8 << d.lg)) ++d.lg;
+        d.pad0 = d.pad1 = d.pad2 = 0;
         d.v_off = v_cells;
         d.p_off = p_cells;
-        d.u_off = u_cells;
-        v_cells += (int64_t)d.n_rows * d.c_pad;
-        p_cells += d.c_pad;
-        u_cells += (int64_t)d.ng * d.c_pad;
-        for (int g = 0; g < d.ng; ++g) {
-            TileItem it;
-            it.batch = b;
-            it.g = g;
-            it.r0 = (int)((int64_t)d.n_rows * g / d.ng);
-            it.r1 = (int)((int64_t)d.n_rows * (g + 1) / d.ng);
-            items.push_back(it);
-        }
+        v_cells += (int64_t)d.n_rows * d.r_pad;
+        p_cells += d.r_pad;
+        max_r_pad = std::max(max_r_pad, d.r_pad);
     }
-    const int n_items = (int)items.size();
-    // Plan of the pass: every CTA works on items of one team width, its 16 / tw teams on
-    // different items.  CTAs are dealt to the widths in proportion to the work (a row costs a
-    // team about 40 + 10 nk issue slots per warp, a little more with the per-row barrier of
-    // wide teams); within a width the teams draw items longest first from a device queue.
-    std::vector<TilePlan> plan;
-    std::vector<int> slot_ptr(1, 0), slot_items;   // work items by width class, longest first
+    // The ring of the pass: three slots of 52 KB, fewer and longer ones if a row is longer than
+    // that (a copy costs every warp ~650 cycles: large copies, measured 24 to 78 KB).
+    const uint32_t slot_bytes = (uint32_t)round_up(std::max<int64_t>(kTileSlotBytes, (int64_t)max_r_pad * 8), 1024);
+    const int n_slots = std::min(kTileMaxSlots, kTileRingBytes / (int)slot_bytes);
+    if (n_slots < 2) return give_up(false, "rows too long for the ring");
+    // Plan of the pass: CTA c gets the rows between the c-th and the (c+1)-th n_cta-quantile of
+    // the tile bytes (+ a fixed cost per batch for its class vectors and the share exchange),
+    // cut at multiples of four rows; the part of a batch inside one CTA's range is a segment.
+    std::vector<TileCta> ctas;
+    std::vector<TileSeg> segs;
+    std::vector<int> ent_batch;           // gather entries: (batch, offset of a U vector)
+    std::vector<int64_t> ent_off;
+    int64_t extra_cells = 0;              // U vectors of the second, third.. segment of a batch
+    int n_copy = 0;
     {
-        auto batch_cost = [&](int i) {     // of work item i
-            const TileDesc &d = desc[(size_t)items[(size_t)i].batch];
-            return (double)(items[(size_t)i].r1 - items[(size_t)i].r0) * (40.0 + 10.0 * d.nk) *
-                   (d.tw > 1 ? 1.3 : 1.0) + 200.0;
+        // Cost of a segment in SM cycles (measured with the kernel's cycle counters at config 2):
+        // ~3200 for the exchange at its end, ~650 per copy (wait, hand-back, refill), and per row
+        // the larger of its bytes at the SM's share of HBM (22 B per cycle) and of its row step
+        // (~1000 cycles for the 512 >> lg rows the CTA handles at a time).
+        auto rows_per_copy = [&](const TileDesc &d) {
+            const int per_step = d.lg < 5 ? 32 >> d.lg : 1;
+            return std::max(per_step, (int)(slot_bytes / (uint32_t)(d.r_pad * 8)) / per_step * per_step);
         };
-        std::vector<int> of_width[5];
-        double demand[5] = {0, 0, 0, 0, 0}, demand_sum = 0.0;
-        for (int i = 0; i < n_items; ++i) {
-            const int tw = desc[(size_t)items[(size_t)i].batch].tw;
-            int k = 0;
-            while ((1 << k) < tw) ++k;
-            of_width[k].push_back(i);
-            demand[k] += batch_cost(i) * tw / kTileWarps;
-        }
-        for (int k = 0; k < 5; ++k) demand_sum += demand[k];
-        int n_cta[5], total = 0;
-        for (int k = 0; k < 5; ++k) {
-            n_cta[k] = 0;
-            if (of_width[k].empty()) continue;
-            const int teams = kTileWarps >> k;
-            const int cap = (int)ceil_div((int64_t)of_width[k].size(), teams);
-            n_cta[k] = std::max(1, std::min(cap, (int)(ctx->num_sms * demand[k] / demand_sum)));
-            total += n_cta[k];
-        }
-        // hand out what rounding left over to the widths with the most work per CTA
-        for (bool grew = true; total < ctx->num_sms && grew;) {
-            grew = false;
-            int best = -1;
-            double best_load = 0.0;
-            for (int k = 0; k < 5; ++k) {
-                if (of_width[k].empty()) continue;
-                const int cap = (int)ceil_div((int64_t)of_width[k].size(), kTileWarps >> k);
-                if (n_cta[k] >= cap) continue;
-                const double load = demand[k] / n_cta[k];
-                if (best < 0 || load > best_load) { best = k; best_load = load; }
+        auto row_cost_of = [&](const TileDesc &d) {
+            return std::max((double)d.r_pad * 8 / 22.0, 1000.0 / (double)(512 >> d.lg)) +
+                   650.0 / rows_per_copy(d);
+        };
+        const double seg_cost = 3200.0;
+        std::vector<double> suffix((size_t)nb + 1, 0.0);     // cost of batches b.. as whole segments
+        for (int b = nb - 1; b >= 0; --b)
+            suffix[(size_t)b] = suffix[(size_t)b + 1] + seg_cost + desc[(size_t)b].n_rows * row_cost_of(desc[(size_t)b]);
+        const int n_cta = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, ceil_div(n, 32)));
+        int c = 0;
+        double budget = suffix[0] / n_cta, used = 0.0;       // of the CTA being filled
+        TileCta cur{0, 0, 0, 0};
+        auto close_cta = [&](double remaining) {
+            if (cur.n_segs > 0) ctas.push_back(cur);
+            cur.seg0 = (int)segs.size();
+            cur.n_segs = cur.n_copies = 0;
+            ++c;
+            used = 0.0;
+            budget = remaining / std::max(1, n_cta - c);     // what is left, shared by the CTAs left
+        };
+        for (int b = 0; b < nb; ++b) {
+            const TileDesc &d = desc[(size_t)b];
+            const double row_cost = row_cost_of(d);
+            int r = 0, seg_no = 0;
+            while (r < d.n_rows) {
+                // rows of this batch that still fit into the CTA's budget
+                int take = d.n_rows - r;
+                const double remaining = suffix[(size_t)b + 1] + seg_cost + take * row_cost;
+                if (c + 1 < n_cta && used + seg_cost + take * row_cost > budget) {
+                    const double room = budget - used - seg_cost;
+                    int fit_rows = room > 0 ? (int)(room / row_cost) / 4 * 4 : 0;
+                    if (fit_rows < 8) fit_rows = 0;                              // no crumbs
+                    else if (take - fit_rows < 8) fit_rows = take;
+                    // a small overshoot is better than one more segment
+                    if (fit_rows < take && used + seg_cost + take * row_cost < 1.04 * budget) fit_rows = take;
+                    take = fit_rows;
+                }
+                if (take == 0) {
+                    if (cur.n_segs == 0) take = std::min(d.n_rows - r, 8);       // a CTA never stays empty
+                    else { close_cta(remaining); continue; }
+                }
+                TileSeg sg;
+                memset(&sg, 0, sizeof(sg));
+                sg.p_off = d.p_off;
+                sg.u_dst = seg_no == 0 ? d.p_off : p_cells + extra_cells;
+                if (seg_no > 0) extra_cells += d.r_pad;
+                sg.r_pad = d.r_pad;
+                sg.n_cls = d.n_cls;
+                sg.lg = d.lg;
+                sg.n_rows = take;
+                sg.batch = b;
+                ent_batch.push_back(b);
+                ent_off.push_back(sg.u_dst);
+                // its copies: whole rows, as many as a slot holds, a multiple of the rows of a
+                // warp step (32 >> lg for lg < 5) so that a step never straddles two copies
+                sg.fit = rows_per_copy(d);
+                sg.n_copies = (int)ceil_div(take, sg.fit);
+                sg.v_off = d.v_off + (int64_t)r * d.r_pad;
+                cur.n_copies += sg.n_copies;
+                n_copy += sg.n_copies;
+                segs.push_back(sg);
+                ++cur.n_segs;
+                used += seg_cost + take * row_cost;
+                r += take;
+                ++seg_no;
             }
-            if (best >= 0) { ++n_cta[best]; ++total; grew = true; }
         }
-        for (int k = 0; k < 5; ++k) {
-            std::vector<int> &list = of_width[k];
-            std::stable_sort(list.begin(), list.end(),
-                             [&](int a, int b) { return batch_cost(a) > batch_cost(b); });
-            for (int i : list) slot_items.push_back(i);
-            slot_ptr.push_back((int)slot_items.size());
-            for (int c = 0; c < n_cta[k]; ++c) {
-                TilePlan pl;
-                pl.tw = 1 << k;
-                pl.klass = k;
-                plan.push_back(pl);
-            }
-        }
+        close_cta(0.0);
     }
-    const int n_plan = (int)plan.size();
+    const int n_cta = (int)ctas.size(), n_seg = (int)segs.size();
+    const int n_ent = (int)ent_batch.size();
+    const int64_t u_cells = p_cells + extra_cells;
     const double tile_bytes = (double)v_cells * 8 + 3.0 * (double)nb * hs * 2 +
-                              2.0 * (double)(p_cells + u_cells) * 8;
+                              ((double)p_cells + (double)u_cells) * 8 * 2;
     const double fp64_bytes = (double)n * (double)em->ld * 8;
     if (verbose) {
         int64_t c_sum = 0, c_max = 0, wide = 0;
         for (int b = 0; b < nb; ++b) {
             c_sum += desc[(size_t)b].n_cls;
             c_max = std::max<int64_t>(c_max, desc[(size_t)b].n_cls);
-            wide += desc[(size_t)b].tw > 1;
+            wide += desc[(size_t)b].lg > 5;
+        }
+        {
+            double mx = 0, mn = 1e30; int smx = 0, cmx = 0;
+            for (const TileCta &c : ctas) {
+                double by = 0;
+                for (int q = 0; q < c.n_segs; ++q) by += (double)segs[(size_t)(c.seg0 + q)].n_rows * segs[(size_t)(c.seg0 + q)].r_pad * 8;
+                mx = std::max(mx, by); mn = std::min(mn, by); smx = std::max(smx, c.n_segs); cmx = std::max(cmx, c.n_copies);
+            }
+            fprintf(stderr, "[mxb tiles] per CTA: bytes min %.0f max %.0f, segments max %d, copies max %d\n", mn, mx, smx, cmx);
         }
         fprintf(stderr, "[mxb tiles] %d batches of %d rows: classes mean %.1f max %lld, %lld wide "
-                "batches, tiles %.3f GB (+ maps and vectors: %.3f GB) vs fp64 rows %.3f GB\n",
+                "batches, tiles %.3f GB (+ maps and vectors: %.3f GB) vs fp64 rows %.3f GB; %d CTAs, "
+                "%d segments, %d copies, %d slots of %u B\n",
                 nb, kTileRows, (double)c_sum / nb, (long long)c_max, (long long)wide,
-                (double)v_cells * 8 / 1e9, tile_bytes / 1e9, fp64_bytes / 1e9);
+                (double)v_cells * 8 / 1e9, tile_bytes / 1e9, fp64_bytes / 1e9, n_cta, n_seg, n_copy,
+                n_slots, slot_bytes);
     }
     if (tile_bytes > 0.5 * fp64_bytes) return give_up(false, "not worth it");
 
     e = dev_alloc(ctx, (void **)&v, (size_t)v_cells * sizeof(double));
     unsigned char *vecs = nullptr;
-    const size_t b_vec = up((size_t)p_cells * sizeof(double));
+    const size_t b_pi = up((size_t)p_cells * sizeof(double));
     const size_t b_u = up((size_t)u_cells * sizeof(double));
-    const size_t b_plan = up((size_t)n_plan * sizeof(TilePlan));
-    const size_t b_sptr = up(slot_ptr.size() * sizeof(int));
-    const size_t b_sitems = up((size_t)n_items * sizeof(int));
-    const size_t b_items = up((size_t)n_items * sizeof(TileItem));
-    const size_t b_poff = up((size_t)nb * sizeof(int64_t)) + 256;   // + the pass's queue counters
+    const size_t b_cta = up((size_t)n_cta * sizeof(TileCta));
+    const size_t b_seg = up((size_t)n_seg * sizeof(TileSeg));
+    const size_t b_entb = up((size_t)n_ent * sizeof(int));
+    const size_t b_ento = up((size_t)n_ent * sizeof(int64_t));
     if (e == cudaSuccess)
-        e = dev_alloc(ctx, (void **)&vecs, 2 * b_vec + b_u + b_plan + b_sptr + b_sitems + b_items +
-                                            b_poff + b_int);
+        e = dev_alloc(ctx, (void **)&vecs, b_pi + b_u + b_cta + b_seg + b_entb + b_ento);
     if (e != cudaSuccess) { dev_free(ctx, vecs); return give_up(false, "tiles"); }
     double *pi_cls = reinterpret_cast<double *>(vecs);
-    double *u_sum = reinterpret_cast<double *>(vecs + b_vec);
-    double *u_cls = reinterpret_cast<double *>(vecs + 2 * b_vec);
-    unsigned char *tail = vecs + 2 * b_vec + b_u;
-    TilePlan *d_plan = reinterpret_cast<TilePlan *>(tail);
-    int *d_slot_ptr = reinterpret_cast<int *>(tail + b_plan);
-    int *d_slot_items = reinterpret_cast<int *>(tail + b_plan + b_sptr);
-    TileItem *d_items = reinterpret_cast<TileItem *>(tail + b_plan + b_sptr + b_sitems);
-    int64_t *d_poff = reinterpret_cast<int64_t *>(tail + b_plan + b_sptr + b_sitems + b_items);
-    int *d_next = reinterpret_cast<int *>(tail + b_plan + b_sptr + b_sitems + b_items + b_poff - 256);
-    int *d_done = reinterpret_cast<int *>(tail + b_plan + b_sptr + b_sitems + b_items + b_poff);
-    std::vector<int64_t> poff((size_t)nb);
-    for (int b = 0; b < nb; ++b) poff[(size_t)b] = desc[(size_t)b].p_off;
+    double *u_sum = reinterpret_cast<double *>(vecs + b_pi);
+    unsigned char *tail = vecs + b_pi + b_u;
+    TileCta *d_ctas = reinterpret_cast<TileCta *>(tail);
+    TileSeg *d_segs = reinterpret_cast<TileSeg *>(tail + b_cta);
+    int *d_entb = reinterpret_cast<int *>(tail + b_cta + b_seg);
+    int64_t *d_ento = reinterpret_cast<int64_t *>(tail + b_cta + b_seg + b_entb);
     e = cudaMemcpyAsync(d_desc, desc.data(), (size_t)nb * sizeof(TileDesc), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(d_plan, plan.data(), (size_t)n_plan * sizeof(TilePlan), cudaMemcpyHostToDevice, ctx->stream);
+        e = cudaMemcpyAsync(d_ctas, ctas.data(), (size_t)n_cta * sizeof(TileCta), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(d_slot_ptr, slot_ptr.data(), slot_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        e = cudaMemcpyAsync(d_segs, segs.data(), (size_t)n_seg * sizeof(TileSeg), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(d_slot_items, slot_items.data(), (size_t)n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        e = cudaMemcpyAsync(d_entb, ent_batch.data(), (size_t)n_ent * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(d_items, items.data(), (size_t)n_items * sizeof(TileItem), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(d_poff, poff.data(), (size_t)nb * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_done, 0, (size_t)nb * sizeof(int), ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_next, 0, 256, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(vecs, 0, 2 * b_vec + b_u, ctx->stream);
+        e = cudaMemcpyAsync(d_ento, ent_off.data(), (size_t)n_ent * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(vecs, 0, b_pi + b_u, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, (size_t)nb * sizeof(int), ctx->stream);
     if (e == cudaSuccess) {
         tile_fill_kernel<<<std::min(nb, ctx->num_sms * 4), kTileThreads, 0, ctx->stream>>>(
-            em->mat->data, h, d_desc, nb, cmap, rep, hs, v, d_bad);
+            em->mat->data, h, d_desc, nb, cmap, rep, hs, (const double *)em->weights, v, d_bad);
         ctx->launches += 1;
         e = cudaGetLastError();
     }
@@ -601,23 +626,23 @@ static int em_pack_tiles(mxb_em *em) {
     em->tile_cmap = cmap;
     em->tile_cword = cword;
     em->tile_desc = d_desc;
-    em->tile_plan = d_plan;
-    em->tile_items = d_items;
+    em->tile_ctas = d_ctas;
+    em->tile_segs = d_segs;
+    em->tile_ent_batch = d_entb;
+    em->tile_ent_off = d_ento;
+    em->tile_n_ent = n_ent;
+    em->tile_slot_bytes = slot_bytes;
+    em->tile_n_slots = n_slots;
     em->tile_usum = u_sum;
-    em->tile_poff = d_poff;
-    em->tile_done = d_done;
-    em->tile_class_ptr = d_slot_ptr;
-    em->tile_class_items = d_slot_items;
-    em->tile_next = d_next;
     em->tile_pi = pi_cls;
-    em->tile_u = u_cls;
     em->tile_v = v;
     em->tile_cells = v_cells;
-    em->tile_grid = n_plan;
-    em->tile_parts = std::max(1, std::min(32, nb / 8));
+    em->tile_grid = n_cta;
+    em->tile_parts = std::max(1, std::min(32, n_ent / 8));
     em->n_part = em->tile_parts;
-    // what an iteration reads: the tiles, perm + cmap (Pi), cmap (gather), the class vectors
-    em->tile_bytes_per_pass = v_cells * 8 + 3 * (int64_t)nb * hs * 2 + 2 * (p_cells + u_cells) * 8 + n * 8;
+    // what an iteration reads and writes: the tiles, perm + cmap (Pi), cmap (gather), the class
+    // vectors (Pi written and read, U written and read)
+    em->tile_bytes_per_pass = v_cells * 8 + 3 * (int64_t)nb * hs * 2 + 2 * (p_cells + u_cells) * 8;
     return rc;
 }
 
@@ -957,6 +982,13 @@ int mxb_em_iterate_fixed(mxb_em *em, int64_t n_iter, float *elapsed_ms, float *p
     cudaEventDestroy(e1);
     return MXB_OK;
 }
+
+#ifdef MXB_TILE_TRACE
+extern "C" int mxb_debug_tile_trace(unsigned long long *out, size_t n_words) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, mxb::g_tile_trace, std::min(n_words * 8, sizeof(mxb::g_tile_trace)));
+}
+#endif
 
 int mxb_em_profile(mxb_em *em, int64_t n_iter, float *ms_out) {
     MXB_REQUIRE(em != nullptr && ms_out != nullptr && n_iter >= 1 && n_iter <= 10000, "bad argument");

@@ -43,21 +43,16 @@ constexpr int kTileThreads = 512;
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kTileMaxNK = 8;        // double2 per thread and row
 constexpr int kTileMaxCols = 8192;   // widest matrix (the fast path's limit on ld)
-constexpr int kTileItems = 4;        // work items (row ranges) per batch, at most
-constexpr int kTileClasses = 5;      // team widths 1, 2, 4, 8, 16
 
 struct TileDesc {           // one batch
     int32_t row0, n_rows;
-    int32_t n_cls, c_pad;   // classes; row stride of the batch's tile in doubles (= 64 tw nk)
-    int32_t tw, nk;         // warps per row team (1, 2, 4, 8, 16), double2 per thread
-    int32_t ng, pad;        // work items (contiguous row ranges) of the batch
+    int32_t n_cls;          // classes
+    int32_t r_pad;          // row stride of its tile = length of its class vectors in doubles:
+                            // n_cls + 1 (the row's weight) rounded up to 4 (32-byte sectors)
+    int32_t lg;             // log2 of the threads that handle a row in the pass
+    int32_t pad0, pad1, pad2;
     int64_t v_off;          // tile offset in V (doubles)
-    int64_t p_off;          // offset of the batch's class sums Pi_b (doubles)
-    int64_t u_off;          // offset of the batch's ng partial class vectors U_b (doubles)
-};
-
-struct TileItem {           // one work item of the pass: rows [r0, r1) of a batch
-    int32_t batch, r0, r1, g;
+    int64_t p_off;          // offset of the batch's class vectors Pi_b and U_b (doubles)
 };
 
 __device__ __forceinline__ uint64_t tile_mix(uint64_t h, uint64_t v) {
@@ -168,13 +163,14 @@ tile_class_kernel(const unsigned long long *__restrict__ hash, int hs, int n_col
 }
 
 // Tiles V_b[r][c] = exp(M[row0 + r][rep_b[c]] - rowmax) (the value to_linear_kernel gives
-// every member of the class), zero padded to c_pad, with the exact check that makes the
+// every member of the class), then the row's weight, zero padded to r_pad, with the exact check that makes the
 // hashing safe: every cell of M must equal the cell of its class representative bit for bit.
 // One warp per row.
 __global__ void __launch_bounds__(kTileThreads)
 tile_fill_kernel(const double *__restrict__ m, int64_t n_cols, const TileDesc *__restrict__ desc,
                  int n_batches, const unsigned short *__restrict__ cmap,
-                 const unsigned short *__restrict__ rep, int hs, double *__restrict__ v,
+                 const unsigned short *__restrict__ rep, int hs,
+                 const double *__restrict__ weights, double *__restrict__ v,
                  int *__restrict__ bad) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int b = blockIdx.x; b < n_batches; b += gridDim.x) {
@@ -189,9 +185,10 @@ tile_fill_kernel(const double *__restrict__ m, int64_t n_cols, const TileDesc *_
             mx = warp_max(mx);
             for (int64_t j = lane; j < n_cols; j += 32)
                 mismatch |= __double_as_longlong(row[j]) != __double_as_longlong(row[rp[cm[j]]]);
-            double *dst = v + d.v_off + (int64_t)r * d.c_pad;
-            for (int c = lane; c < d.c_pad; c += 32)
-                dst[c] = c < d.n_cls ? exp(row[rp[c]] - mx) : 0.0;
+            double *dst = v + d.v_off + (int64_t)r * d.r_pad;
+            const double w_row = weights[d.row0 + r];
+            for (int c = lane; c < d.r_pad; c += 32)
+                dst[c] = c < d.n_cls ? exp(row[rp[c]] - mx) : c == d.n_cls ? w_row : 0.0;
         }
         if (__any_sync(0xffffffffu, mismatch) && lane == 0) bad[b] = 1;
     }
@@ -228,8 +225,7 @@ __global__ void __launch_bounds__(kTileThreads)
 tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned int *__restrict__ cword,
                int hs, int n_cols, const TileDesc *__restrict__ desc, int n_batches,
                const double *__restrict__ pi0, const double *__restrict__ pi1,
-               const EmState *__restrict__ st, double *__restrict__ pi_cls,
-               int *__restrict__ next_item) {
+               const EmState *__restrict__ st, double *__restrict__ pi_cls) {
     static_assert(PER % 4 == 0 && PER <= 16, "chunks are read as 8-byte words");
     extern __shared__ __align__(128) unsigned char tile_smem[];
     double *pi = reinterpret_cast<double *>(tile_smem);     // [n_cols]: the gathers below are
@@ -237,7 +233,6 @@ tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned int *__re
     pdl_wait();
     pdl_launch_dependents();
     if (st->done) return;
-    if (blockIdx.x == 0 && threadIdx.x < kTileClasses) next_item[threadIdx.x] = 0;  // the pass's queues
     const double *__restrict__ pi_g = st->cur ? pi1 : pi0;
     __shared__ int s_flag[kTileWarps];
     __shared__ double s_val[kTileWarps];
@@ -320,254 +315,313 @@ tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned int *__re
 }
 
 // ---- the pass ------------------------------------------------------------------------------
-// A work item is a contiguous range of rows of one batch (a batch is cut into up to four), handled
-// by a *team* of `tw` warps (tw = 1 for at most 512 classes -- the bulk --, 2, 4, 8 or 16 for the
-// wider ones); the 16 / tw teams of a CTA work on different items independently.  Every CTA is
-// given a width when the tiles are built (CTAs in proportion to the work of each width, em.cu);
-// its teams draw items of that width, longest first, from a device-wide queue.  Thread tt of a team owns the double2 chunks tt + 32 tw k (k < nk) of the
-// class vectors: Pi_b and the item's share of U_b live in registers for the whole item, the
-// share is stored straight from registers, and the item of a batch that finishes last adds
-// the shares in item order into U_b -- no block-level synchronisation anywhere.
-// The rows of the tile stream through a team-private shared-memory ring filled by 1-D bulk
-// async copies (cp.async.bulk + mbarrier complete_tx, one instruction per row, issued by the
-// team's first thread); a row costs a warp nk 16-byte shared loads, 4 nk DFMA, one shuffle
-// butterfly and a division (plus one named barrier per row step for tw > 1); two rows are in
-// flight per team where the registers allow it (nk <= 4).
-constexpr int kTileRingBytes = 192 * 1024;     // all teams of a CTA together
-constexpr int kTileMaxStages = 16;             // ring slots of a team
-constexpr size_t kTilePassSmem = kTileRingBytes + kTileWarps * kTileMaxStages * sizeof(uint64_t) +
-                                 4 * kTileWarps * sizeof(double) + 2 * kTileWarps * sizeof(int) + 128;
+// Every CTA owns one contiguous range of rows (equal bytes of tiles per CTA, fixed when the
+// tiles are built) and streams it through a CTA-wide shared-memory ring of 1-D bulk async
+// copies (cp.async.bulk + mbarrier complete_tx) of whole rows, up to a slot per copy, in the
+// order of a copy list written with the plan; the warp that is the last to finish with a slot
+// issues the copy that takes it next.  The 16 warps work on the rows of one batch at a time.
+// A row is handled by L = 2^lg threads (8 or 16 lanes for rows of at most 64 / 128 double2
+// chunks -- four or two rows per warp step --, a warp, or 2..16 warps for more than 512
+// classes); thread t owns the chunks (t mod L) + L k (k < 8) of the rows (t div L) + (512 / L) i
+// of the batch, so Pi_b and its share of U_b stay in registers for the whole batch.  A row step
+// costs 8 16-byte shared loads, 32 DFMA, a shuffle butterfly of lg levels (plus one named
+// barrier across the warps of a wide row) and one division; the weight of a row travels with
+// the row (column n_cls of the tile).  At the end of a batch the consumers add their shares in
+// fixed order through shared memory and store U_b; the class sums of the next batch are already
+// on their way into the registers.  No global atomics, fences or queues: the only global
+// traffic of the pass is the tile stream (contiguous per CTA), Pi_b in and U_b out.
+// A batch that straddles two CTAs' ranges is two segments with a U vector each; the gather
+// kernel adds them like two batches.
+constexpr int kTileConsumers = kTileWarps;
+constexpr int kTilePassThreads = kTileThreads;
+constexpr int kTileRingBytes = 160 * 1024;
+constexpr int kTileSlotBytes = 52 * 1024;                        // default slot: three per ring
+constexpr int kTileScratchBytes = 64 * 1024;                     // [row slices][class vector]
+constexpr int kTileMaxSlots = 16;
+constexpr size_t kTilePassSmem = kTileRingBytes + kTileScratchBytes +
+                                 2 * kTileMaxSlots * sizeof(uint64_t) +
+                                 2 * kTileWarps * sizeof(double) + 128;
 
-struct TilePlan {          // one per CTA
-    int32_t tw;            // team width of this CTA
-    int32_t klass;         // log2(tw): its teams take the work items of this width class
+struct TileSeg {           // the rows of one batch inside one CTA's range
+    int64_t v_off;         // its first row in V (doubles)
+    int64_t p_off;         // Pi_b (doubles)
+    int64_t u_dst;         // where the segment's column sums go (doubles in u_sum)
+    int32_t r_pad;         // row stride of the tile = length of the class vectors (doubles)
+    int32_t n_cls;         // classes; column n_cls of a row holds the row's weight
+    int32_t lg;            // log2 of the threads per row: 3, 4, 5 (one warp), 6..9 (2..16 warps)
+    int32_t n_rows;
+    int32_t fit, n_copies; // rows per copy (the last one takes what is left), copies
+    int32_t batch;
+    int32_t pad[3];
+};
+static_assert(sizeof(TileSeg) == 64, "one record per 64-byte line");
+
+struct TileCta {           // one per CTA: its segments
+    int32_t seg0, n_segs, n_copies, pad;
 };
 
-__device__ __forceinline__ void team_barrier(int id, int threads) {
+struct TileCursor {        // the copy that takes a freed slot: n_slots copies ahead of the warps
+    int64_t v_off;
+    int32_t r_pad, n_rows, fit, n_copies;
+};
+__device__ __forceinline__ TileCursor tile_cursor(const TileSeg *sg) {
+    TileCursor c;
+    c.v_off = sg->v_off;
+    c.r_pad = sg->r_pad;
+    c.n_rows = sg->n_rows;
+    c.fit = sg->fit;
+    c.n_copies = sg->n_copies;
+    return c;
+}
+
+__device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+#ifdef MXB_TILE_TRACE
+// development aid (never in the product build): per CTA and warp: cycles blocked on the ring,
+// in row steps, in the end-of-batch exchange; total
+__device__ long long g_tile_trace[160 * kTileWarps * 8];
+#endif
 
-template <int NKMAX, int RU>
-__device__ __forceinline__ void tile_batch(const TileDesc &d, const TileItem &it, int tw, int team, int tt,
-                                           const double *__restrict__ v,
-                                           const double *__restrict__ pi_cls,
-                                           const double *__restrict__ w, double *__restrict__ u_out,
-                                           double *__restrict__ u_sum, int *__restrict__ done,
-                                           uint32_t ring_u32, int ring_bytes, uint32_t bars_u32,
-                                           double *red, int *ired, uint32_t &phase_bits,
-                                           int &parity, int &bad) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nk = d.nk;
-    const int tthreads = 32 * tw;
-    const uint32_t row_bytes = (uint32_t)d.c_pad * 8u;
-    const int ns = min(kTileMaxStages, ring_bytes / (int)row_bytes);
-    const bool producer = tt == 0;
-    const int n_rows = it.r1 - it.r0;
-    const double *tile = v + d.v_off + (size_t)it.r0 * d.c_pad;
-    if (producer) {
-        for (int q = 0; q < ns && q < n_rows; ++q) {
-            mbar_expect_tx_u32(bars_u32 + 8u * q, row_bytes);
-            bulk_load_u32(ring_u32 + (uint32_t)q * row_bytes, tile + (size_t)q * d.c_pad, row_bytes,
-                          bars_u32 + 8u * q);
-        }
-    }
-    const double2 *pcls = reinterpret_cast<const double2 *>(pi_cls + d.p_off) + tt;
-    double2 p[NKMAX], u[NKMAX];
-#pragma unroll
-    for (int k = 0; k < NKMAX; ++k) {
-        p[k] = k < nk ? pcls[k * tthreads] : make_double2(0.0, 0.0);
-        u[k] = make_double2(0.0, 0.0);
-    }
-    // an item holds at most 32 rows (128-row batches, up to four items of at least 16 rows):
-    // lane l keeps the weight of row l, so the row loop has no global load of its own
-    const double w_lane = lane < n_rows ? w[d.row0 + it.r0 + lane] : 0.0;
-    int q = 0;
-    for (int r = 0; r < n_rows; r += RU) {
-        // RU rows per step: their dependency chains (shared loads -> dot product -> butterfly ->
-        // division -> column-sum update) overlap; the sums are formed in row order as before
-        double2 x[RU][NKMAX];
-        double dot[RU], wr[RU];
-        int qs[RU];
-        bool have[RU];
-#pragma unroll
-        for (int g = 0; g < RU; ++g) {
-            have[g] = r + g < n_rows;
-            wr[g] = have[g] ? __shfl_sync(0xffffffffu, w_lane, (r + g) & 31) : 0.0;
-            qs[g] = q;
-            if (have[g]) {
-                mbar_wait_u32(bars_u32 + 8u * q, (phase_bits >> q) & 1u);
-                phase_bits ^= 1u << q;
-                if (++q == ns) q = 0;
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < RU; ++g) {
-            const uint32_t src = ring_u32 + (uint32_t)qs[g] * row_bytes + (uint32_t)tt * 16u;
-            double dx = 0.0, dy = 0.0;
-#pragma unroll
-            for (int k = 0; k < NKMAX; ++k) {
-                x[g][k] = (have[g] && k < nk) ? lds_v2_f64(src + (uint32_t)(k * tthreads) * 16u)
-                                              : make_double2(0.0, 0.0);
-                dx = fma(x[g][k].x, p[k].x, dx);
-                dy = fma(x[g][k].y, p[k].y, dy);
-            }
-            dot[g] = dx + dy;
-        }
-#pragma unroll
-        for (int g = 0; g < RU; ++g) dot[g] = warp_sum(dot[g]);
-        if (tw > 1) {
-            // warp totals -> red[parity][g][warp]; after the team barrier every thread adds the
-            // tw totals of its team in warp order (lanes < tw fetch, butterfly, broadcast)
-            if (lane == 0) {
-#pragma unroll
-                for (int g = 0; g < RU; ++g) red[(parity * RU + g) * kTileWarps + warp] = dot[g];
-            }
-            team_barrier(1 + team, tthreads);
-#pragma unroll
-            for (int g = 0; g < RU; ++g) {
-                double t = lane < tw ? red[(parity * RU + g) * kTileWarps + team * tw + lane] : 0.0;
-                for (int off = tw >> 1; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-                dot[g] = __shfl_sync(0xffffffffu, t, 0);
-            }
-            parity ^= 1;
-        }
-        // every thread of the team holds its cells of these rows in registers: refill the slots
-        // (tw > 1: the team barrier above orders the reads before the refill; one warp: its
-        // lanes have converged in the butterfly, the explicit __syncwarp says so)
-        if (tw == 1) __syncwarp();
-        if (producer) {
-#pragma unroll
-            for (int g = 0; g < RU; ++g) {
-                if (have[g] && r + g + ns < n_rows) {
-                    mbar_expect_tx_u32(bars_u32 + 8u * qs[g], row_bytes);
-                    bulk_load_u32(ring_u32 + (uint32_t)qs[g] * row_bytes,
-                                  tile + (size_t)(r + g + ns) * d.c_pad, row_bytes,
-                                  bars_u32 + 8u * qs[g]);
-                }
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < RU; ++g) {
-            double coef = 0.0;
-            if (wr[g] != 0.0) {
-                coef = wr[g] / dot[g];
-                bad |= (dot[g] == 0.0);
-            }
-#pragma unroll
-            for (int k = 0; k < NKMAX; ++k) {
-                u[k].x = fma(coef, x[g][k].x, u[k].x);
-                u[k].y = fma(coef, x[g][k].y, u[k].y);
-            }
-        }
-    }
-    if (d.ng == 1) {        // the item is the whole batch
-        double2 *uo = reinterpret_cast<double2 *>(u_sum + d.p_off) + tt;
-#pragma unroll
-        for (int k = 0; k < NKMAX; ++k)
-            if (k < nk) uo[k * tthreads] = u[k];
-        return;
-    }
-    // Store this item's share; the item of the batch that finishes last adds the ng shares in
-    // item order (so the sum does not depend on which one that is) into U_b.  `done` counts
-    // the finished items of the batch and is put back to zero by the last one.
-    double2 *uo = reinterpret_cast<double2 *>(u_out + d.u_off + (size_t)it.g * d.c_pad) + tt;
-#pragma unroll
-    for (int k = 0; k < NKMAX; ++k)
-        if (k < nk) uo[k * tthreads] = u[k];
-    __threadfence();
-    int last = 0;
-    if (tw > 1) {
-        team_barrier(1 + team, tthreads);              // every warp's stores are fenced
-        // (a slot of its own: the team's next queue index goes through ired[team] with no
-        // barrier between this read and that write)
-        if (tt == 0) ired[kTileWarps + team] = atomicAdd(done + it.batch, 1) == d.ng - 1;
-        team_barrier(1 + team, tthreads);
-        last = ired[kTileWarps + team];
-    } else {
-        if (lane == 0) last = atomicAdd(done + it.batch, 1) == d.ng - 1;
-        last = __shfl_sync(0xffffffffu, last, 0);
-    }
-    if (!last) return;
-    __threadfence();
-    const double2 *sh = reinterpret_cast<const double2 *>(u_out + d.u_off) + tt;
-    double2 *us = reinterpret_cast<double2 *>(u_sum + d.p_off) + tt;
-    const int row_d2 = d.c_pad >> 1;
-#pragma unroll
-    for (int k = 0; k < NKMAX; ++k) {
-        if (k < nk) {
-            double2 acc = __ldcg(sh + k * tthreads);
-            for (int g = 1; g < d.ng; ++g) {
-                const double2 o = __ldcg(sh + (size_t)g * row_d2 + k * tthreads);
-                acc.x += o.x;
-                acc.y += o.y;
-            }
-            us[k * tthreads] = acc;
-        }
-    }
-    if (tt == 0) done[it.batch] = 0;
-}
-
-__global__ void __launch_bounds__(kTileThreads, 1)
-tile_pass_kernel(const TileDesc *__restrict__ desc, const TileItem *__restrict__ items,
-                 const TilePlan *__restrict__ plan, const int *__restrict__ class_ptr,
-                 const int *__restrict__ class_items, int *__restrict__ next_item,
-                 const double *__restrict__ v, const double *__restrict__ pi_cls,
-                 const double *__restrict__ w, EmState *__restrict__ st,
-                 double *__restrict__ u_out, double *__restrict__ u_sum, int *__restrict__ done) {
+__global__ void __launch_bounds__(kTilePassThreads, 1)
+tile_pass_kernel(const TileCta *__restrict__ ctas, const TileSeg *__restrict__ segs,
+                 const double *__restrict__ v,
+                 const double *__restrict__ pi_cls, EmState *__restrict__ st,
+                 double *__restrict__ u_sum, uint32_t slot_bytes, int n_slots) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tile_smem + kTileRingBytes);   // [16][16]
-    double *red = reinterpret_cast<double *>(bars + kTileWarps * kTileMaxStages);  // [2][2][16]
-    int *ired = reinterpret_cast<int *>(red + 4 * kTileWarps);                     // [2][16]
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const TilePlan pl = plan[blockIdx.x];
-    const int tw = pl.tw;
-    const int team = warp / tw, tt = tid - team * 32 * tw;
-    const int ring_bytes = kTileRingBytes / (kTileWarps / tw);        // this team's share
-    const uint32_t ring_u32 = smem_u32(tile_smem) + (uint32_t)(team * ring_bytes);
-    const uint32_t bars_u32 = smem_u32(bars) + (uint32_t)(team * kTileMaxStages) * 8u;
-    if (tt == 0) {
-        for (int q = 0; q < kTileMaxStages; ++q) mbar_init(bars + team * kTileMaxStages + q, 1);
+    double *scratch = reinterpret_cast<double *>(tile_smem + kTileRingBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(tile_smem + kTileRingBytes + kTileScratchBytes);
+    int *freed = reinterpret_cast<int *>(full + kTileMaxSlots);   // warps done with a slot ([16], padded)
+    double *red = reinterpret_cast<double *>(full + 2 * kTileMaxSlots);  // [2][16]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int q = 0; q < n_slots; ++q) {
+            mbar_init(full + q, 1);
+            freed[q] = 0;
+        }
         mbar_init_fence();
     }
     __syncthreads();
     pdl_wait();               // the class sums of this iteration are complete
     pdl_launch_dependents();
     if (st->done) return;
-    int bad = 0, parity = 0;
-    uint32_t phase_bits = 0;
-    // The teams of all CTAs of a width class draw their items from one list (longest first)
-    // through a counter that tile_pi_kernel put back to zero: which team handles an item does
-    // not change any result, so this costs no determinism and evens out the load.
-    const int k = pl.klass;
-    const int list0 = class_ptr[k], list1 = class_ptr[k + 1];
-    const int lane = tid & 31;
-    for (;;) {
-        int i = 0;
-        if (tw > 1) {
-            if (tt == 0) ired[team] = atomicAdd(next_item + k, 1);
-            team_barrier(1 + team, 32 * tw);
-            i = ired[team];
-            team_barrier(1 + team, 32 * tw);
-        } else {
-            if (lane == 0) i = atomicAdd(next_item + k, 1);
-            i = __shfl_sync(0xffffffffu, i, 0);
+    const TileCta cta = ctas[blockIdx.x];
+    const uint32_t ring_u32 = smem_u32(tile_smem);
+    const uint32_t full_u32 = smem_u32(full);
+    const TileSeg *my_segs = segs + cta.seg0;
+    // The copy cursor (kept by every warp: any of them may be the one that fills a slot): primed
+    // n_slots copies ahead by thread 0, then moved one copy per copy consumed.
+    int ps = 0, pc = 0;
+    TileCursor cur_p = tile_cursor(my_segs), next_p = cur_p;
+    if (cta.n_segs > 1) next_p = tile_cursor(my_segs + 1);
+    auto cursor_issue = [&](int q) {       // copy (ps, pc) -> slot q
+        const int row0 = pc * cur_p.fit;
+        const uint32_t bytes = (uint32_t)(min(cur_p.fit, cur_p.n_rows - row0) * cur_p.r_pad) * 8u;
+        mbar_expect_tx_u32(full_u32 + 8u * q, bytes);
+        bulk_load_u32(ring_u32 + (uint32_t)q * slot_bytes, v + cur_p.v_off + (size_t)row0 * cur_p.r_pad,
+                      bytes, full_u32 + 8u * q);
+    };
+    auto cursor_advance = [&]() {
+        if (++pc == cur_p.n_copies) {
+            pc = 0;
+            ++ps;
+            cur_p = next_p;
+            if (ps + 1 < cta.n_segs) next_p = tile_cursor(my_segs + ps + 1);
         }
-        if (list0 + i >= list1) break;
-        const TileItem it = items[class_items[list0 + i]];
-        const TileDesc d = desc[it.batch];
-        if (d.nk <= 2)
-            tile_batch<2, 2>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
-                          ring_bytes, bars_u32, red, ired, phase_bits, parity, bad);
-        else if (d.nk <= 4)
-            tile_batch<4, 2>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
-                          ring_bytes, bars_u32, red, ired, phase_bits, parity, bad);
-        else
-            tile_batch<8, 1>(d, it, tw, team, tt, v, pi_cls, w, u_out, u_sum, done, ring_u32,
-                          ring_bytes, bars_u32, red, ired, phase_bits, parity, bad);
-        // the next batch may prime the ring at once: the team barrier of the last row (tw > 1)
-        // or the warp's own program order (tw == 1) came after every read of the ring
+    };
+    for (int q = 0; q < n_slots && q < cta.n_copies; ++q) {
+        if (tid == 0) cursor_issue(q);
+        cursor_advance();
     }
-    if (__any_sync(0xffffffffu, bad) && (tid & 31) == 0) atomicAdd(&st->bad, 1);
+
+#ifdef MXB_TILE_TRACE
+    long long t_wait = 0, t_step = 0, t_red = 0, t_fill = 0;
+    const long long t_begin = clock64();
+#endif
+    constexpr int K = 8;
+    int j = 0, slot = 0, bad = 0, parity = 0;
+    uint32_t phase = 0;
+    double2 p[K], u[K];
+    TileSeg sg = segs[cta.seg0];
+    int L = 1 << sg.lg, idx = tid & (L - 1);
+    int kl = min(K, max(0, (((sg.n_cls + 1) >> 1) - idx + L - 1) >> sg.lg));
+    {
+        const double2 *pcls = reinterpret_cast<const double2 *>(pi_cls + sg.p_off) + idx;
+#pragma unroll
+        for (int k = 0; k < K; ++k) p[k] = k < kl ? pcls[k << sg.lg] : make_double2(0.0, 0.0);
+    }
+    for (int si = 0; si < cta.n_segs; ++si) {
+        // the record of the next segment is on its way while this one is worked on
+        TileSeg sg_next = sg;
+        if (si + 1 < cta.n_segs) sg_next = my_segs[si + 1];
+#pragma unroll
+        for (int k = 0; k < K; ++k) u[k] = make_double2(0.0, 0.0);
+        const int lg = sg.lg;
+        const int tw = lg > 5 ? 1 << (lg - 5) : 1;                 // warps per row
+        const int rows_per_sweep = (32 * kTileConsumers) >> lg;
+        const uint32_t row_bytes = (uint32_t)sg.r_pad * 8u;
+        const uint32_t chunk0 = (uint32_t)min(idx, ((sg.n_cls + 1) >> 1) - 1) * 16u;   // see the loads below
+        const uint32_t chunk_stride = 16u << lg;
+        const int k_last = max(kl, 1) - 1;
+        int row = tid >> lg;                                       // this thread's next row
+        const int warp_row = (lg >= 5 ? tid >> lg : (warp << (5 - lg)));   // first row of the warp's step
+        const int warp0 = warp & ~(tw - 1);
+        for (int c = 0; c < sg.n_copies; ++c, ++j) {
+            const int copy_row0 = c * sg.fit;
+            const int row_end = min(copy_row0 + sg.fit, sg.n_rows);
+            // rows of this warp (or team of warps) inside the copy: warp-uniform test
+            int wrow = warp_row + (row - (tid >> lg));
+            // (every warp waits for every copy, also for one that holds none of its rows: its
+            // count below must not land in the slot's previous round)
+#ifdef MXB_TILE_TRACE
+            const long long tw0 = clock64();
+#endif
+            mbar_wait_u32(full_u32 + 8u * slot, phase);
+#ifdef MXB_TILE_TRACE
+            const long long tw1 = clock64();
+            t_wait += tw1 - tw0;
+#endif
+            if (wrow < row_end) {
+                do {
+                    const bool have = row < row_end;
+                    // Branch-free loads: a chunk this thread does not own (k >= kl) or a row past
+                    // the end of the batch reads a cell that exists (finite) instead; its class
+                    // sum p[k] is zero and the weight of a missing row is zero, so neither
+                    // reaches a result.
+                    const uint32_t src = ring_u32 + (uint32_t)slot * slot_bytes +
+                                         (uint32_t)((have ? row : wrow) - copy_row0) * row_bytes;
+                    double2 x[K];
+                    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        x[k] = lds_v2_f64(src + chunk0 + (uint32_t)min(k, k_last) * chunk_stride);
+                    double wr;
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(wr) : "r"(src + (uint32_t)sg.n_cls * 8u) : "memory");
+                    if (!have) wr = 0.0;
+#pragma unroll
+                    for (int k = 0; k < K; k += 2) {
+                        d0 = fma(x[k].x, p[k].x, d0);
+                        d1 = fma(x[k].y, p[k].y, d1);
+                        d2 = fma(x[k + 1].x, p[k + 1].x, d2);
+                        d3 = fma(x[k + 1].y, p[k + 1].y, d3);
+                    }
+                    double dot = (d0 + d1) + (d2 + d3);
+                    if (lg >= 5) {
+                        dot = warp_sum(dot);
+                        if (tw > 1) {
+                            // warp totals -> red[parity][warp]; after the barrier of the row's
+                            // warps every thread adds them in warp order
+                            if (lane == 0) red[parity * kTileWarps + warp] = dot;
+                            named_barrier(1 + (warp0 >> 1), 32 * tw);
+                            double t = lane < tw ? red[parity * kTileWarps + warp0 + lane] : 0.0;
+                            for (int o = tw >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                            dot = __shfl_sync(0xffffffffu, t, 0);
+                            parity ^= 1;
+                        }
+                    } else if (lg == 4) {
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                    } else {
+#pragma unroll
+                        for (int o = 4; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                    }
+                    double coef = 0.0;
+                    if (wr != 0.0) {
+                        coef = wr / dot;
+                        bad |= (dot == 0.0);
+                    }
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        u[k].x = fma(coef, x[k].x, u[k].x);
+                        u[k].y = fma(coef, x[k].y, u[k].y);
+                    }
+                    row += rows_per_sweep;
+                    wrow += rows_per_sweep;
+                } while (wrow < row_end);
+            }
+#ifdef MXB_TILE_TRACE
+            const long long tw2 = clock64();
+            t_step += tw2 - tw1;
+#endif
+            // done with the slot (every lane's reads of it have been consumed by now): the warp
+            // that is the last one to say so fills it again
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(freed + slot, 1) == kTileConsumers - 1) {
+                    freed[slot] = 0;
+                    __threadfence_block();
+                    if (j + n_slots < cta.n_copies) cursor_issue(slot);
+                }
+            }
+            if (j + n_slots < cta.n_copies) cursor_advance();
+#ifdef MXB_TILE_TRACE
+            t_fill += clock64() - tw2;
+#endif
+            if (++slot == n_slots) { slot = 0; phase ^= 1u; }
+        }
+#ifdef MXB_TILE_TRACE
+        const long long tr0 = clock64();
+#endif
+        // ---- end of the batch (segment): add the consumers' shares in fixed order ----
+        if (lg < 5) {
+            // the groups of a warp first (pairwise, fixed)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                for (int o = L; o < 32; o <<= 1) {
+                    u[k].x += __shfl_xor_sync(0xffffffffu, u[k].x, o);
+                    u[k].y += __shfl_xor_sync(0xffffffffu, u[k].y, o);
+                }
+            }
+        }
+        const int chunks = (sg.n_cls + 1) >> 1;     // double2 chunks that hold class values
+        const int slice = lg >= 5 ? tid >> lg : warp;              // of the scratch: [slices][chunks]
+        const int n_slices = lg >= 5 ? (32 * kTileConsumers) >> lg : kTileConsumers;
+        // the class sums of the next batch start their way into the registers now
+        const int kl_cur = kl;
+        const int idx_cur = idx;
+        L = 1 << sg_next.lg;
+        idx = tid & (L - 1);
+        kl = min(K, max(0, (((sg_next.n_cls + 1) >> 1) - idx + L - 1) >> sg_next.lg));
+        if (si + 1 < cta.n_segs) {
+            const double2 *pcls = reinterpret_cast<const double2 *>(pi_cls + sg_next.p_off) + idx;
+#pragma unroll
+            for (int k = 0; k < K; ++k) p[k] = k < kl ? pcls[k << sg_next.lg] : make_double2(0.0, 0.0);
+        }
+        named_barrier(9, 32 * kTileConsumers);      // the scratch of the previous batch has been read
+        if (lg >= 5 || lane < (1 << lg)) {
+            double2 *dst = reinterpret_cast<double2 *>(scratch) + (size_t)slice * chunks + idx_cur;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (k < kl_cur) dst[k << lg] = u[k];
+        }
+        named_barrier(9, 32 * kTileConsumers);
+        {
+            const double2 *sc = reinterpret_cast<const double2 *>(scratch);
+            double2 *out = reinterpret_cast<double2 *>(u_sum + sg.u_dst);
+            for (int c = tid; c < chunks; c += 32 * kTileConsumers) {
+                double2 acc = sc[c];
+                for (int t = 1; t < n_slices; ++t) {
+                    const double2 o = sc[(size_t)t * chunks + c];
+                    acc.x += o.x;
+                    acc.y += o.y;
+                }
+                out[c] = acc;
+            }
+        }
+        sg = sg_next;
+#ifdef MXB_TILE_TRACE
+        t_red += clock64() - tr0;
+#endif
+    }
+#ifdef MXB_TILE_TRACE
+    if (lane == 0) {
+        long long *tr = g_tile_trace + ((size_t)blockIdx.x * kTileWarps + warp) * 8;
+        tr[0] = clock64() - t_begin; tr[1] = t_wait; tr[2] = t_step; tr[3] = t_fill; tr[4] = t_red;
+        tr[5] = cta.n_segs; tr[6] = cta.n_copies; tr[7] = 1;
+    }
+#endif
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(&st->bad, 1);
 }
 
 // T_j = sum over batches of U_b[cmap_b[j]], batches in ascending order; the batches are split
@@ -578,8 +632,8 @@ constexpr int kGatherUnroll = 8;
 
 __global__ void __launch_bounds__(kGatherThreads)
 tile_gather_kernel(const unsigned short *__restrict__ cmap, int hs, int n_cols, int64_t ld,
-                   const int64_t *__restrict__ p_off, int n_batches,
-                   const double *__restrict__ u_sum, const EmState *__restrict__ st,
+                   const int *__restrict__ ent_batch, const int64_t *__restrict__ ent_off,
+                   int n_ent, const double *__restrict__ u_sum, const EmState *__restrict__ st,
                    double *__restrict__ partials) {
     pdl_wait();
     pdl_launch_dependents();
@@ -587,20 +641,20 @@ tile_gather_kernel(const unsigned short *__restrict__ cmap, int hs, int n_cols, 
     const int j = blockIdx.x * kGatherThreads + threadIdx.x;
     if (j >= ld) return;
     const int part = blockIdx.y, n_part = gridDim.y;
-    const int b0 = (int)((int64_t)n_batches * part / n_part);
-    const int b1 = (int)((int64_t)n_batches * (part + 1) / n_part);
+    const int e0 = (int)((int64_t)n_ent * part / n_part);
+    const int e1 = (int)((int64_t)n_ent * (part + 1) / n_part);
     double t = 0.0;
     if (j < n_cols) {
-        int b = b0;
-        for (; b + kGatherUnroll <= b1; b += kGatherUnroll) {
+        int e = e0;
+        for (; e + kGatherUnroll <= e1; e += kGatherUnroll) {
             double x[kGatherUnroll];
 #pragma unroll
             for (int q = 0; q < kGatherUnroll; ++q)
-                x[q] = u_sum[p_off[b + q] + cmap[(size_t)(b + q) * hs + j]];
+                x[q] = u_sum[ent_off[e + q] + cmap[(size_t)ent_batch[e + q] * hs + j]];
 #pragma unroll
             for (int q = 0; q < kGatherUnroll; ++q) t += x[q];
         }
-        for (; b < b1; ++b) t += u_sum[p_off[b] + cmap[(size_t)b * hs + j]];
+        for (; e < e1; ++e) t += u_sum[ent_off[e] + cmap[(size_t)ent_batch[e] * hs + j]];
     }
     partials[(size_t)part * ld + j] = t;
 }
