@@ -445,9 +445,14 @@ static int em_pack_tiles(mxb_em *em) {
     const uint32_t slot_bytes = (uint32_t)round_up(std::max<int64_t>(kTileSlotBytes, (int64_t)max_r_pad * 8), 1024);
     const int n_slots = std::min(kTileMaxSlots, kTileRingBytes / (int)slot_bytes);
     if (n_slots < 2) return give_up(false, "rows too long for the ring");
-    // Plan of the pass: CTA c gets the rows between the c-th and the (c+1)-th n_cta-quantile of
-    // the tile bytes (+ a fixed cost per batch for its class vectors and the share exchange),
-    // cut at multiples of four rows; the part of a batch inside one CTA's range is a segment.
+    // Plan of the pass.  The rows are dealt to the CTAs in order, every CTA one contiguous range;
+    // the part of a batch inside a CTA's range is a segment, cut at copy boundaries.  A CTA takes
+    // rows until either of its two clocks reaches the target T: its bytes at the SM's share of
+    // HBM (22 B per cycle) or its warps' time (cycle counters of the kernel at config 2: ~4200
+    // cycles per segment for the exchange at its end and the wait for the next class sums, ~500
+    // per copy for waiting, handing back and refilling, and a row step of 440 .. 1900 cycles for
+    // every 512 >> lg rows of a copy); the smallest T that needs no more CTAs than there are SMs
+    // is found by bisection.
     std::vector<TileCta> ctas;
     std::vector<TileSeg> segs;
     std::vector<int> ent_batch;           // gather entries: (batch, offset of a U vector)
@@ -455,82 +460,95 @@ static int em_pack_tiles(mxb_em *em) {
     int64_t extra_cells = 0;              // U vectors of the second, third.. segment of a batch
     int n_copy = 0;
     {
-        // Cost of a segment in SM cycles (measured with the kernel's cycle counters at config 2):
-        // ~3200 for the exchange at its end, ~650 per copy (wait, hand-back, refill), and per row
-        // the larger of its bytes at the SM's share of HBM (22 B per cycle) and of its row step
-        // (~1000 cycles for the 512 >> lg rows the CTA handles at a time).
+        static const double step_cycles[10] = {440, 440, 440, 440, 440, 600, 1000, 1300, 1626, 1900};
+        const double seg_cycles = 4200.0, copy_cycles = 500.0, bytes_per_cycle = 22.0;
         auto rows_per_copy = [&](const TileDesc &d) {
             const int per_step = d.lg < 5 ? 32 >> d.lg : 1;
             return std::max(per_step, (int)(slot_bytes / (uint32_t)(d.r_pad * 8)) / per_step * per_step);
         };
-        auto row_cost_of = [&](const TileDesc &d) {
-            return std::max((double)d.r_pad * 8 / 22.0, 1000.0 / (double)(512 >> d.lg)) +
-                   650.0 / rows_per_copy(d);
+        auto copy_cost = [&](const TileDesc &d, int rows) {      // warps' time for a copy of `rows`
+            return copy_cycles + ceil_div(rows, 512 >> d.lg) * step_cycles[d.lg];
         };
-        const double seg_cost = 3200.0;
-        std::vector<double> suffix((size_t)nb + 1, 0.0);     // cost of batches b.. as whole segments
-        for (int b = nb - 1; b >= 0; --b)
-            suffix[(size_t)b] = suffix[(size_t)b + 1] + seg_cost + desc[(size_t)b].n_rows * row_cost_of(desc[(size_t)b]);
-        const int n_cta = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, ceil_div(n, 32)));
-        int c = 0;
-        double budget = suffix[0] / n_cta, used = 0.0;       // of the CTA being filled
-        TileCta cur{0, 0, 0, 0};
-        auto close_cta = [&](double remaining) {
-            if (cur.n_segs > 0) ctas.push_back(cur);
-            cur.seg0 = (int)segs.size();
-            cur.n_segs = cur.n_copies = 0;
-            ++c;
-            used = 0.0;
-            budget = remaining / std::max(1, n_cta - c);     // what is left, shared by the CTAs left
-        };
-        for (int b = 0; b < nb; ++b) {
-            const TileDesc &d = desc[(size_t)b];
-            const double row_cost = row_cost_of(d);
-            int r = 0, seg_no = 0;
-            while (r < d.n_rows) {
-                // rows of this batch that still fit into the CTA's budget
-                int take = d.n_rows - r;
-                const double remaining = suffix[(size_t)b + 1] + seg_cost + take * row_cost;
-                if (c + 1 < n_cta && used + seg_cost + take * row_cost > budget) {
-                    const double room = budget - used - seg_cost;
-                    int fit_rows = room > 0 ? (int)(room / row_cost) / 4 * 4 : 0;
-                    if (fit_rows < 8) fit_rows = 0;                              // no crumbs
-                    else if (take - fit_rows < 8) fit_rows = take;
-                    // a small overshoot is better than one more segment
-                    if (fit_rows < take && used + seg_cost + take * row_cost < 1.04 * budget) fit_rows = take;
-                    take = fit_rows;
+        const int max_cta = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, ceil_div(n, 32)));
+        // deal the rows for target T; with `emit` the segments are written down
+        auto deal = [&](double T, bool emit) {
+            int used_ctas = 0;
+            double warp_t = 0.0, mem_t = 0.0;
+            TileCta cur{(int)segs.size(), 0, 0, 0};
+            auto close_cta = [&]() {
+                if (warp_t > 0.0) {
+                    ++used_ctas;
+                    if (emit) ctas.push_back(cur);
                 }
-                if (take == 0) {
-                    if (cur.n_segs == 0) take = std::min(d.n_rows - r, 8);       // a CTA never stays empty
-                    else { close_cta(remaining); continue; }
+                cur.seg0 = (int)segs.size();
+                cur.n_segs = cur.n_copies = 0;
+                warp_t = mem_t = 0.0;
+            };
+            for (int b = 0; b < nb; ++b) {
+                const TileDesc &d = desc[(size_t)b];
+                const int fit = rows_per_copy(d);
+                const double row_mem = (double)d.r_pad * 8 / bytes_per_cycle;
+                int r = 0, seg_no = 0;
+                while (r < d.n_rows) {
+                    const int left = d.n_rows - r;
+                    // whole copies of this batch that still fit under T on both clocks
+                    int take = 0;
+                    double w = warp_t + seg_cycles, m = mem_t;
+                    while (take < left) {
+                        const int rows = std::min(fit, left - take);
+                        if (std::max(w + copy_cost(d, rows), m + rows * row_mem) > T) break;
+                        w += copy_cost(d, rows);
+                        m += rows * row_mem;
+                        take += rows;
+                    }
+                    if (take < left && left - take < 8) {         // no crumbs for the next CTA
+                        w += copy_cost(d, left - take);
+                        m += (left - take) * row_mem;
+                        take = left;
+                    }
+                    if (take == 0) {
+                        if (warp_t > 0.0) { close_cta(); continue; }
+                        take = std::min(fit, left);               // a CTA takes at least one copy
+                        w += copy_cost(d, take);
+                        m += take * row_mem;
+                    }
+                    if (emit) {
+                        TileSeg sg;
+                        memset(&sg, 0, sizeof(sg));
+                        sg.p_off = d.p_off;
+                        sg.u_dst = seg_no == 0 ? d.p_off : p_cells + extra_cells;
+                        if (seg_no > 0) extra_cells += d.r_pad;
+                        sg.r_pad = d.r_pad;
+                        sg.n_cls = d.n_cls;
+                        sg.lg = d.lg;
+                        sg.n_rows = take;
+                        sg.batch = b;
+                        sg.fit = fit;
+                        sg.n_copies = (int)ceil_div(take, fit);
+                        sg.v_off = d.v_off + (int64_t)r * d.r_pad;
+                        ent_batch.push_back(b);
+                        ent_off.push_back(sg.u_dst);
+                        cur.n_copies += sg.n_copies;
+                        n_copy += sg.n_copies;
+                        segs.push_back(sg);
+                        ++cur.n_segs;
+                    }
+                    warp_t = w;
+                    mem_t = m;
+                    r += take;
+                    ++seg_no;
                 }
-                TileSeg sg;
-                memset(&sg, 0, sizeof(sg));
-                sg.p_off = d.p_off;
-                sg.u_dst = seg_no == 0 ? d.p_off : p_cells + extra_cells;
-                if (seg_no > 0) extra_cells += d.r_pad;
-                sg.r_pad = d.r_pad;
-                sg.n_cls = d.n_cls;
-                sg.lg = d.lg;
-                sg.n_rows = take;
-                sg.batch = b;
-                ent_batch.push_back(b);
-                ent_off.push_back(sg.u_dst);
-                // its copies: whole rows, as many as a slot holds, a multiple of the rows of a
-                // warp step (32 >> lg for lg < 5) so that a step never straddles two copies
-                sg.fit = rows_per_copy(d);
-                sg.n_copies = (int)ceil_div(take, sg.fit);
-                sg.v_off = d.v_off + (int64_t)r * d.r_pad;
-                cur.n_copies += sg.n_copies;
-                n_copy += sg.n_copies;
-                segs.push_back(sg);
-                ++cur.n_segs;
-                used += seg_cost + take * row_cost;
-                r += take;
-                ++seg_no;
             }
+            close_cta();
+            return used_ctas;
+        };
+        double lo = 0.0, hi = 1.0;
+        while (deal(hi, false) > max_cta) hi *= 2.0;
+        for (int it = 0; it < 30; ++it) {
+            const double mid = 0.5 * (lo + hi);
+            if (deal(mid, false) > max_cta) lo = mid; else hi = mid;
         }
-        close_cta(0.0);
+        deal(hi, true);
     }
     const int n_cta = (int)ctas.size(), n_seg = (int)segs.size();
     const int n_ent = (int)ent_batch.size();
@@ -539,6 +557,28 @@ static int em_pack_tiles(mxb_em *em) {
                               ((double)p_cells + (double)u_cells) * 8 * 2;
     const double fp64_bytes = (double)n * (double)em->ld * 8;
     if (verbose) {
+        {   // invariants of the plan
+            std::vector<int> rows_of((size_t)nb, 0);
+            int errs = 0, next_seg = 0, copies_sum = 0;
+            for (const TileCta &c : ctas) {
+                if (c.seg0 != next_seg) ++errs;
+                int cc = 0;
+                for (int q = 0; q < c.n_segs; ++q) {
+                    const TileSeg &g = segs[(size_t)(c.seg0 + q)];
+                    const TileDesc &d = desc[(size_t)g.batch];
+                    if (g.v_off != d.v_off + (int64_t)rows_of[(size_t)g.batch] * d.r_pad) ++errs;
+                    rows_of[(size_t)g.batch] += g.n_rows;
+                    if (g.n_copies != (int)ceil_div(g.n_rows, g.fit)) ++errs;
+                    cc += g.n_copies;
+                }
+                if (cc != c.n_copies) ++errs;
+                copies_sum += cc;
+                next_seg += c.n_segs;
+            }
+            for (int b = 0; b < nb; ++b) if (rows_of[(size_t)b] != desc[(size_t)b].n_rows) ++errs;
+            fprintf(stderr, "[mxb tiles] plan check: %d errors, %d segs in ctas of %d, copies %d / %d\n", errs,
+                    next_seg, (int)segs.size(), copies_sum, n_copy);
+        }
         int64_t c_sum = 0, c_max = 0, wide = 0;
         for (int b = 0; b < nb; ++b) {
             c_sum += desc[(size_t)b].n_cls;

@@ -440,6 +440,7 @@ tile_pass_kernel(const TileCta *__restrict__ ctas, const TileSeg *__restrict__ s
 #endif
     constexpr int K = 8;
     int j = 0, slot = 0, bad = 0, parity = 0;
+    bool prev_small = true;
     uint32_t phase = 0;
     double2 p[K], u[K];
     TileSeg sg = segs[cta.seg0];
@@ -466,6 +467,10 @@ tile_pass_kernel(const TileCta *__restrict__ ctas, const TileSeg *__restrict__ s
         int row = tid >> lg;                                       // this thread's next row
         const int warp_row = (lg >= 5 ? tid >> lg : (warp << (5 - lg)));   // first row of the warp's step
         const int warp0 = warp & ~(tw - 1);
+        // (the warps of a row agree on the buffer of their partial dot products: the teams of
+        // the previous batch may have taken different numbers of steps; every thread has passed
+        // the barrier of the exchange since its last read of `red`)
+        parity = 0;
         for (int c = 0; c < sg.n_copies; ++c, ++j) {
             const int copy_row0 = c * sg.fit;
             const int row_end = min(copy_row0 + sg.fit, sg.n_rows);
@@ -547,7 +552,8 @@ tile_pass_kernel(const TileCta *__restrict__ ctas, const TileSeg *__restrict__ s
             // that is the last one to say so fills it again
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
+                // (the reads of this warp have returned: the column-sum updates that consume
+                // them were issued before this atomic)
                 if (atomicAdd(freed + slot, 1) == kTileConsumers - 1) {
                     freed[slot] = 0;
                     __threadfence_block();
@@ -564,16 +570,6 @@ tile_pass_kernel(const TileCta *__restrict__ ctas, const TileSeg *__restrict__ s
         const long long tr0 = clock64();
 #endif
         // ---- end of the batch (segment): add the consumers' shares in fixed order ----
-        if (lg < 5) {
-            // the groups of a warp first (pairwise, fixed)
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                for (int o = L; o < 32; o <<= 1) {
-                    u[k].x += __shfl_xor_sync(0xffffffffu, u[k].x, o);
-                    u[k].y += __shfl_xor_sync(0xffffffffu, u[k].y, o);
-                }
-            }
-        }
         const int chunks = (sg.n_cls + 1) >> 1;     // double2 chunks that hold class values
         const int slice = lg >= 5 ? tid >> lg : warp;              // of the scratch: [slices][chunks]
         const int n_slices = lg >= 5 ? (32 * kTileConsumers) >> lg : kTileConsumers;
@@ -588,16 +584,33 @@ tile_pass_kernel(const TileCta *__restrict__ ctas, const TileSeg *__restrict__ s
 #pragma unroll
             for (int k = 0; k < K; ++k) p[k] = k < kl ? pcls[k << sg_next.lg] : make_double2(0.0, 0.0);
         }
-        named_barrier(9, 32 * kTileConsumers);      // the scratch of the previous batch has been read
+        if (lg < 5) {
+            // the groups of a warp first (pairwise, fixed)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                for (int o = 1 << lg; o < 32; o <<= 1) {
+                    u[k].x += __shfl_xor_sync(0xffffffffu, u[k].x, o);
+                    u[k].y += __shfl_xor_sync(0xffffffffu, u[k].y, o);
+                }
+            }
+        }
+        // Shares that fit into half of the scratch alternate between its halves: the barrier
+        // below then also says that the half written two batches ago has been read.  Otherwise
+        // one more barrier: the scratch of the previous batch has been read.
+        const bool small = n_slices * chunks * (int)sizeof(double2) <= kTileScratchBytes / 2;
+        if (!(small && prev_small)) named_barrier(9, 32 * kTileConsumers);
+        prev_small = small;
+        double2 *sc_base = reinterpret_cast<double2 *>(scratch) +
+                           (small && (si & 1) ? kTileScratchBytes / 2 / sizeof(double2) : 0);
         if (lg >= 5 || lane < (1 << lg)) {
-            double2 *dst = reinterpret_cast<double2 *>(scratch) + (size_t)slice * chunks + idx_cur;
+            double2 *dst = sc_base + (size_t)slice * chunks + idx_cur;
 #pragma unroll
             for (int k = 0; k < K; ++k)
                 if (k < kl_cur) dst[k << lg] = u[k];
         }
         named_barrier(9, 32 * kTileConsumers);
         {
-            const double2 *sc = reinterpret_cast<const double2 *>(scratch);
+            const double2 *sc = sc_base;
             double2 *out = reinterpret_cast<double2 *>(u_sum + sg.u_dst);
             for (int c = tid; c < chunks; c += 32 * kTileConsumers) {
                 double2 acc = sc[c];
