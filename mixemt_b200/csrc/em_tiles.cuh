@@ -337,7 +337,8 @@ constexpr int kTilePassThreads = kTileThreads;
 constexpr int kTileRingBytes = 160 * 1024;
 constexpr int kTileSlotBytes = 52 * 1024;                        // default slot: three per ring
 constexpr int kTileScratchBytes = 64 * 1024;                     // [row slices][class vector]
-constexpr int kTileMaxSlots = 16;
+constexpr int kTileMaxSlots = 6;                                 // named barriers 10..15
+constexpr int kTileSlotBarrier0 = 10;
 constexpr size_t kTilePassSmem = kTileRingBytes + kTileScratchBytes +
                                  2 * kTileMaxSlots * sizeof(uint64_t) +
                                  2 * kTileWarps * sizeof(double) + 128;
@@ -550,15 +551,25 @@ tile_pass_kernel(const TileCta *__restrict__ ctas, const TileSeg *__restrict__ s
 #endif
             // done with the slot (every lane's reads of it have been consumed by now): the warp
             // that is the last one to say so fills it again
+            // A counter tells which warp is the last one (nobody waits to find out); a named
+            // barrier per slot, on which the others only arrive, orders every warp's reads
+            // before the copy that overwrites them.
             __syncwarp();
+            int last = 0;
             if (lane == 0) {
-                // (the reads of this warp have returned: the column-sum updates that consume
-                // them were issued before this atomic)
-                if (atomicAdd(freed + slot, 1) == kTileConsumers - 1) {
+                __threadfence_block();
+                last = atomicAdd(freed + slot, 1) == kTileConsumers - 1;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                named_barrier(kTileSlotBarrier0 + slot, 32 * kTileConsumers);
+                if (lane == 0) {
                     freed[slot] = 0;
                     __threadfence_block();
                     if (j + n_slots < cta.n_copies) cursor_issue(slot);
                 }
+            } else {
+                asm volatile("bar.arrive %0, %1;" ::"r"(kTileSlotBarrier0 + slot), "r"(32 * kTileConsumers) : "memory");
             }
             if (j + n_slots < cta.n_copies) cursor_advance();
 #ifdef MXB_TILE_TRACE
