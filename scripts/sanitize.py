@@ -42,7 +42,7 @@ def main():
         props, read_mix, info, _ = em.run_em_device(dev, wts, a, inits=inits)
         assert np.isfinite(props).all() and np.isfinite(read_mix).all(), (n, h)
         dev.free()
-    # kernel 2 over class tiles: blocks of identical columns (narrow teams), a block of noise
+    # kernel 2 over class tiles: blocks of identical columns (8 lanes per row), a block of noise
     # rows in the middle (all columns distinct: 16 warps per row), several work items per batch,
     # and a row that underflows in linear space (log-space rescue step)
     n, h = 420, 5408

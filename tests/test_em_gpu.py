@@ -338,7 +338,7 @@ def test_class_tiles_equal_fp64_rows(phylo17, n_extra, n_multi):
     tile_gather kernels).  The same non-negative terms enter every sum, regrouped; results must
     equal the fp64-row pass (MXB_EM_NO_PACK=1) to rounding with identical iteration counts,
     and the oracle.  Noise rows in the middle make batches whose columns are all distinct
-    (the widest row teams: 16 warps per row)."""
+    (16 warps per row)."""
     import ctypes
     import os
     from mixemt_b200._lib import lib, check, ptr
