@@ -315,11 +315,11 @@ tile_pi_kernel(const unsigned short *__restrict__ perm, const unsigned int *__re
 }
 
 // ---- the pass ------------------------------------------------------------------------------
-// Every CTA owns one contiguous range of rows (equal bytes of tiles per CTA, fixed when the
-// tiles are built) and streams it through a CTA-wide shared-memory ring of 1-D bulk async
-// copies (cp.async.bulk + mbarrier complete_tx) of whole rows, up to a slot per copy, in the
-// order of a copy list written with the plan; the warp that is the last to finish with a slot
-// issues the copy that takes it next.  The 16 warps work on the rows of one batch at a time.
+// Every CTA owns one contiguous range of rows (ranges of equal cost, fixed when the tiles are
+// built: em.cu) and streams it through a CTA-wide shared-memory ring of 1-D bulk async copies
+// (cp.async.bulk + mbarrier complete_tx) of whole rows, up to a slot per copy, in row order;
+// the warp that is the last to finish with a slot issues the copy that takes it next from a
+// cursor every warp keeps.  The 16 warps work on the rows of one batch (segment) at a time.
 // A row is handled by L = 2^lg threads (8 or 16 lanes for rows of at most 64 / 128 double2
 // chunks -- four or two rows per warp step --, a warp, or 2..16 warps for more than 512
 // classes); thread t owns the chunks (t mod L) + L k (k < 8) of the rows (t div L) + (512 / L) i

@@ -338,7 +338,10 @@ def test_class_tiles_equal_fp64_rows(phylo17, n_extra, n_multi):
     tile_gather kernels).  The same non-negative terms enter every sum, regrouped; results must
     equal the fp64-row pass (MXB_EM_NO_PACK=1) to rounding with identical iteration counts,
     and the oracle.  Noise rows in the middle make batches whose columns are all distinct
-    (16 warps per row)."""
+    (16 warps per row).  With a few thousand rows over the whole genome nearly every batch is
+    wide and the pass's CTAs hold two segments of different widths whose row counts are not
+    multiples of the rows handled at a time: the case in which the warps of a wide row must
+    agree anew on the buffer of their partial dot products at every batch."""
     import ctypes
     import os
     from mixemt_b200._lib import lib, check, ptr
