@@ -220,6 +220,17 @@ int mxb_em_iterate(mxb_em *em, int64_t max_iter, double tol,
  * whole matrix several times). */
 int mxb_em_pass_bytes(const mxb_em *em, int64_t *bytes_per_pass, int64_t *layout);
 
+/* Host only (no device needed): the plan of the class-tile pass that mxb_em_create makes for
+ * n_batches batches of 128 rows (the last one shorter, n_rows in all) whose columns fall into
+ * n_cls[b] classes, on a GPU with num_sms SMs (csrc/tile_plan.h).  seg_out (nullable,
+ * seg_cap x 8 int32) receives per segment, in CTA order, {CTA, batch, first row inside the
+ * batch, rows, rows per copy, copies, log2 of the threads per row, row stride in doubles};
+ * errors = violated invariants (0).  For the CPU tests of the host logic; no counterpart in the
+ * reference, whose em_step (em.py:57-91) is three numpy expressions over the whole matrix. */
+int mxb_tile_plan(const int32_t *n_cls, int64_t n_batches, int64_t n_rows, int32_t num_sms,
+                  int32_t *seg_out, int64_t seg_cap, int32_t *n_cta, int32_t *n_seg,
+                  int32_t *n_slots, int32_t *slot_bytes, int32_t *errors);
+
 /* Exactly n_iter iterations without convergence test or host sync (bench);
  * elapsed_ms (nullable) = device time between first and last launch,
  * pass_ms (nullable) = summed device time from the first pass kernel of an iteration to

@@ -103,6 +103,7 @@ _PROTOS = {
     "mxb_em_iterate": (ctypes.c_int, [P, c_i64, c_dbl, ctypes.POINTER(c_i64),
                                       ctypes.POINTER(c_i32)]),
     "mxb_em_pass_bytes": (ctypes.c_int, [P, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "mxb_tile_plan": (ctypes.c_int, [P, c_i64, c_i64, c_i32, P, c_i64, P, P, P, P, P]),
     "mxb_em_iterate_fixed": (ctypes.c_int, [P, c_i64, ctypes.POINTER(ctypes.c_float),
                                             ctypes.POINTER(ctypes.c_float)]),
     "mxb_em_profile": (ctypes.c_int, [P, c_i64, ctypes.POINTER(ctypes.c_float)]),

@@ -41,6 +41,7 @@
 #include "common.cuh"
 #include "em_kernels.cuh"
 #include "em_tiles.cuh"
+#include "tile_plan.h"
 
 
 using namespace mxb;
@@ -419,137 +420,22 @@ static int em_pack_tiles(mxb_em *em) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return give_up(true, "classes");
 
-    // layout: threads per row, tile and class-vector offsets
-    std::vector<TileDesc> desc((size_t)nb);
+    // layout of the batches, ring geometry and plan of the pass (tile_plan.h)
+    std::vector<TileDesc> desc;
     int64_t v_cells = 0, p_cells = 0;
     int max_r_pad = 4;
-    for (int b = 0; b < nb; ++b) {
-        TileDesc &d = desc[(size_t)b];
-        d.row0 = b * kTileRows;
-        d.n_rows = (int)std::min<int64_t>(kTileRows, n - (int64_t)b * kTileRows);
-        d.n_cls = ncls[(size_t)b];
-        d.r_pad = (int)round_up(d.n_cls + 1, 4);      // + the weight column
-        // a row is handled by 2^lg threads, each with at most 8 double2 chunks of its class
-        // values (the weight behind them is read apart): up to 8192 classes with 16 warps
-        d.lg = 3;
-        while (((d.n_cls + 1) >> 1) > (8 << d.lg)) ++d.lg;
-        d.pad0 = d.pad1 = d.pad2 = 0;
-        d.v_off = v_cells;
-        d.p_off = p_cells;
-        v_cells += (int64_t)d.n_rows * d.r_pad;
-        p_cells += d.r_pad;
-        max_r_pad = std::max(max_r_pad, d.r_pad);
-    }
-    // The ring of the pass: three slots of 52 KB, fewer and longer ones if a row is longer than
-    // that (a copy costs every warp ~650 cycles: large copies, measured 24 to 78 KB).
-    const uint32_t slot_bytes = (uint32_t)round_up(std::max<int64_t>(kTileSlotBytes, (int64_t)max_r_pad * 8), 1024);
-    const int n_slots = std::min(kTileMaxSlots, kTileRingBytes / (int)slot_bytes);
-    if (n_slots < 2) return give_up(false, "rows too long for the ring");
-    // Plan of the pass.  The rows are dealt to the CTAs in order, every CTA one contiguous range;
-    // the part of a batch inside a CTA's range is a segment, cut at copy boundaries.  A CTA takes
-    // rows until either of its two clocks reaches the target T: its bytes at the SM's share of
-    // HBM (22 B per cycle) or its warps' time (cycle counters of the kernel at config 2: ~4200
-    // cycles per segment for the exchange at its end and the wait for the next class sums, ~500
-    // per copy for waiting, handing back and refilling, and a row step of 440 .. 1900 cycles for
-    // every 512 >> lg rows of a copy); the smallest T that needs no more CTAs than there are SMs
-    // is found by bisection.
-    std::vector<TileCta> ctas;
-    std::vector<TileSeg> segs;
-    std::vector<int> ent_batch;           // gather entries: (batch, offset of a U vector)
-    std::vector<int64_t> ent_off;
-    int64_t extra_cells = 0;              // U vectors of the second, third.. segment of a batch
-    int n_copy = 0;
-    {
-        static const double step_cycles[10] = {440, 440, 440, 440, 440, 600, 1000, 1300, 1626, 1900};
-        const double seg_cycles = 4200.0, copy_cycles = 500.0, bytes_per_cycle = 22.0;
-        auto rows_per_copy = [&](const TileDesc &d) {
-            const int per_step = d.lg < 5 ? 32 >> d.lg : 1;
-            return std::max(per_step, (int)(slot_bytes / (uint32_t)(d.r_pad * 8)) / per_step * per_step);
-        };
-        auto copy_cost = [&](const TileDesc &d, int rows) {      // warps' time for a copy of `rows`
-            return copy_cycles + ceil_div(rows, 512 >> d.lg) * step_cycles[d.lg];
-        };
-        const int max_cta = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, ceil_div(n, 32)));
-        // deal the rows for target T; with `emit` the segments are written down
-        auto deal = [&](double T, bool emit) {
-            int used_ctas = 0;
-            double warp_t = 0.0, mem_t = 0.0;
-            TileCta cur{(int)segs.size(), 0, 0, 0};
-            auto close_cta = [&]() {
-                if (warp_t > 0.0) {
-                    ++used_ctas;
-                    if (emit) ctas.push_back(cur);
-                }
-                cur.seg0 = (int)segs.size();
-                cur.n_segs = cur.n_copies = 0;
-                warp_t = mem_t = 0.0;
-            };
-            for (int b = 0; b < nb; ++b) {
-                const TileDesc &d = desc[(size_t)b];
-                const int fit = rows_per_copy(d);
-                const double row_mem = (double)d.r_pad * 8 / bytes_per_cycle;
-                int r = 0, seg_no = 0;
-                while (r < d.n_rows) {
-                    const int left = d.n_rows - r;
-                    // whole copies of this batch that still fit under T on both clocks
-                    int take = 0;
-                    double w = warp_t + seg_cycles, m = mem_t;
-                    while (take < left) {
-                        const int rows = std::min(fit, left - take);
-                        if (std::max(w + copy_cost(d, rows), m + rows * row_mem) > T) break;
-                        w += copy_cost(d, rows);
-                        m += rows * row_mem;
-                        take += rows;
-                    }
-                    if (take < left && left - take < 8) {         // no crumbs for the next CTA
-                        w += copy_cost(d, left - take);
-                        m += (left - take) * row_mem;
-                        take = left;
-                    }
-                    if (take == 0) {
-                        if (warp_t > 0.0) { close_cta(); continue; }
-                        take = std::min(fit, left);               // a CTA takes at least one copy
-                        w += copy_cost(d, take);
-                        m += take * row_mem;
-                    }
-                    if (emit) {
-                        TileSeg sg;
-                        memset(&sg, 0, sizeof(sg));
-                        sg.p_off = d.p_off;
-                        sg.u_dst = seg_no == 0 ? d.p_off : p_cells + extra_cells;
-                        if (seg_no > 0) extra_cells += d.r_pad;
-                        sg.r_pad = d.r_pad;
-                        sg.n_cls = d.n_cls;
-                        sg.lg = d.lg;
-                        sg.n_rows = take;
-                        sg.batch = b;
-                        sg.fit = fit;
-                        sg.n_copies = (int)ceil_div(take, fit);
-                        sg.v_off = d.v_off + (int64_t)r * d.r_pad;
-                        ent_batch.push_back(b);
-                        ent_off.push_back(sg.u_dst);
-                        cur.n_copies += sg.n_copies;
-                        n_copy += sg.n_copies;
-                        segs.push_back(sg);
-                        ++cur.n_segs;
-                    }
-                    warp_t = w;
-                    mem_t = m;
-                    r += take;
-                    ++seg_no;
-                }
-            }
-            close_cta();
-            return used_ctas;
-        };
-        double lo = 0.0, hi = 1.0;
-        while (deal(hi, false) > max_cta) hi *= 2.0;
-        for (int it = 0; it < 30; ++it) {
-            const double mid = 0.5 * (lo + hi);
-            if (deal(mid, false) > max_cta) lo = mid; else hi = mid;
-        }
-        deal(hi, true);
-    }
+    tile_layout(ncls.data(), nb, n, desc, v_cells, p_cells, max_r_pad);
+    uint32_t slot_bytes = 0;
+    int n_slots = 0;
+    if (!tile_ring(max_r_pad, slot_bytes, n_slots)) return give_up(false, "rows too long for the ring");
+    TilePlanOut plan;
+    tile_plan(desc, n, ctx->num_sms, slot_bytes, p_cells, plan);
+    const std::vector<TileCta> &ctas = plan.ctas;
+    const std::vector<TileSeg> &segs = plan.segs;
+    const std::vector<int> &ent_batch = plan.ent_batch;
+    const std::vector<int64_t> &ent_off = plan.ent_off;
+    const int64_t extra_cells = plan.extra_cells;
+    const int n_copy = plan.n_copy;
     const int n_cta = (int)ctas.size(), n_seg = (int)segs.size();
     const int n_ent = (int)ent_batch.size();
     const int64_t u_cells = p_cells + extra_cells;
@@ -557,28 +443,7 @@ static int em_pack_tiles(mxb_em *em) {
                               ((double)p_cells + (double)u_cells) * 8 * 2;
     const double fp64_bytes = (double)n * (double)em->ld * 8;
     if (verbose) {
-        {   // invariants of the plan
-            std::vector<int> rows_of((size_t)nb, 0);
-            int errs = 0, next_seg = 0, copies_sum = 0;
-            for (const TileCta &c : ctas) {
-                if (c.seg0 != next_seg) ++errs;
-                int cc = 0;
-                for (int q = 0; q < c.n_segs; ++q) {
-                    const TileSeg &g = segs[(size_t)(c.seg0 + q)];
-                    const TileDesc &d = desc[(size_t)g.batch];
-                    if (g.v_off != d.v_off + (int64_t)rows_of[(size_t)g.batch] * d.r_pad) ++errs;
-                    rows_of[(size_t)g.batch] += g.n_rows;
-                    if (g.n_copies != (int)ceil_div(g.n_rows, g.fit)) ++errs;
-                    cc += g.n_copies;
-                }
-                if (cc != c.n_copies) ++errs;
-                copies_sum += cc;
-                next_seg += c.n_segs;
-            }
-            for (int b = 0; b < nb; ++b) if (rows_of[(size_t)b] != desc[(size_t)b].n_rows) ++errs;
-            fprintf(stderr, "[mxb tiles] plan check: %d errors, %d segs in ctas of %d, copies %d / %d\n", errs,
-                    next_seg, (int)segs.size(), copies_sum, n_copy);
-        }
+        fprintf(stderr, "[mxb tiles] plan check: %d errors\n", tile_plan_check(desc, plan));
         int64_t c_sum = 0, c_max = 0, wide = 0;
         for (int b = 0; b < nb; ++b) {
             c_sum += desc[(size_t)b].n_cls;
@@ -1029,6 +894,49 @@ extern "C" int mxb_debug_tile_trace(unsigned long long *out, size_t n_words) {
     return (int)cudaMemcpyFromSymbol(out, mxb::g_tile_trace, std::min(n_words * 8, sizeof(mxb::g_tile_trace)));
 }
 #endif
+
+int mxb_tile_plan(const int32_t *n_cls, int64_t n_batches, int64_t n_rows, int32_t num_sms,
+                  int32_t *seg_out, int64_t seg_cap, int32_t *n_cta, int32_t *n_seg,
+                  int32_t *n_slots_out, int32_t *slot_bytes_out, int32_t *errors) {
+    MXB_REQUIRE(n_cls != nullptr && n_batches > 0 && n_rows > (n_batches - 1) * kTileRows &&
+                n_rows <= n_batches * kTileRows && num_sms > 0, "bad arguments");
+    for (int64_t b = 0; b < n_batches; ++b)
+        MXB_REQUIRE(n_cls[b] >= 1 && n_cls[b] <= kTileMaxCols, "class counts must be in 1..8192");
+    std::vector<TileDesc> desc;
+    int64_t v_cells = 0, p_cells = 0;
+    int max_r_pad = 4;
+    tile_layout(n_cls, (int)n_batches, n_rows, desc, v_cells, p_cells, max_r_pad);
+    uint32_t slot_bytes = 0;
+    int n_slots = 0;
+    const bool ring_ok = tile_ring(max_r_pad, slot_bytes, n_slots);
+    if (n_slots_out) *n_slots_out = n_slots;
+    if (slot_bytes_out) *slot_bytes_out = (int32_t)slot_bytes;
+    MXB_REQUIRE(ring_ok, "rows too long for the ring");
+    TilePlanOut plan;
+    tile_plan(desc, n_rows, num_sms, slot_bytes, p_cells, plan);
+    if (n_cta) *n_cta = (int32_t)plan.ctas.size();
+    if (n_seg) *n_seg = (int32_t)plan.segs.size();
+    if (errors) *errors = tile_plan_check(desc, plan);
+    if (seg_out) {
+        int64_t k = 0;
+        for (size_t c = 0; c < plan.ctas.size(); ++c) {
+            for (int q = 0; q < plan.ctas[c].n_segs && k < seg_cap; ++q, ++k) {
+                const TileSeg &g = plan.segs[(size_t)(plan.ctas[c].seg0 + q)];
+                const TileDesc &d = desc[(size_t)g.batch];
+                int32_t *o = seg_out + 8 * k;
+                o[0] = (int32_t)c;
+                o[1] = g.batch;
+                o[2] = (int32_t)((g.v_off - d.v_off) / d.r_pad);     // first row inside the batch
+                o[3] = g.n_rows;
+                o[4] = g.fit;
+                o[5] = g.n_copies;
+                o[6] = g.lg;
+                o[7] = g.r_pad;
+            }
+        }
+    }
+    return MXB_OK;
+}
 
 int mxb_em_profile(mxb_em *em, int64_t n_iter, float *ms_out) {
     MXB_REQUIRE(em != nullptr && ms_out != nullptr && n_iter >= 1 && n_iter <= 10000, "bad argument");
