@@ -357,6 +357,16 @@ def run_b200(opts):
     def sum_over_ranks(x):
         return reduce_ranks(x, dist.ReduceOp.SUM if world > 1 else None)
 
+    def guarded(name, fn, *fargs):
+        """An optional leg must not take the bench line down: its error is reported under its
+        key.  (The kernels of the peer exchange time out instead of hanging, so a rank that
+        fails alone costs the others a bounded wait.)"""
+        try:
+            return fn(*fargs)
+        except Exception as exc:
+            sys.stderr.write("[bench] rank %d: leg %s failed: %r\n" % (rank, name, exc))
+            return {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     def new_session(dmat, weights, sharded):
         sess = ctypes.c_void_p()
         check(lib.mxb_em_create(ctx.handle, dmat.handle, ptr(weights), 1 if sharded else 0,
@@ -498,16 +508,17 @@ def run_b200(opts):
     # ---- multi-GPU legs ------------------------------------------------------------------
     parity = strong = config3 = None
     if world > 1:
-        parity = parity_leg(ctx, tables, phylo, haps, rank, world, barrier)
+        parity = guarded("parity", parity_leg, ctx, tables, phylo, haps, rank, world, barrier)
         if not opts.no_strong and opts.rows == 0:
-            strong = strong_leg(ctx, tables, phylo, haps, opts, rank, world, barrier,
-                                max_over_ranks, lnp0)
+            strong = guarded("strong_scaling", strong_leg, ctx, tables, phylo, haps, opts, rank,
+                             world, barrier, max_over_ranks, lnp0)
         if (world == 8 or opts.config3) and opts.rows == 0 and not opts.no_config3:
             dmat.free()
             dmat = None
             ctx.trim()
-            config3 = config3_leg(ctx, tables, phylo, haps, opts, rank, world, barrier,
-                                  max_over_ranks, sum_over_ranks, peak)
+            config3 = guarded("config3", config3_leg, ctx, tables, phylo, haps, opts, rank, world,
+                              barrier, max_over_ranks, sum_over_ranks, peak)
+            ctx.trim()
             _, _, dmat, _ = build_matrix_from_csr(tables, csr, ctx=ctx, want_host=False,
                                                   keep_device=True)
 
@@ -515,8 +526,7 @@ def run_b200(opts):
     # n_multi random-init restarts (default 100, fixed seed) on the config-2 matrix; under
     # torchrun the matrix of rank 0's seed is replicated, the restarts are dealt in contiguous
     # blocks (args.b200_shard = "restarts") and combined like em.py:145-163 combines them.
-    sweep = None
-    if not opts.no_sweep and opts.rows == 0 and opts.restarts > 0:
+    def sweep_leg():
         n_multi = opts.restarts
         inits = np.log(np.random.RandomState(3).dirichlet([1.0] * h, size=n_multi))
         sargs = argparse.Namespace(verbose=False, init_alpha=1.0, tolerance=1e-4, max_iter=10000,
@@ -537,26 +547,30 @@ def run_b200(opts):
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         iters_total = sum_over_ranks(float(sum(s_info["iterations"])))
-        sweep = {"n_multi": n_multi, "seconds": dt, "restarts_per_s": n_multi / dt,
-                 "iterations_total": iters_total,
-                 "cell_updates_per_s": float(smat.shape[0]) * h * iters_total / dt,
-                 "props_sum": float(s_props.sum()),
-                 "top_haplogroups": [[haps[i], float(s_props[i])]
-                                     for i in np.argsort(s_props)[::-1][:3]],
-                 "call": "run_em(config-2 matrix, n_multi=%d, tolerance 1e-4, fixed seed) to "
-                         "convergence, read matrices folded on the device" % n_multi,
-                 "parallelism": ("matrix replicated, restarts in contiguous blocks over %d GPUs, "
-                                 "read matrices combined by an all-to-all of row shards + local "
-                                 "logaddexp fold" % world) if world > 1 else "single GPU"}
+        out = {"n_multi": n_multi, "seconds": dt, "restarts_per_s": n_multi / dt,
+               "iterations_total": iters_total,
+               "cell_updates_per_s": float(smat.shape[0]) * h * iters_total / dt,
+               "props_sum": float(s_props.sum()),
+               "top_haplogroups": [[haps[i], float(s_props[i])]
+                                   for i in np.argsort(s_props)[::-1][:3]],
+               "call": "run_em(config-2 matrix, n_multi=%d, tolerance 1e-4, fixed seed) to "
+                       "convergence, read matrices folded on the device" % n_multi,
+               "parallelism": ("matrix replicated, restarts in contiguous blocks over %d GPUs, "
+                               "read matrices combined by an all-to-all of row shards + local "
+                               "logaddexp fold" % world) if world > 1 else "single GPU"}
         if smat is not dmat:
             smat.free()
+        return out
+
+    sweep = None
+    if not opts.no_sweep and opts.rows == 0 and opts.restarts > 0:
+        sweep = guarded("restart_sweep", sweep_leg)
 
     # ---- e2e: the drop-in call with host buffers -----------------------------------------
     # Input: an ordinary (pageable) numpy array, like a caller of the reference API holds.
     # Result: pooled pinned host memory, reserved before the untimed warm-up call (what a
     # service does once; MIXEMT_B200_PINNED / reserve_pinned).
-    e2e = None
-    if not opts.no_e2e:
+    def e2e_leg():
         host = np.empty((n, h), dtype=np.float64)      # pageable
         dmat.to_host(out=host)
         if not opts.pageable_result:
@@ -587,7 +601,7 @@ def run_b200(opts):
         found = re.findall(r"Converged! \((\d+)\)", buf.getvalue())
         iters = int(found[0]) if found else args.max_iter
         top = np.argsort(props)[::-1][:3]
-        e2e = {"value": cells_total * iters / e2e_s, "unit": UNIT,
+        out = {"value": cells_total * iters / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": (host.nbytes + weights.nbytes + 8 * h) / iters,
                "d2h_bytes_per_step": (read_mix.nbytes + 8 * h) / iters,
                "call": "mixemt_b200.run_em(pageable host ndarray, weights, args) to convergence "
@@ -604,11 +618,15 @@ def run_b200(opts):
                "top_haplogroups": [[haps[i], float(props[i])] for i in top],
                "clocks": clocks_e2e.summary()}
         del host, read_mix
+        return out
+
+    e2e = None
+    if not opts.no_e2e:
+        e2e = guarded("e2e", e2e_leg)
     dmat.free()
 
     # ---- e2e of kernel 1: the drop-in build_em_matrix(signature strings) -> host ndarray ----
-    build_e2e = None
-    if not opts.no_e2e and world == 1 and opts.rows == 0:
+    def build_e2e_leg():
         _, _, smix = load_workload(opts.fragments, opts.seed, strings=True)
         bargs = argparse.Namespace(verbose=False)
         mixemt_b200.build_em_matrix(phylo.refseq, phylo, smix.signatures[:2000], haps, bargs)
@@ -617,14 +635,19 @@ def run_b200(opts):
         mat = mixemt_b200.build_em_matrix(phylo.refseq, phylo, smix.signatures, haps, bargs)
         barrier()
         dt = time.perf_counter() - t0
-        build_e2e = {"seconds": dt, "cells_per_s": mat.size / dt, "d2h_bytes": mat.nbytes,
-                     "result_memory": "pooled pinned block" if mat.base is not None
-                     else "pageable numpy array",
-                     "call": "mixemt_b200.build_em_matrix(refseq, phylo, %d signature strings, "
-                             "%d haplogroups, args) -> host ndarray: table packing, string "
-                             "parsing, kernel 1 and the %.2f GB device->host copy inside"
-                             % (len(smix.signatures), h, mat.nbytes / 1e9)}
+        out = {"seconds": dt, "cells_per_s": mat.size / dt, "d2h_bytes": mat.nbytes,
+               "result_memory": "pooled pinned block" if mat.base is not None
+               else "pageable numpy array",
+               "call": "mixemt_b200.build_em_matrix(refseq, phylo, %d signature strings, "
+                       "%d haplogroups, args) -> host ndarray: table packing, string "
+                       "parsing, kernel 1 and the %.2f GB device->host copy inside"
+                       % (len(smix.signatures), h, mat.nbytes / 1e9)}
         del mat
+        return out
+
+    build_e2e = None
+    if not opts.no_e2e and world == 1 and opts.rows == 0:
+        build_e2e = guarded("build.e2e", build_e2e_leg)
 
     cpu = None
     if rank == 0 and world == 1 and not opts.no_cpu:
@@ -759,25 +782,28 @@ def config3_leg(ctx, tables, phylo, haps, opts, rank, world, barrier, max_over_r
                                                  keep_device=True)
     wts = mix.weights.astype(np.float64)
     sess = ctypes.c_void_p()
-    t0 = time.perf_counter()
-    check(lib.mxb_em_create(ctx.handle, dmat.handle, ptr(wts), 1, ctypes.byref(sess)))
-    ctx.synchronize()
-    setup_s = time.perf_counter() - t0
-    nb, flag = ctypes.c_int64(), ctypes.c_int64()
-    check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nb), ctypes.byref(flag)))
-    lnp0 = np.log(np.random.RandomState(1).dirichlet([1.0] * h))
-    check(lib.mxb_em_set_lnprops(sess, ptr(lnp0)))
-    el = ctypes.c_float()
-    check(lib.mxb_em_iterate_fixed(sess, 3, ctypes.byref(el), None))
-    barrier()
-    steps = min(opts.steps, 50)
-    check(lib.mxb_em_iterate_fixed(sess, steps, ctypes.byref(el), None))
-    barrier()
-    ms = max_over_ranks(el.value) / steps
-    free_b, total_b = torch.cuda.mem_get_info()
-    lib.mxb_em_destroy(sess)
-    dmat.free()
-    ctx.trim()
+    try:
+        t0 = time.perf_counter()
+        check(lib.mxb_em_create(ctx.handle, dmat.handle, ptr(wts), 1, ctypes.byref(sess)))
+        ctx.synchronize()
+        setup_s = time.perf_counter() - t0
+        nb, flag = ctypes.c_int64(), ctypes.c_int64()
+        check(lib.mxb_em_pass_bytes(sess, ctypes.byref(nb), ctypes.byref(flag)))
+        lnp0 = np.log(np.random.RandomState(1).dirichlet([1.0] * h))
+        check(lib.mxb_em_set_lnprops(sess, ptr(lnp0)))
+        el = ctypes.c_float()
+        check(lib.mxb_em_iterate_fixed(sess, 3, ctypes.byref(el), None))
+        barrier()
+        steps = min(opts.steps, 50)
+        check(lib.mxb_em_iterate_fixed(sess, steps, ctypes.byref(el), None))
+        barrier()
+        ms = max_over_ranks(el.value) / steps
+        free_b, total_b = torch.cuda.mem_get_info()
+    finally:                    # a shard is 54 GB: give it back also when the leg fails
+        if sess:
+            lib.mxb_em_destroy(sess)
+        dmat.free()
+        ctx.trim()
     ld = ((h + 15) // 16) * 16
     cells = sum_over_ranks(float(n) * h)
     contract = float(n) * ld * 8
