@@ -32,7 +32,7 @@ def main():
         t.append(time.perf_counter())
         n = len(reads)
         row_ptr = np.zeros(n + 1, dtype=np.int64)
-        lib.mxb_sig_count(ctypes.c_char_p(buf), ptr(offsets), n, ptr(row_ptr))
+        lib.mxb_sig_count(buf, ptr(offsets), n, ptr(row_ptr))
         t.append(time.perf_counter())
         csr, err = preprocess.parse_signatures(reads, hv)
         t.append(time.perf_counter())
