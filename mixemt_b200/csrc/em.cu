@@ -1056,26 +1056,31 @@ namespace mxb {
 // keeps going.  The host polls the control blocks two chunks behind the device, exactly
 // like mxb_em_iterate does for one restart.  Results are combined as the reference
 // combines them: final log-proportions summed in restart order (em.py:145-155), read
-// matrices folded with logaddexp (em.py:156; in completion order).
+// matrices folded with logaddexp in restart order (em.py:156): a restart that finishes before
+// an earlier one parks the proportions its read matrix is formed from until its turn.
 static int run_em_batched(mxb_em *em, const double *init_lnprops, int32_t n_multi,
                           int64_t max_iter, double tol, bool raw, mxb_matrix *mix,
                           double *props_out, int64_t *iters_out, int32_t *converged_out) {
     mxb_ctx *ctx = em->ctx;
     cudaStream_t s = ctx->stream;
     const int64_t h = em->n_cols, ld = em->ld;
-    // device: [inits n_multi x h][final log-proportions n_multi x h]; the finals are read
-    // back in one copy at the end (no pinned host buffer, no blocking copy mid-run)
+    // device: [inits n_multi x h][final log-proportions n_multi x h][the proportions before
+    // the last step n_multi x h]; the finals are read back in one copy at the end (no pinned
+    // host buffer, no blocking copy mid-run)
     const size_t vec_bytes = (size_t)n_multi * h * sizeof(double);
     double *d_inits = nullptr;
-    if (dev_alloc(ctx, (void **)&d_inits, 2 * vec_bytes) != cudaSuccess) {
-        set_error("run_em: device allocation of %zu bytes failed", 2 * vec_bytes);
+    if (dev_alloc(ctx, (void **)&d_inits, 3 * vec_bytes) != cudaSuccess) {
+        set_error("run_em: device allocation of %zu bytes failed", 3 * vec_bytes);
         cudaGetLastError();
         return MXB_ERR_NOMEM;
     }
     double *d_fin = d_inits + (size_t)n_multi * h;
+    double *d_prev = d_fin + (size_t)n_multi * h;
     std::vector<double> h_fin;
+    std::vector<char> done_restart;       // finished, read matrix not folded yet (or folded)
     try {
         h_fin.resize((size_t)n_multi * h);
+        done_restart.assign((size_t)n_multi, 0);
     } catch (const std::bad_alloc &) {
         dev_free(ctx, d_inits);
         set_error("run_em: out of host memory");
@@ -1145,13 +1150,25 @@ static int run_em_batched(mxb_em *em, const double *init_lnprops, int32_t n_mult
                 }
                 ++finished;
                 if (mix) {
-                    const bool last = finished == n_multi;
-                    const double sub = (last && n_multi > 1 && !raw) ? log((double)n_multi) : 0.0;
-                    read_mix_kernel<<<grid_mix, kMixThreads, 0, s>>>(
-                        em->mat->data, em->n_rows, em->n_cols, em->lnp[st.cur] + sl * ld, mix->data,
-                        folded == 0 ? 0 : 1, sub);
-                    ctx->launches++;
-                    ++folded;
+                    // the read matrix comes from the proportions before the last step (SURVEY
+                    // F5); the slot is reused, so they are kept until the restarts before this
+                    // one have been folded
+                    if (cudaMemcpyAsync(d_prev + (size_t)idx * h, em->lnp[st.cur] + sl * ld,
+                                        h * sizeof(double), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+                        set_error("run_em: result copy failed");
+                        rc = MXB_ERR_CUDA;
+                        break;
+                    }
+                    done_restart[(size_t)idx] = 1;
+                    while (folded < n_multi && done_restart[(size_t)folded]) {
+                        const bool last = folded == n_multi - 1;
+                        const double sub = (last && n_multi > 1 && !raw) ? log((double)n_multi) : 0.0;
+                        read_mix_kernel<<<grid_mix, kMixThreads, 0, s>>>(
+                            em->mat->data, em->n_rows, em->n_cols, d_prev + (size_t)folded * h,
+                            mix->data, folded == 0 ? 0 : 1, sub);
+                        ctx->launches++;
+                        ++folded;
+                    }
                 }
                 slot_restart[sl] = -1;
                 if (next < n_multi) start_slot(sl);
