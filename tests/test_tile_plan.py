@@ -121,6 +121,23 @@ def test_config2_like_plan_is_balanced():
     assert len(seg) <= 1083 + 148
 
 
+@pytest.mark.parametrize("median,min_bytes", [(135, 0), (500, 2 ** 32)])
+def test_config3_shard_plan(median, min_bytes):
+    """A config-3 shard (1.25 M rows = 9766 batches per GPU, BASELINE.json configs[2]; measured
+    tiles: ~1.8 GB) and the same rows with four times as many classes per batch (tiles beyond
+    2^32 bytes: offsets are 64-bit): the plan covers every row once with 148 balanced CTAs."""
+    rs = np.random.RandomState(3)
+    n_rows = 1250000
+    nb = (n_rows + ROWS - 1) // ROWS
+    n_cls = np.minimum(5408, np.maximum(20, rs.lognormal(np.log(median), 0.9, size=nb))).astype(int)
+    seg, n_cta, slot_bytes = check_plan(n_cls, n_rows)
+    assert n_cta == 148 and len(seg) <= nb + 148
+    tile_bytes = sum(rows * r_pad * 8 for _, _, _, rows, _, _, _, r_pad in seg.tolist())
+    assert tile_bytes > min_bytes
+    t = modelled_cycles(seg, slot_bytes)
+    assert t.max() < 1.02 * t.mean(), (t.max(), t.mean())
+
+
 def test_tiny_and_extreme_shapes():
     check_plan([1], 1)
     check_plan([8192], 128)                  # 64 KB rows: two slots of one row
