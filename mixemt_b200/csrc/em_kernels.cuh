@@ -920,7 +920,6 @@ read_mix_kernel(const double *__restrict__ m, int64_t n_rows, int64_t n_cols,
     }
 }
 
-// Cross-rank fold helpers: m <- exp(m - mx) ; m <- mx + log(m) - sub_log.
 // ---- one EM iteration in log space (rescue path) -------------------------------------
 // The linear-space pass needs s_i = sum_j L_ij pi_j > 0.  When every haplotype that still
 // has mass explains a row more than ~700 log units worse than the row's best one, s_i
