@@ -182,8 +182,9 @@ int mxb_reduce_reads(const int64_t *frag_ptr, const int32_t *pos, const uint8_t 
                        (size_t)k * sizeof(int32_t));
                 memcpy(ss->base.data() + ss->row_ptr[(size_t)r], base + frag_ptr[f], (size_t)k);
             }
-            memcpy(ss->strings.data() + ss->str_off[(size_t)r], raw.data() + raw_off[(size_t)u],
-                   (size_t)raw_len[(size_t)u]);
+            if (raw_len[(size_t)u])
+                memcpy(ss->strings.data() + ss->str_off[(size_t)r], raw.data() + raw_off[(size_t)u],
+                       (size_t)raw_len[(size_t)u]);
             for (int64_t i = starts[u]; i < starts[u + 1]; ++i) {
                 ss->sig_of_frag[(size_t)order[i]] = r;
                 ss->frag_order[(size_t)(frag_off[(size_t)r] + (i - starts[u]))] = order[i];
