@@ -171,3 +171,40 @@ def test_consumers_live_reference():
     assert dict(ref) == got
     a, b = ref_pre.reduce_em_matrix(mix, haps, contribs), oracle_np.reduce_em_matrix(mix, haps, contribs)
     assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference not mounted")
+def test_em_step_fuzz_against_live_reference():
+    """The oracles' em_step against the reference's own (em.py:57-91, scipy logsumexp) on small
+    random inputs with the edge values the domain has: -inf cells, ties among the row and
+    column maxima, a row that fits no haplotype (NaN, like the reference), zero weights,
+    components with zero proportion.  numpy restatement: bit-identical, NaN for NaN; C port:
+    the same non-finite pattern and within 1e-12."""
+    import warnings
+    _, _, ref_em = refload.load()
+    rs = np.random.RandomState(0)
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        for it in range(200):
+            n, h = rs.randint(1, 14), rs.randint(1, 10)
+            mat = -rs.gamma(2.0, 4.0, size=(n, h))
+            mode = it % 5
+            if mode >= 1:
+                mat[rs.rand(n, h) < 0.2] = -np.inf
+            if mode >= 2:
+                mat = np.round(mat)
+            if mode == 3:
+                mat[rs.randint(n)] = -np.inf
+            wts = rs.randint(0 if mode >= 2 else 1, 50, size=n)
+            lp = np.log(rs.dirichlet([1.0] * h))
+            if mode == 4:
+                lp[rs.rand(h) < 0.3] = -np.inf
+            z_ref, p_ref = ref_em.em_step(mat, wts, lp, np.empty_like(mat))
+            z_np, p_np = oracle_np.em_step(mat, wts, lp)
+            assert np.array_equal(z_np, z_ref, equal_nan=True), it
+            assert np.array_equal(p_np, p_ref, equal_nan=True), it
+            z_c, p_c = oracle_c.em_step(mat, wts.astype(np.float64), lp)
+            for got, want in ((z_c, z_ref), (p_c, p_ref)):
+                fin = np.isfinite(want)
+                assert np.array_equal(got[~fin], want[~fin], equal_nan=True), it
+                assert not fin.any() or np.abs(got[fin] - want[fin]).max() < 1e-12, it
