@@ -7,7 +7,6 @@ the C-ABI of include/mixemt_b200.h.
 """
 import ctypes
 import math
-import os
 import sys
 
 import numpy as np
