@@ -6,6 +6,7 @@ N x H x K Python loop is replaced by the bitset kernel in csrc/build.cu behind
 the C-ABI of include/mixemt_b200.h.
 """
 import ctypes
+import itertools
 import math
 import sys
 
@@ -116,18 +117,42 @@ class HapVarBaseMatrix(object):
                 self.sym2code[raw[0]] = i
         self.ref_code = np.array([code_of[self.refseq[p]] for p in positions], dtype=np.uint8)
 
-        ptrs = np.zeros(len(hap_tables) + 1, dtype=np.int64)
-        m_pos, m_code = [], []
-        for j, table in enumerate(hap_tables):
-            for pos, der in table.items():
-                i = pos_index.get(pos)
-                if i is not None:  # markers off the variant table are dead data (F8)
-                    m_pos.append(i)
-                    m_code.append(code_of[der])
-            ptrs[j + 1] = len(m_pos)
-        self.marker_ptr = ptrs
-        self.marker_pos_idx = np.asarray(m_pos, dtype=np.int32)
-        self.marker_code = np.asarray(m_code, dtype=np.uint8)
+        # markers as CSR over the haplotype columns, in the tables' own order; markers off the
+        # variant table are dead data (F8).  263 826 entries at Build 17: flattened and looked up
+        # with numpy (the per-entry Python loop below remains for exotic tables)
+        n_tab = len(hap_tables)
+        lens = np.fromiter(map(len, hap_tables), dtype=np.int64, count=n_tab)
+        total = int(lens.sum())
+        all_pos = np.fromiter(itertools.chain.from_iterable(hap_tables), dtype=np.int64, count=total)
+        all_der = "".join(itertools.chain.from_iterable(map(dict.values, hap_tables)))
+        if len(all_der) == total and all_der.isascii() and (total == 0 or all_pos.min() >= 0):
+            inside = all_pos < max_pos
+            idx = np.full(total, -1, dtype=np.int32)
+            idx[inside] = self.pos2idx[all_pos[inside]]
+            keep = idx >= 0
+            code_lut = np.full(256, 255, dtype=np.uint8)
+            for sym, i in code_of.items():
+                if len(sym) == 1 and sym.isascii():
+                    code_lut[ord(sym)] = i
+            codes = code_lut[np.frombuffer(all_der.encode("ascii"), dtype=np.uint8)]
+            kept_before = np.concatenate(([0], np.cumsum(keep, dtype=np.int64)))
+            bounds = np.concatenate(([0], np.cumsum(lens)))
+            self.marker_ptr = kept_before[bounds]
+            self.marker_pos_idx = idx[keep]
+            self.marker_code = codes[keep]
+        else:
+            ptrs = np.zeros(n_tab + 1, dtype=np.int64)
+            m_pos, m_code = [], []
+            for j, table in enumerate(hap_tables):
+                for pos, der in table.items():
+                    i = pos_index.get(pos)
+                    if i is not None:
+                        m_pos.append(i)
+                        m_code.append(code_of[der])
+                ptrs[j + 1] = len(m_pos)
+            self.marker_ptr = ptrs
+            self.marker_pos_idx = np.asarray(m_pos, dtype=np.int32)
+            self.marker_code = np.asarray(m_code, dtype=np.uint8)
         self.n_pos, self.n_hap, self.n_sym = n_pos, len(hap_tables), max(1, len(symbols))
         return self
 

@@ -220,3 +220,29 @@ def test_table_packing_fuzz_against_live_reference():
         got, counts = oracle_c.build_matrix(tables, csr)
         assert np.array_equal(got, want), it
         assert (counts >= 0).all() and (counts <= np.diff(csr.row_ptr)[:, None]).all()
+
+
+@pytest.mark.parametrize("exotic", [None, "A0G", "A3é"])
+def test_marker_csr_both_packing_paths(toy_phylo, exotic):
+    """pack() flattens the marker tables with numpy; a table with a negative position ('A0G')
+    or a non-ASCII derived base takes the per-entry loop.  Both must give the CSR a plain
+    Python walk over ``markers`` gives."""
+    import types
+    hap_var = {h: list(v) for h, v in toy_phylo.hap_var.items()}
+    if exotic:
+        hap_var[sorted(hap_var)[1]].append(exotic)
+    phylo = types.SimpleNamespace(variants=toy_phylo.variants, hap_var=hap_var,
+                                  refseq=toy_phylo.refseq)
+    haps = sorted(hap_var)
+    t = HapVarBaseMatrix(toy_phylo.refseq, phylo, haps).pack()
+    pos_index = {int(p): i for i, p in enumerate(t.positions)}
+    ptr, pos, code = [0], [], []
+    for hap in haps:
+        for p, der in t.markers[hap].items():
+            if p in pos_index:
+                pos.append(pos_index[p])
+                code.append(t.symbols.index(der))
+        ptr.append(len(pos))
+    assert t.marker_ptr.tolist() == ptr and t.marker_ptr.dtype == np.int64
+    assert t.marker_pos_idx.tolist() == pos and t.marker_pos_idx.dtype == np.int32
+    assert t.marker_code.tolist() == code and t.marker_code.dtype == np.uint8
