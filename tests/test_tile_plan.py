@@ -54,8 +54,15 @@ def check_plan(n_cls, n_rows, num_sms=148):
         assert r_pad == (int(n_cls[b]) + 1 + 3) // 4 * 4
         per_step = 32 >> lg if lg < 5 else 1
         assert fit % per_step == 0 and fit >= per_step
-        assert fit * r_pad * 8 <= slot_bytes or fit == per_step
+        assert fit * r_pad * 8 <= slot_bytes, "a copy must fit into a ring slot"
         assert copies == math.ceil(rows / fit)
+        # what the kernel's bulk copies and its exchange scratch rely on: 16-byte aligned
+        # copies of at most 2^20 - 1 bytes, and the row slices' shares fit the 64 KB scratch
+        assert (r_pad * 8) % 32 == 0 and fit * r_pad * 8 < 2 ** 20
+        chunks = (int(n_cls[b]) + 1) >> 1
+        n_slices = (512 >> lg) if lg >= 5 else 16
+        assert n_slices * chunks * 16 <= 64 * 1024
+        assert chunks <= 8 << lg                 # eight double2 chunks per thread
         # a segment ends at a copy boundary or at the end of its batch (or takes the crumbs)
         assert rows % fit == 0 or r0 + rows == batch_rows
     assert pos == n_rows
